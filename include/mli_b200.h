@@ -1,0 +1,258 @@
+/*
+ * mli_b200.h -- C ABI of libmli_b200.so: the B200 (sm_100a) implementation of MLI-NeRF's per-ray render
+ * hot path (projects/NeuralLumen, reference citations relative to /root/reference/).
+ *
+ * The reference has no FFI of its own: its only native boundary is
+ *   tinycudann.Encoding(3, {"otype":"HashGrid",...})      projects/neuralangelo/utils/modules.py:42-50,84-86
+ * and everything else on the path is eager torch.  This header is the boundary a maintainer binds instead
+ * (ctypes stub shown in INTEGRATION.md); each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Every pointer is a DEVICE pointer unless named host_*.
+ *   - the library never allocates or frees device memory and never takes ownership; the caller sizes
+ *     workspaces with the *_bytes() helpers.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); stream-ordered, re-entrant
+ *     per process, not thread-safe across host threads that share a device.
+ *   - return 0 on success, negative MLI_E* on failure; mli_last_error() gives the thread-local message.
+ *   - row-major everywhere.  "M" = number of sample points, "R" = number of rays, "N" = samples per ray.
+ *   - there is NO CPU fallback: every entry point fails with MLI_ENODEV if no sm_100 device is current.
+ */
+#ifndef MLI_B200_H
+#define MLI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLI_ABI_VERSION 1
+
+enum {
+  MLI_OK = 0,
+  MLI_EINVAL = -1,   /* bad argument (shape, alignment, unknown mode) -> ValueError / NotImplementedError */
+  MLI_ECUDA = -2,    /* CUDA runtime error (message has cudaGetErrorString) */
+  MLI_ENODEV = -3,   /* no sm_100-class device current */
+  MLI_ENOTSUP = -4   /* valid in the reference but not built (e.g. analytical gradient mode) */
+};
+
+const char* mli_last_error(void);
+int mli_abi_version(void);
+/* 1 if the current device is compute capability 10.x, else 0 (never errors) */
+int mli_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Hash grid (replaces tcnn.Encoding HashGrid; modules.py:42-50, 84-86)
+ * ---------------------------------------------------------------------------------------------------- */
+#define MLI_MAX_LEVELS 32
+
+typedef struct {
+  float scale;       /* exp2f(l*log2f(per_level_scale))*base_resolution - 1 */
+  uint32_t res;      /* ceilf(scale)+1 */
+  uint32_t size;     /* entries in this level */
+  uint32_t offset;   /* first entry of this level in the flat table */
+  uint32_t hashed;   /* 1: coherent-prime hash, 0: dense index */
+} mli_level_t;
+
+typedef struct {
+  uint32_t n_levels;            /* L  (16) */
+  uint32_t feat;                /* F  (8; must be 8, 4 or 2) */
+  uint32_t active_levels;       /* coarse-to-fine mask (modules.py:110-113): levels >= this output 0 */
+  uint32_t n_entries;           /* sum of level sizes */
+  mli_level_t level[MLI_MAX_LEVELS];
+} mli_grid_t;
+
+/* host-only: fills `grid` the way tcnn's GridEncodingTemplated constructor does. */
+int mli_grid_init(mli_grid_t* grid, uint32_t n_levels, uint32_t feat, uint32_t log2_hashmap_size,
+                  uint32_t base_resolution, float per_level_scale);
+
+/* tcnn.Encoding.forward: x01 [M,3] in [0,1] -> out [M, ld_out] (first L*F columns written, level-major). */
+int mli_hashgrid_fwd(const mli_grid_t* grid, const float* table, const float* x01, int64_t M,
+                     float* out, int64_t ld_out, void* stream);
+/* tcnn.Encoding.backward w.r.t. params: table_grad[entry,f] += sum_m w * d_out[m, l*F+f]. */
+int mli_hashgrid_bwd(const mli_grid_t* grid, const float* x01, int64_t M, const float* d_out, int64_t ld_dout,
+                     float* table_grad, void* stream);
+/* KAT helper: the 8 corner rows (with level offset) of every point for one level -> idx [M,8] uint32. */
+int mli_hashgrid_corners(const mli_grid_t* grid, uint32_t level, const float* x01, int64_t M, uint32_t* idx,
+                         void* stream);
+
+/* Encode sample points along rays (fuses camera.get_3D_points_from_dist, camera.py:314-320; the [0,1]
+ * normalisation + xyz concat of NeuralSDF.encode, modules.py:82-94; and the tap offsets of
+ * compute_gradients, modules.py:133-166).  Writes rows [enc(L*F) | xyz(3) | 1 | 0-pad] of width ldx for
+ * `planes` = 1 (centre only) or 1+taps stencil planes: row = plane*R*n + ray*n + i.
+ *   dists [R, ld_d] (first n used), tap_eps = per-axis tap offset (eps/sqrt3 for 4 taps, eps for 6 taps). */
+int mli_encode_rays(const mli_grid_t* grid, const float* table, const float* center, const float* ray_unit,
+                    const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps,
+                    float vol_min, float vol_max, float* X, int64_t ldx, void* stream);
+/* backward of mli_encode_rays w.r.t. the table: dX rows as above, enc columns only. */
+int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, const float* ray_unit, const float* dists,
+                        int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps, float vol_min,
+                        float vol_max, const float* dX, int64_t ldx, float* table_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Dense layers (replace torch.nn.Linear + weight_norm + activation: mlp.py:55-69, nerf_util.py:186-196)
+ * ---------------------------------------------------------------------------------------------------- */
+enum { MLI_ACT_NONE = 0, MLI_ACT_RELU = 1, MLI_ACT_SOFTPLUS100 = 2, MLI_ACT_SIGMOID = 3 };
+enum { MLI_PREC_FP32 = 0, MLI_PREC_BF16 = 1 };
+
+/* Y[b] = act(X[b] W[b]^T + bias[b]) for b < batch.  X [M,K] ld ldx, W [N,K] ld ldw, Y [M,N] ld ldy.
+ * strides are in elements between batch members (0 = shared).  K % 16 == 0, ld* % 4 == 0. */
+int mli_linear_fwd(const float* X, int64_t ldx, int64_t sx, const float* W, int64_t ldw, int64_t sw,
+                   const float* bias, int64_t sb, float* Y, int64_t ldy, int64_t sy, int64_t M, int32_t N,
+                   int32_t K, int32_t act, int32_t batch, int32_t prec, void* stream);
+/* dX[b] = (dZ[b] Wt[b]^T) * act'(Yprev[b])   -- Wt is W transposed: [K_in, N_out] ld ldwt.
+ * act' is evaluated from the *output* Yprev of the previous layer (NULL / MLI_ACT_NONE: no factor).
+ * accumulate != 0: dX += ... */
+int mli_linear_dgrad(const float* dZ, int64_t lddz, int64_t sdz, const float* Wt, int64_t ldwt, int64_t swt,
+                     const float* Yprev, int64_t ldyp, int64_t syp, float* dX, int64_t lddx, int64_t sdx,
+                     int64_t M, int32_t N_out, int32_t K_in, int32_t act_prev, int32_t accumulate, int32_t batch,
+                     int32_t prec, void* stream);
+/* dW[b] = dZ[b]^T X[b]  ([N_out,K_in], ld lddw), db[b] = colsum(dZ[b]); split over M with a deterministic
+ * second-stage reduction.  ws must hold mli_linear_wgrad_ws_bytes(...) bytes. */
+int64_t mli_linear_wgrad_ws_bytes(int64_t M, int32_t N_out, int32_t K_in, int32_t batch);
+int mli_linear_wgrad(const float* dZ, int64_t lddz, int64_t sdz, const float* X, int64_t ldx, int64_t sx,
+                     float* dW, int64_t lddw, int64_t sdw, float* db, int64_t sdb, int64_t M, int32_t N_out,
+                     int32_t K_in, int32_t batch, int32_t prec, void* ws, void* stream);
+
+/* Narrow output layers (SDF head 256->1, mlp.py:50,66; head output layers 256->3/3/1, nerf_util.py:191):
+ * out[m, j] = act_j(sum_k A[m, col_off[j] + k] * w[j, k] + b[j]),  j < J <= 8, k < K; act_j = act if bit j of
+ * act_mask is set, identity otherwise (network_mode r_s leaves o_s without a sigmoid, modules.py:119).
+ * col_off is a HOST array of J column offsets. */
+int mli_rowdot_fwd(const float* A, int64_t lda, int64_t M, const float* w, const float* b,
+                   const int32_t* host_col_off, int32_t J, int32_t K, int32_t act, uint32_t act_mask, float* out,
+                   int64_t ldo, void* stream);
+/* dA[m,c] = ((accumulate ? dA[m,c] : 0) + sum_{j: col_off[j] <= c < col_off[j]+K} dS[m,j] w[j,c-col_off[j]])
+ *           * act_prev'(A[m,c])   for c < n_cols_dA;   dw[j,k] = sum_m dS[m,j] A[m,col_off[j]+k];  db[j] = sum_m dS[m,j].
+ * dA and/or dw may be NULL to skip that half. */
+int64_t mli_rowdot_bwd_ws_bytes(int64_t M, int32_t J, int32_t K);
+int mli_rowdot_bwd(const float* dS, int64_t lds, const float* A, int64_t lda, int64_t M, const float* w,
+                   const int32_t* host_col_off, int32_t J, int32_t K, int32_t act_prev, float* dA, int64_t ldda,
+                   int32_t n_cols_dA, int32_t accumulate, float* dw, float* db, void* ws, void* stream);
+
+/* weight_norm reparameterisation W = g * v / ||v||_row (mlp.py:42-44), scattered into a packed/padded layout:
+ * Wp[row_off + n, col_map[k]] = W[n,k]; Wpt is the transpose copy used by dgrad.  col_map NULL = identity. */
+int mli_weightnorm_pack(const float* v, const float* g, int32_t N, int32_t K, const int32_t* col_map,
+                        float* Wp, int64_t ldw, float* Wpt, int64_t ldwt, int32_t row_off, void* stream);
+/* dv, dg from dWp (same layout as Wp). */
+int mli_weightnorm_unpack_grad(const float* v, const float* g, const float* dWp, int64_t ldw, int32_t N, int32_t K,
+                               const int32_t* col_map, int32_t row_off, float* dv, float* dg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Rays, bounds, sampling (projects/neuralangelo/model.py:420-484; nerf_util.py:20-68,199-205;
+ * NeuralLumen/utils/utils.py:86-123)
+ * ---------------------------------------------------------------------------------------------------- */
+/* camera.get_center_and_ray + slice_by_ray_idx + F.normalize + get_center(pose_light)
+ * (camera.py:283-311; nerf_util.py:127-131; NeuralLumen/model.py:120-131). pose/pose_light [B,3,4] = world->camera,
+ * intr [B,3,3], ray_idx [B,R] pixel indices (NULL = 0..R-1), W = image width; outputs [B*R,3] (ray_norm [B*R]). */
+int mli_rays_from_pose(const float* pose, const float* intr, const float* pose_light, const int64_t* ray_idx,
+                       int64_t B, int64_t R, int32_t W, float* center, float* ray_unit, float* ray_norm,
+                       float* pts_light, void* stream);
+/* get_dist_bounds: aabb == NULL -> unit sphere.  outside is uint8 [R]. */
+int mli_dist_bounds(const float* center, const float* ray_unit, int64_t R, const float* host_aabb6, float* near,
+                    float* far, uint8_t* outside, void* stream);
+/* nerf_util.sample_dists: dists[r,i] = (rand+i)/n*(far-near)+near; rands NULL -> 0.5. */
+int mli_sample_coarse(const float* near, const float* far, const float* rands, int64_t R, int32_t n, float* dists,
+                      int64_t ld_d, void* stream);
+/* sample_dists_hierarchical + sample_dists_from_pdf: dists/sdfs [R, ld] (first n used) -> fine [R, n_fine].
+ * Optional KAT outputs (may be NULL): idx/low/high int32 [R, n_fine], cdf float [R, n] (n = n-1 weights + leading 0). */
+int mli_sample_fine(const float* dists, const float* sdfs, int64_t ld, int64_t R, int32_t n, int32_t n_fine,
+                    float inv_s, float* fine, int32_t* idx, int32_t* low, int32_t* high, float* cdf, void* stream);
+/* inverse-CDF binning alone, from given weights [R, ld_w] (n_w used): bit-exact KAT entry. */
+int mli_pdf_bins(const float* weights, int64_t ld_w, int64_t R, int32_t n_w, int32_t n_fine, int32_t* idx,
+                 int32_t* low, int32_t* high, float* cdf, void* stream);
+/* cat + sort(dim=2) (+ gather of sdfs): merges n sorted + n_fine new samples, stable. sdf pointers may be NULL. */
+int mli_sample_merge(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n, const float* fine,
+                     const float* sdf_fine, int32_t n_fine, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Per-sample geometry + head inputs (modules.py:157-175; NeuralLumen/model.py:343-349;
+ * spherical_harmonics.py:47-70; NeuralLumen/utils/modules.py:106-109)
+ * ---------------------------------------------------------------------------------------------------- */
+/* sdf [planes*M] (plane 0 = centre; overwritten with outside_val for outside rays, model.py:343).
+ * Writes gradients/hessians [M,3] (hessians NULL in eval) and XH[m, xh_off .. xh_off+38] =
+ * [pts(3) | SH(view)(16) | normal(3) | SH(light position)(16)]; columns beyond that up to ldxh are zeroed.
+ * tap_eps is the per-axis offset as a double (eps/sqrt(3) for 4 taps); the float32 divisors 4e, e^2 are derived
+ * from it exactly as torch derives them from the Python float. */
+int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, double tap_eps, const uint8_t* outside,
+                     float outside_val, const float* center, const float* ray_unit, const float* pts_light,
+                     const float* dists, int64_t ld_d, float* gradients, float* hessians, float* XH, int64_t ldxh,
+                     int32_t xh_off, void* stream);
+/* d_sdf [planes*M] = backward of gradients/hessians/normals (+ d_sdf_center_in from the alpha path).
+ * d_grad_in / d_hess_in [M,3] may be NULL; dXH supplies d normal at columns xh_off+19..21 (may be NULL). */
+int mli_geometry_bwd(const float* gradients, int64_t M, int32_t N, int32_t taps, double tap_eps,
+                     const uint8_t* outside, const float* d_grad_in, const float* d_hess_in, const float* dXH,
+                     int64_t ldxh, int32_t xh_off, const float* d_sdf_center_in, float* d_sdf, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * NeuS alpha + alpha compositing (neuralangelo/model.py:492-515; render.py:87-112;
+ * NeuralLumen/model.py:266-323, eval extras :365-368, :101-104)
+ * ---------------------------------------------------------------------------------------------------- */
+/* cfg.model.object.rgb.network_mode (NeuralLumen/utils/modules.py:16-55).  Per-sample channels S / per-ray out:
+ *   RGB     S = rgb3                 out = rgb3
+ *   RGB_R_S S = rgb3|o_r3|o_s1       out = rgb3|o_r3|o_s1|o_re3     (o_re = rgb - o_r*o_s)
+ *   RGB_R   S = rgb3|o_r3            out = rgb3|o_r3|o_s3           (o_s = rgb / o_r)
+ *   R_S     S = o_r3|o_s3            out = rgb3|o_r3|o_s3           (rgb = o_r*o_s)
+ *   R_S_RE  S = o_r3|o_s3|o_re3      out = rgb3|o_r3|o_s3|o_re3     (rgb = o_r*o_s + o_re) */
+enum { MLI_MODE_RGB = 0, MLI_MODE_RGB_R_S = 1, MLI_MODE_RGB_R = 2, MLI_MODE_R_S = 3, MLI_MODE_R_S_RE = 4 };
+
+typedef struct {
+  int32_t N;              /* samples per ray (<= 256) */
+  int32_t mode;           /* MLI_MODE_* */
+  int32_t white_bg;       /* add (1-opacity) to every composited channel */
+  int32_t eval_extras;    /* also opacity, gradient, dist composites */
+  float anneal_ratio;     /* min(progress/anneal_end, 1) */
+} mli_composite_cfg_t;
+
+/* S [M, lds] per-sample head outputs; out [R, n_out(mode)]; weights [R,N]; alphas [R,N] or NULL;
+ * extras [R,5] = opacity, gradient(3), dist (only with eval_extras). */
+int mli_composite_fwd(const mli_composite_cfg_t* cfg, const float* s_var, const float* sdf_center,
+                      const float* gradients, const float* ray_unit, const float* dists, int64_t ld_d,
+                      const float* far, const float* S, int64_t lds, int64_t R, float* alphas, float* weights,
+                      float* out, float* extras, void* stream);
+/* d_out [R,n_out], d_weights [R,N] or NULL -> dS_pre [M,lds] (gradient w.r.t. the PRE-activation head outputs;
+ * act_mask bit c set = channel c went through a sigmoid), d_sdf_center [M] (written), d_gradients [M,3]
+ * (ACCUMULATED into: pre-load it with the eikonal seeds or zeros), d_s_var[0] (+)= sum over rays (deterministic
+ * two-stage reduction; ws = R floats; NULL d_s_var skips it). */
+int mli_composite_bwd(const mli_composite_cfg_t* cfg, const float* s_var, const float* sdf_center,
+                      const float* gradients, const float* ray_unit, const float* dists, int64_t ld_d,
+                      const float* far, const float* S, int64_t lds, int64_t R, const float* weights,
+                      const float* d_out, const float* d_weights, uint32_t act_mask, float* dS_pre,
+                      float* d_sdf_center, float* d_gradients, float* d_s_var, int32_t accumulate_s_var, void* ws,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Losses, reduced in-kernel (NeuralLumen/trainer.py:133-149; neuralangelo/utils/misc.py:74-89;
+ * NeuralLumen/utils/utils.py:142-174; imaginaire/trainers/base.py:534-544)
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float w_render, w_eikonal, w_curvature, w_intrinsic, w_regularize_re;
+  float range_sha[2], range_vis[2], factor_ref, factor_sha;
+  float factor_negative, factor_positive, exponent_positive;
+  int32_t has_intrinsic;  /* o_r/o_s/o_re + pseudo labels present */
+} mli_loss_cfg_t;
+
+enum { MLI_LOSS_TOTAL = 0, MLI_LOSS_RENDER, MLI_LOSS_EIKONAL, MLI_LOSS_CURVATURE, MLI_LOSS_INTRINSIC,
+       MLI_LOSS_REG_RE, MLI_LOSS_MSE, MLI_LOSS_COUNT = 8 };
+
+/* out [R,n_out(mode)] as produced by mli_composite_fwd; pseudo_* may be NULL when !has_intrinsic.
+ * losses [MLI_LOSS_COUNT] floats.  Seeds (already multiplied by the loss weights): d_out [R,n_out] in the same
+ * column layout as out, d_gradients [M,3], d_hessians [M,3] (hessians NULL = eval: no curvature term).
+ * ws: mli_losses_ws_bytes(). */
+int64_t mli_losses_ws_bytes(int64_t R, int64_t M);
+int mli_losses_fwd_bwd(const mli_loss_cfg_t* cfg, int32_t mode, const float* out, const float* gradients,
+                       const float* hessians, const uint8_t* outside, int64_t R, int32_t N, const float* image,
+                       const float* pseudo_ref, const float* pseudo_sha, const float* pseudo_vis, float* losses,
+                       float* d_out, float* d_gradients, float* d_hessians, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * "Next" rows
+ * ---------------------------------------------------------------------------------------------------- */
+/* dense AdamW step (torch.optim.AdamW semantics, get_trainer.py:106-150) fused with gradient scaling (1/world). */
+int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLI_B200_H */

@@ -1,0 +1,188 @@
+"""ctypes binding of libmli_b200.so (include/mli_b200.h).  PyTorch is only the allocator / stream provider here:
+tensors are passed as raw device pointers, the stream as ``torch.cuda.current_stream().cuda_stream``.
+
+There is NO CPU fallback: if the library is missing it must be built (``python -m mli_nerf_b200.build``); if no
+sm_100 device is current every compute entry point returns MLI_ENODEV and this module raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmli_b200.so")
+
+MLI_MAX_LEVELS = 32
+ACT_NONE, ACT_RELU, ACT_SOFTPLUS100, ACT_SIGMOID = 0, 1, 2, 3
+PREC_FP32, PREC_BF16 = 0, 1
+MODE_RGB, MODE_RGB_R_S, MODE_RGB_R, MODE_R_S, MODE_R_S_RE = 0, 1, 2, 3, 4
+MODE_BY_NAME = {None: MODE_RGB, "rgb": MODE_RGB, "rgb_r_s": MODE_RGB_R_S, "rgb_r": MODE_RGB_R, "r_s": MODE_R_S,
+                "r_s_re": MODE_R_S_RE}
+LOSS_NAMES = ("total", "render", "eikonal", "curvature", "intrinsic", "regularize_re", "mse")
+
+
+class Level(C.Structure):
+    _fields_ = [("scale", C.c_float), ("res", C.c_uint32), ("size", C.c_uint32), ("offset", C.c_uint32),
+                ("hashed", C.c_uint32)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("feat", C.c_uint32), ("active_levels", C.c_uint32),
+                ("n_entries", C.c_uint32), ("level", Level * MLI_MAX_LEVELS)]
+
+
+class CompositeCfg(C.Structure):
+    _fields_ = [("N", C.c_int32), ("mode", C.c_int32), ("white_bg", C.c_int32), ("eval_extras", C.c_int32),
+                ("anneal_ratio", C.c_float)]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [("w_render", C.c_float), ("w_eikonal", C.c_float), ("w_curvature", C.c_float),
+                ("w_intrinsic", C.c_float), ("w_regularize_re", C.c_float), ("range_sha", C.c_float * 2),
+                ("range_vis", C.c_float * 2), ("factor_ref", C.c_float), ("factor_sha", C.c_float),
+                ("factor_negative", C.c_float), ("factor_positive", C.c_float), ("exponent_positive", C.c_float),
+                ("has_intrinsic", C.c_int32)]
+
+
+# Signature table derived from include/mli_b200.h itself (single source of truth for the ABI):
+#   p = device pointer (tensor / None / int), i = int32, l = int64, f = float, d = double, u = uint32,
+#   s = stream, h / H = HOST int32 / float array (parameter names starting with host_).
+HEADER_PATH = os.path.join(_HERE, "..", "include", "mli_b200.h")
+
+
+def _parse_header(path=HEADER_PATH):
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\b(int|int64_t)\s+(mli_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        if ret != "int" or args in ("void", ""):
+            continue
+        sig = ""
+        for a in args.split(","):
+            a = a.strip()
+            pname = a.split()[-1].lstrip("*")
+            if "*" in a:
+                if pname == "stream":
+                    sig += "s"
+                elif pname.startswith("host_"):
+                    sig += "h" if "int32_t" in a else "H"
+                else:
+                    sig += "p"
+            else:
+                ty = a.replace("const", "").split()[0]
+                sig += {"int64_t": "l", "int32_t": "i", "uint32_t": "u", "float": "f", "double": "d", "int": "i"}[ty]
+        sigs[name] = sig
+    return sigs
+
+
+_SIGS = {k: v for k, v in _parse_header().items() if k not in ("mli_abi_version", "mli_device_ok", "mli_grid_init")}
+_CTYPE = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "d": C.c_double, "u": C.c_uint32,
+          "s": C.c_void_p, "h": C.c_void_p, "H": C.c_void_p}
+
+_lib = None
+
+
+class MliError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MliError(f"{LIB_PATH} not found: build it with `python -m mli_nerf_b200.build` "
+                       "(hand-written sm_100a CUDA; there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.mli_last_error.restype = C.c_char_p
+    lib.mli_abi_version.restype = C.c_int
+    lib.mli_device_ok.restype = C.c_int
+    lib.mli_grid_init.argtypes = [C.POINTER(Grid), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
+    lib.mli_grid_init.restype = C.c_int
+    for name, sig in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_CTYPE[c] for c in sig]
+        fn.restype = C.c_int
+    for name in ("mli_linear_wgrad_ws_bytes", "mli_rowdot_bwd_ws_bytes", "mli_losses_ws_bytes"):
+        getattr(lib, name).restype = C.c_int64
+    lib.mli_linear_wgrad_ws_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+    lib.mli_rowdot_bwd_ws_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.mli_losses_ws_bytes.argtypes = [C.c_int64, C.c_int64]
+    _lib = lib
+    return lib
+
+
+def _raise(code, name):
+    msg = (load().mli_last_error() or b"").decode()
+    if code == -1 and "Only support 4 or 6 taps" in msg:
+        raise ValueError(msg)  # same exception type/message as modules.py:177
+    if code in (-1,):
+        raise ValueError(f"{name}: {msg}")
+    if code == -4:
+        raise NotImplementedError(f"{name}: {msg}")
+    raise MliError(f"{name} failed ({code}): {msg}")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            raise MliError("libmli_b200 takes CUDA tensors only (no CPU fallback)")
+        return x.data_ptr()
+    if isinstance(x, C.Structure):
+        return C.addressof(x)
+    return int(x)
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an entry point; tensors -> device pointers, 's' slot filled with the current stream when omitted."""
+    lib = load()
+    sig = _SIGS[name]
+    if len(args) == len(sig) - 1:
+        args = args + (stream_ptr(),)
+    if len(args) != len(sig):
+        raise TypeError(f"{name}: expected {len(sig)} arguments, got {len(args)}")
+    conv, keep = [], []
+    for c, a in zip(sig, args):
+        if c in "ps":
+            conv.append(_ptr(a))
+        elif c == "h":
+            if a is None:
+                conv.append(None)
+            else:
+                arr = (C.c_int32 * len(a))(*[int(v) for v in a])
+                keep.append(arr)
+                conv.append(C.addressof(arr))
+        elif c == "H":
+            if a is None:
+                conv.append(None)
+            else:
+                arr = (C.c_float * len(a))(*[float(v) for v in a])
+                keep.append(arr)
+                conv.append(C.addressof(arr))
+        elif c in "f" "d":
+            conv.append(float(a))
+        else:
+            conv.append(int(a))
+    code = getattr(lib, name)(*conv)
+    if code != 0:
+        _raise(code, name)
+
+
+def make_grid(n_levels, feat, log2_hashmap_size, base_resolution, per_level_scale):
+    g = Grid()
+    code = load().mli_grid_init(C.byref(g), n_levels, feat, log2_hashmap_size, base_resolution, per_level_scale)
+    if code != 0:
+        _raise(code, "mli_grid_init")
+    return g
+
+
+def device_ok():
+    return bool(load().mli_device_ok())

@@ -1,0 +1,77 @@
+// capi.cu -- error state, device check, host-side helpers of the C ABI (include/mli_b200.h)
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mli_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mli_last_error(void) { return g_err; }
+extern "C" int mli_abi_version(void) { return MLI_ABI_VERSION; }
+
+extern "C" int mli_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+int mli_check_device() {
+  static thread_local int cached = -1;
+  if (cached == 1) return MLI_OK;
+  if (!mli_device_ok()) {
+    mli_set_error("libmli_b200 needs a compute-capability 10.x (B200, sm_100a) device; there is no CPU fallback");
+    return MLI_ENODEV;
+  }
+  cached = 1;
+  return MLI_OK;
+}
+
+// tcnn GridEncodingTemplated constructor + grid_scale()/grid_resolution() (float32 arithmetic), see
+// oracle/torch_hashgrid.py for the formulas this follows.
+extern "C" int mli_grid_init(mli_grid_t* grid, uint32_t n_levels, uint32_t feat, uint32_t log2_hashmap_size,
+                             uint32_t base_resolution, float per_level_scale) {
+  MLI_REQUIRE(grid != nullptr, "grid is NULL");
+  MLI_REQUIRE(n_levels >= 1 && n_levels <= MLI_MAX_LEVELS, "n_levels %u out of range", n_levels);
+  MLI_REQUIRE(feat == 8 || feat == 4 || feat == 2, "n_features_per_level must be 2, 4 or 8 (got %u)", feat);
+  MLI_REQUIRE(log2_hashmap_size >= 4 && log2_hashmap_size <= 28, "log2_hashmap_size %u out of range",
+              log2_hashmap_size);
+  memset(grid, 0, sizeof(*grid));
+  grid->n_levels = n_levels;
+  grid->feat = feat;
+  grid->active_levels = n_levels;
+  // tcnn evaluates exp2f(l * log2f(s)) * base - 1 in float32 on the device; its last-ulp rounding is platform
+  // dependent, so oracle and product both use the float64 formula rounded once to float32 (bit-reproducible).
+  const double log2_pls = log2((double)per_level_scale);
+  uint64_t offset = 0;
+  for (uint32_t l = 0; l < n_levels; ++l) {
+    mli_level_t& lv = grid->level[l];
+    lv.scale = (float)(exp2((double)l * log2_pls) * (double)base_resolution - 1.0);
+    lv.res = (uint32_t)ceilf(lv.scale) + 1u;
+    const uint32_t max_params = 0xFFFFFFFFu / 2u;
+    double dense = (double)lv.res * (double)lv.res * (double)lv.res;
+    uint32_t n = dense > (double)max_params ? max_params : (uint32_t)dense;
+    n = (n + 7u) / 8u * 8u;
+    uint32_t cap = 1u << log2_hashmap_size;
+    lv.size = n < cap ? n : cap;
+    uint64_t stride = 1;
+    for (int d = 0; d < 3 && stride <= lv.size; ++d) stride *= lv.res;
+    lv.hashed = lv.size < stride ? 1u : 0u;
+    lv.offset = (uint32_t)offset;
+    offset += lv.size;
+    MLI_REQUIRE(offset < 0xFFFFFFFFull, "hash table too large for 32-bit row indices");
+  }
+  grid->n_entries = (uint32_t)offset;
+  return MLI_OK;
+}

@@ -1,0 +1,339 @@
+// hashgrid.cu -- multi-resolution hash-grid encoding for sm_100a (replaces tcnn.Encoding HashGrid,
+// /root/reference/projects/neuralangelo/utils/modules.py:42-50,84-86).
+//
+// Data layout in HBM: one flat fp32 table [n_entries][F] (the reference's state_dict tensor
+// neural_sdf.tcnn_encoding.params, level-major).  With F = 8 one entry is exactly one 32-byte DRAM/L2 sector,
+// so every corner fetch is one fully used sector (2 x LDG.128).  Thread mapping: one thread per
+// (sample, level), gridDim.y = level, so a CTA touches a single level's slab (L2 locality for the dense
+// levels 0-5, 57 MB) and the per-level constants are warp-uniform.  The ray variant loops over the 1+taps
+// stencil planes inside the thread: the 5 points of Neuralangelo's 4-tap stencil are < 0.3 fine cells
+// apart, so their corner sectors mostly coincide and are served by L1 instead of a second trip to L2/HBM.
+// Bound: HBM/L2 gather bandwidth (16 levels * 8 corners * 32 B = 4 KB per query).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int F>
+__device__ __forceinline__ void load_entry(const float* __restrict__ table, uint32_t row, float* v) {
+  if constexpr (F == 8) {
+    const float4* p = reinterpret_cast<const float4*>(table + (size_t)row * 8);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else if constexpr (F == 4) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(table + (size_t)row * 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+    float2 a = __ldg(reinterpret_cast<const float2*>(table + (size_t)row * 2));
+    v[0] = a.x; v[1] = a.y;
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void interp(const mli_level_t& lv, const float* __restrict__ table, float x, float y,
+                                       float z, float* acc) {
+  mli_cell_t cell = mli_grid_cell(lv, x, y, z);
+  uint32_t rows[8];
+  float wts[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mli_corner(lv, cell, c, &rows[c], &wts[c]);
+  float vals[8][F];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) load_entry<F>(table, rows[c], vals[c]);  // 8 independent sector fetches in flight
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)  // same corner order as tcnn's fma chain
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = fmaf(wts[c], vals[c][f], acc[f]);
+}
+
+template <int F>
+__device__ __forceinline__ void store_feat(float* __restrict__ dst, const float* acc) {
+  if constexpr (F == 8) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  } else if constexpr (F == 4) {
+    reinterpret_cast<float4*>(dst)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+    reinterpret_cast<float2*>(dst)[0] = make_float2(acc[0], acc[1]);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_entry(float* __restrict__ grad, uint32_t row, float w, const float* d) {
+  float* p = grad + (size_t)row * F;
+  if constexpr (F == 8) {
+    // vector reductions (RED.E.ADD.F32x4 on sm_90+): 2 per corner instead of 8 scalar atomics
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(w * d[0], w * d[1], w * d[2], w * d[3]));
+    atomicAdd(reinterpret_cast<float4*>(p) + 1, make_float4(w * d[4], w * d[5], w * d[6], w * d[7]));
+  } else if constexpr (F == 4) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(w * d[0], w * d[1], w * d[2], w * d[3]));
+  } else {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(w * d[0], w * d[1]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tcnn-compatible entry: x01 [M,3] -> out [M, ld]
+// ---------------------------------------------------------------------------------------------------------
+template <int F>
+__global__ void __launch_bounds__(kThreads) hashgrid_fwd_kernel(mli_grid_t grid, const float* __restrict__ table,
+                                                                const float* __restrict__ x01, int64_t M,
+                                                                float* __restrict__ out, int64_t ld) {
+  const int level = blockIdx.y;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M) return;
+  float acc[F];
+  if (level >= (int)grid.active_levels) {
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+  } else {
+    interp<F>(grid.level[level], table, x01[m * 3 + 0], x01[m * 3 + 1], x01[m * 3 + 2], acc);
+  }
+  store_feat<F>(out + m * ld + level * F, acc);
+}
+
+template <int F>
+__global__ void __launch_bounds__(kThreads) hashgrid_bwd_kernel(mli_grid_t grid, const float* __restrict__ x01,
+                                                                int64_t M, const float* __restrict__ d_out,
+                                                                int64_t ld, float* __restrict__ table_grad) {
+  const int level = blockIdx.y;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M || level >= (int)grid.active_levels) return;
+  const mli_level_t& lv = grid.level[level];
+  float d[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) d[f] = d_out[m * ld + level * F + f];
+  mli_cell_t cell = mli_grid_cell(lv, x01[m * 3 + 0], x01[m * 3 + 1], x01[m * 3 + 2]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t row;
+    float w;
+    mli_corner(lv, cell, c, &row, &w);
+    scatter_entry<F>(table_grad, row, w, d);
+  }
+}
+
+__global__ void hashgrid_corners_kernel(mli_grid_t grid, uint32_t level, const float* __restrict__ x01, int64_t M,
+                                        uint32_t* __restrict__ idx) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const mli_level_t& lv = grid.level[level];
+  mli_cell_t cell = mli_grid_cell(lv, x01[m * 3 + 0], x01[m * 3 + 1], x01[m * 3 + 2]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t row;
+    float w;
+    mli_corner(lv, cell, c, &row, &w);
+    idx[m * 8 + c] = row;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ray variant: points from (center, ray_unit, dists), 1+taps stencil planes, rows [enc | xyz | 0-pad]
+// ---------------------------------------------------------------------------------------------------------
+struct RayArgs {
+  const float* center;
+  const float* ray_unit;
+  const float* dists;
+  int64_t ld_d, R;
+  int32_t n, taps;
+  float tap_eps, vol_min, vol_range;
+};
+
+__device__ __forceinline__ void ray_point01(const RayArgs& a, int64_t ray, int i, int plane, float* p, float* x01) {
+  float c[3] = {a.center[ray * 3], a.center[ray * 3 + 1], a.center[ray * 3 + 2]};
+  float r[3] = {a.ray_unit[ray * 3], a.ray_unit[ray * 3 + 1], a.ray_unit[ray * 3 + 2]};
+  mli_sample_point(c, r, a.dists[ray * a.ld_d + i], a.taps, plane, a.tap_eps, p);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) x01[k] = mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+}
+
+template <int F>
+__global__ void __launch_bounds__(kThreads) encode_rays_kernel(mli_grid_t grid, const float* __restrict__ table,
+                                                               RayArgs a, float* __restrict__ X, int64_t ldx) {
+  const int level = blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M) return;
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  const int planes = 1 + a.taps;
+  const int enc = grid.n_levels * F;
+  for (int pl = 0; pl < planes; ++pl) {
+    float p[3], x01[3], acc[F];
+    ray_point01(a, ray, i, pl, p, x01);
+    float* row = X + ((int64_t)pl * M + m) * ldx;
+    if (level >= (int)grid.active_levels) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+    } else {
+      interp<F>(grid.level[level], table, x01[0], x01[1], x01[2], acc);
+    }
+    store_feat<F>(row + level * F, acc);
+    if (level == 0) {  // xyz + zero padding, once per row
+      row[enc + 0] = p[0]; row[enc + 1] = p[1]; row[enc + 2] = p[2];
+      for (int k = enc + 3; k < ldx; ++k) row[k] = 0.0f;
+    }
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t grid, RayArgs a,
+                                                                   const float* __restrict__ dX, int64_t ldx,
+                                                                   float* __restrict__ table_grad) {
+  const int level = blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M || level >= (int)grid.active_levels) return;
+  const mli_level_t& lv = grid.level[level];
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  const int planes = 1 + a.taps;
+  // Aggregate the stencil planes that fall into the centre's cell before touching memory: their 8 corner
+  // rows are identical, so one vector reduction per corner carries all of them (up to 5x fewer atomics).
+  float p[3], x01[3];
+  ray_point01(a, ray, i, 0, p, x01);
+  const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+  float agg[8][F];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int f = 0; f < F; ++f) agg[c][f] = 0.0f;
+  for (int pl = 0; pl < planes; ++pl) {
+    mli_cell_t cell = cell0;
+    if (pl) {
+      ray_point01(a, ray, i, pl, p, x01);
+      cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+    }
+    float d[F];
+    const float* src = dX + ((int64_t)pl * M + m) * ldx + level * F;
+#pragma unroll
+    for (int f = 0; f < F; ++f) d[f] = src[f];
+    const bool same = cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2];
+    if (same) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float w = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell.w[k] : 1.0f - cell.w[k];
+#pragma unroll
+        for (int f = 0; f < F; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t row;
+        float w;
+        mli_corner(lv, cell, c, &row, &w);
+        scatter_entry<F>(table_grad, row, w, d);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t row;
+    float w;
+    mli_corner(lv, cell0, c, &row, &w);
+    scatter_entry<F>(table_grad, row, 1.0f, agg[c]);
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_F(feat, CALL)                                      \
+  switch (feat) {                                                   \
+    case 8: { constexpr int F = 8; CALL; } break;                   \
+    case 4: { constexpr int F = 4; CALL; } break;                   \
+    case 2: { constexpr int F = 2; CALL; } break;                   \
+    default: mli_set_error("unsupported n_features_per_level %u", feat); return MLI_EINVAL; \
+  }
+
+static int check_grid(const mli_grid_t* g) {
+  MLI_REQUIRE(g != nullptr, "grid is NULL");
+  MLI_REQUIRE(g->n_levels >= 1 && g->n_levels <= MLI_MAX_LEVELS, "bad n_levels %u", g->n_levels);
+  MLI_REQUIRE(g->active_levels <= g->n_levels, "active_levels %u > n_levels %u", g->active_levels, g->n_levels);
+  return MLI_OK;
+}
+
+extern "C" int mli_hashgrid_fwd(const mli_grid_t* grid, const float* table, const float* x01, int64_t M, float* out,
+                                int64_t ld_out, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  MLI_REQUIRE(M >= 0 && ld_out >= (int64_t)grid->n_levels * grid->feat, "bad M/ld_out");
+  MLI_REQUIRE(ld_out % 4 == 0 || grid->feat == 2, "ld_out must keep rows 16-byte aligned");
+  if (M == 0) return MLI_OK;
+  dim3 g(mli_cdiv(M, kThreads), grid->n_levels);
+  DISPATCH_F(grid->feat, (hashgrid_fwd_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, table, x01, M, out,
+                                                                                          ld_out)));
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_hashgrid_bwd(const mli_grid_t* grid, const float* x01, int64_t M, const float* d_out,
+                                int64_t ld_dout, float* table_grad, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  MLI_REQUIRE(M >= 0 && ld_dout >= (int64_t)grid->n_levels * grid->feat, "bad M/ld_dout");
+  if (M == 0) return MLI_OK;
+  dim3 g(mli_cdiv(M, kThreads), grid->n_levels);
+  DISPATCH_F(grid->feat, (hashgrid_bwd_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, x01, M, d_out,
+                                                                                          ld_dout, table_grad)));
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_hashgrid_corners(const mli_grid_t* grid, uint32_t level, const float* x01, int64_t M,
+                                    uint32_t* idx, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  MLI_REQUIRE(level < grid->n_levels, "level %u out of range", level);
+  if (M == 0) return MLI_OK;
+  hashgrid_corners_kernel<<<mli_cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(*grid, level, x01, M, idx);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+static int make_ray_args(RayArgs* a, const float* center, const float* ray_unit, const float* dists, int64_t ld_d,
+                         int64_t R, int32_t n, int32_t taps, float tap_eps, float vol_min, float vol_max) {
+  MLI_REQUIRE(taps == 0 || taps == 4 || taps == 6, "Only support 4 or 6 taps.");
+  MLI_REQUIRE(R >= 0 && n >= 1 && ld_d >= n, "bad R/n/ld_d");
+  MLI_REQUIRE(vol_max > vol_min, "empty volume range");
+  a->center = center; a->ray_unit = ray_unit; a->dists = dists; a->ld_d = ld_d; a->R = R; a->n = n;
+  a->taps = taps; a->tap_eps = tap_eps; a->vol_min = vol_min; a->vol_range = vol_max - vol_min;
+  return MLI_OK;
+}
+
+extern "C" int mli_encode_rays(const mli_grid_t* grid, const float* table, const float* center,
+                               const float* ray_unit, const float* dists, int64_t ld_d, int64_t R, int32_t n,
+                               int32_t taps, float tap_eps, float vol_min, float vol_max, float* X, int64_t ldx,
+                               void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  RayArgs a;
+  if (int e = make_ray_args(&a, center, ray_unit, dists, ld_d, R, n, taps, tap_eps, vol_min, vol_max)) return e;
+  MLI_REQUIRE(ldx >= (int64_t)grid->n_levels * grid->feat + 3 && ldx % 4 == 0, "ldx too small / unaligned");
+  if (R == 0) return MLI_OK;
+  dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
+  DISPATCH_F(grid->feat, (encode_rays_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, table, a, X, ldx)));
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, const float* ray_unit,
+                                   const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps,
+                                   float tap_eps, float vol_min, float vol_max, const float* dX, int64_t ldx,
+                                   float* table_grad, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  RayArgs a;
+  if (int e = make_ray_args(&a, center, ray_unit, dists, ld_d, R, n, taps, tap_eps, vol_min, vol_max)) return e;
+  if (R == 0) return MLI_OK;
+  dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
+  DISPATCH_F(grid->feat,
+             (encode_rays_bwd_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, a, dX, ldx, table_grad)));
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
