@@ -1,0 +1,392 @@
+"""Host-side orchestration of the per-ray render path over the C ABI (libmli_b200.so).
+
+This file is plumbing: it owns the HBM layout (which buffer each kernel reads/writes), issues the C-ABI calls in
+order on the current CUDA stream and hands torch-allocated device pointers across the boundary.  No arithmetic of the
+path happens here and there is no CPU fallback.
+
+Reference call stack being replaced (relative to /root/reference/):
+  projects/NeuralLumen/model.py:232-336 render_rays_lumen, :338-403 render_rays_object_lumen
+  projects/neuralangelo/model.py:420-515 bounds / sampling / NeuS alphas
+  projects/neuralangelo/utils/modules.py:68-178 NeuralSDF forward + numerical gradients
+  projects/NeuralLumen/utils/modules.py:106-174 LumenRGB forward
+  + the autograd backward of all of it (projects/NeuralLumen/trainer.py:189-206).
+
+HBM layout (fp32, row-major; M = R*N samples, P = 1+taps stencil planes)
+  X0   [P*M, 144]  = [hash encoding 0:128 | xyz 128:131 | 0-pad]          input of SDF layer 0 (K padded to 16)
+  H0   [P*M, 256]  = softplus100(X0 W0^T + b0)                            (plane 0 = centre rows)
+  sdf  [P*M]       = H0 w_sdf + b_sdf
+  XH   [M, 304]    = [feat 0:256 | xyz | SH(view) | normal | SH(light) | 0-pad]   input of the fused head layer 0
+  A1..A4 [M, nh*256] hidden activations of the nh heads side by side (batched block-diagonal layers 1..3)
+  S    [M, 8]      per-sample head outputs (rgb3|o_r3|o_s1 for rgb_r_s)
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS100, call
+
+K0_PAD = 144      # 128 + 3 -> multiple of 16
+KH_PAD = 304      # 256 + 38 -> multiple of 16
+XH_OFF = 256      # first non-feature column of XH
+HID = 256
+
+
+@dataclass
+class PathCfg:
+    """Resolved hot-path hyper-parameters (what the reference reads from cfg.model / cfg.data / cfg.trainer)."""
+    n_levels: int = 16
+    feat_per_level: int = 8
+    log2_hashmap_size: int = 22
+    min_logres: int = 5
+    max_logres: int = 11
+    vol_range: Tuple[float, float] = (-2.0, 2.0)
+    hidden: int = 256
+    taps: int = 4
+    coarse: int = 64
+    fine: int = 16
+    hierarchy: int = 4
+    sh_levels: int = 3
+    network_mode: Optional[str] = "rgb_r_s"
+    white_background: bool = True
+    anneal_end: float = 0.1
+    outside_val: float = 1000.0
+    bounding: str = "unit_sphere"
+    aabb: Optional[Tuple[float, ...]] = None
+    c2f_enabled: bool = False
+    precision: int = _lib.PREC_FP32
+
+    @property
+    def n_samples(self):
+        return self.coarse + self.fine * self.hierarchy
+
+    @property
+    def growth_rate(self):
+        return float(math.exp((math.log(2 ** self.max_logres) - math.log(2 ** self.min_logres)) / (self.n_levels - 1)))
+
+    def resolutions(self):
+        return [int(math.floor(2 ** self.min_logres * self.growth_rate ** lv)) + 1 for lv in range(self.n_levels)]
+
+
+def head_layout(mode):
+    """(state-dict name, input kind, out_dim, sigmoid) per head, in the channel order of the composite kernel."""
+    table = {
+        "rgb_r_s": [("mlp", "full", 3, True), ("mlp_r", "geo", 3, True), ("mlp_s", "geo_l", 1, True)],
+        "rgb_r": [("mlp", "full", 3, True), ("mlp_r", "geo", 3, True)],
+        "r_s": [("mlp_r", "geo", 3, True), ("mlp_s", "full", 3, False)],
+        "r_s_re": [("mlp_r", "geo", 3, True), ("mlp_s", "geo_l", 3, True), ("mlp_re", "full", 3, True)],
+        "rgb": [("mlp", "full", 3, True)],
+        None: [("mlp", "full", 3, True)],
+    }
+    if mode not in table:
+        raise NotImplementedError(f"unknown network_mode {mode}")
+    return table[mode]
+
+
+def _col_map(kind):
+    pts, view, nrm = [256, 257, 258], list(range(259, 275)), [275, 276, 277]
+    feat, light = list(range(0, 256)), list(range(278, 294))
+    return {"full": pts + view + nrm + feat + light, "geo": pts + nrm + feat, "geo_l": pts + nrm + feat + light}[kind]
+
+
+class RenderEngine:
+    def __init__(self, cfg: PathCfg, device="cuda"):
+        if cfg.hidden != HID or cfg.sh_levels != 3 or cfg.n_levels * cfg.feat_per_level != 128:
+            raise NotImplementedError("engine is specialised for hidden=256, SH level 3 and a 128-wide hash encoding")
+        _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.grid = _lib.make_grid(cfg.n_levels, cfg.feat_per_level, cfg.log2_hashmap_size, 2 ** cfg.min_logres,
+                                   cfg.growth_rate)
+        self.heads = head_layout(cfg.network_mode)
+        self.nh = len(self.heads)
+        self.mode = _lib.MODE_BY_NAME[cfg.network_mode]
+        self.J = sum(h[2] for h in self.heads)
+        self.col_off = [hi * HID for hi, h in enumerate(self.heads) for _ in range(h[2])]
+        self.act_mask = 0
+        j = 0
+        for h in self.heads:
+            for _ in range(h[2]):
+                self.act_mask |= (1 << j) if h[3] else 0
+                j += 1
+        self.n_out = {0: 3, 1: 10, 2: 9, 3: 9, 4: 12}[self.mode]
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.map_sdf0 = torch.tensor([128, 129, 130] + list(range(128)), **i32)
+        self.map_head = [torch.tensor(_col_map(h[1]), **i32) for h in self.heads]
+        self.normal_eps = 1.0 / cfg.resolutions()[-1]
+        self.active_levels = cfg.n_levels
+        self.W = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def n_table_params(self):
+        return int(self.grid.n_entries) * self.cfg.feat_per_level
+
+    def set_active_levels(self, active):
+        self.active_levels = int(active)
+        self.grid.active_levels = int(active) if self.cfg.c2f_enabled else self.cfg.n_levels
+
+    def _f(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def _z(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+
+    @property
+    def tap_eps(self):  # modules.py:133,158
+        return self.normal_eps / math.sqrt(3) if self.cfg.taps == 4 else self.normal_eps
+
+    # ------------------------------------------------------------------------------------------------------
+    def pack_weights(self, p):
+        """weight_norm reparameterisation into the padded / fused layouts the layer kernels read (per step)."""
+        nh, W = self.nh, {}
+        W["W0"], W["W0t"] = self._z(HID, K0_PAD), self._z(K0_PAD, HID)
+        call("mli_weightnorm_pack", p["neural_sdf.mlp.linears.0.weight_v"], p["neural_sdf.mlp.linears.0.weight_g"], HID,
+             131, self.map_sdf0, W["W0"], K0_PAD, W["W0t"], HID, 0)
+        W["W1"], W["W1t"] = self._f(HID, HID), self._f(HID, HID)
+        call("mli_weightnorm_pack", p["neural_sdf.mlp.linears.1.weight_v"], p["neural_sdf.mlp.linears.1.weight_g"], HID,
+             HID, None, W["W1"], HID, W["W1t"], HID, 0)
+        W["b0"], W["b1"] = p["neural_sdf.mlp.linears.0.bias"], p["neural_sdf.mlp.linears.1.bias"]
+        W["w_sdf"], W["b_sdf"] = p["neural_sdf.mlp.linear_sdf.weight"], p["neural_sdf.mlp.linear_sdf.bias"]
+        W["Wh0"], W["Wh0t"] = self._z(nh * HID, KH_PAD), self._z(KH_PAD, nh * HID)
+        W["Whl"] = [self._f(nh, HID, HID) for _ in range(3)]
+        W["Whlt"] = [self._f(nh, HID, HID) for _ in range(3)]
+        W["Wout"] = self._f(self.J, HID)
+        j0 = 0
+        for hi, (name, kind, odim, _) in enumerate(self.heads):
+            pre = f"neural_rgb.{name}.linears."
+            k_in = len(_col_map(kind))
+            call("mli_weightnorm_pack", p[pre + "0.weight_v"], p[pre + "0.weight_g"], HID, k_in, self.map_head[hi],
+                 W["Wh0"], KH_PAD, W["Wh0t"], nh * HID, hi * HID)
+            for l in range(3):
+                call("mli_weightnorm_pack", p[pre + f"{l + 1}.weight_v"], p[pre + f"{l + 1}.weight_g"], HID, HID, None,
+                     W["Whl"][l][hi], HID, W["Whlt"][l][hi], HID, 0)
+            call("mli_weightnorm_pack", p[pre + "4.weight_v"], p[pre + "4.weight_g"], odim, HID, None, W["Wout"], HID,
+                 None, 0, j0)
+            j0 += odim
+        W["bh"] = [torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for h in self.heads]) for l in range(4)]
+        W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
+        self.W = W
+        return W
+
+    # ------------------------------------------------------------------------------------------------------
+    def bounds(self, center, ray_unit):
+        R = center.shape[0]
+        near, far = self._f(R), self._f(R)
+        outside = torch.empty(R, dtype=torch.uint8, device=self.device)
+        aabb = list(self.cfg.aabb) if self.cfg.bounding == "box" else None
+        call("mli_dist_bounds", center, ray_unit, R, aabb, near, far, outside)
+        return near, far, outside
+
+    def sdf_query(self, table, center, ray_unit, dists, ld, n):
+        """SDF-only network query at n samples per ray (NeuralSDF.sdf, modules.py:73-74)."""
+        R, W = center.shape[0], self.W
+        X = self._f(R * n, K0_PAD)
+        call("mli_encode_rays", self.grid, table, center, ray_unit, dists, ld, R, n, 0, 0.0, self.cfg.vol_range[0],
+             self.cfg.vol_range[1], X, K0_PAD)
+        H = self._f(R * n, HID)
+        call("mli_linear_fwd", X, K0_PAD, 0, W["W0"], K0_PAD, 0, W["b0"], 0, H, HID, 0, R * n, HID, K0_PAD,
+             ACT_SOFTPLUS100, 1, self.cfg.precision)
+        sdf = self._f(R * n)
+        call("mli_rowdot_fwd", H, HID, R * n, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
+        return sdf
+
+    def sample(self, table, center, ray_unit, near, far, rands=None):
+        """Model.sample_dists_all (neuralangelo/model.py:449-465): coarse + hierarchical importance sampling."""
+        cfg, R, N = self.cfg, center.shape[0], self.cfg.n_samples
+        dists, sdfs = self._f(R, N), self._f(R, N)
+        call("mli_sample_coarse", near, far, rands, R, cfg.coarse, dists, N)
+        n = cfg.coarse
+        if cfg.hierarchy > 0:
+            s = self.sdf_query(table, center, ray_unit, dists, N, n)
+            sdfs[:, :n] = s.view(R, n)
+        fine = self._f(R, cfg.fine)
+        for h in range(cfg.hierarchy):
+            call("mli_sample_fine", dists, sdfs, N, R, n, cfg.fine, float(64 * 2 ** h), fine, None, None, None, None)
+            if h != cfg.hierarchy - 1:
+                sf = self.sdf_query(table, center, ray_unit, fine, cfg.fine, cfg.fine)
+                call("mli_sample_merge", dists, sdfs, N, R, n, fine, sf, cfg.fine)
+            else:
+                call("mli_sample_merge", dists, None, N, R, n, fine, None, cfg.fine)
+            n += cfg.fine
+        return dists
+
+    # ------------------------------------------------------------------------------------------------------
+    def forward(self, p, center, ray_unit, pts_light, dists, near, far, outside, training, progress):
+        """render_rays_object_lumen + compositing for R rays with given sample distances.  Returns (out, ctx)."""
+        cfg, W, nh = self.cfg, self.W, self.nh
+        R, N = center.shape[0], cfg.n_samples
+        M, P = R * N, 1 + cfg.taps
+        table = p["neural_sdf.tcnn_encoding.params"]
+        prec = cfg.precision
+        X0 = self._f(P * M, K0_PAD)
+        call("mli_encode_rays", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
+             cfg.vol_range[0], cfg.vol_range[1], X0, K0_PAD)
+        H0 = self._f(P * M, HID)
+        call("mli_linear_fwd", X0, K0_PAD, 0, W["W0"], K0_PAD, 0, W["b0"], 0, H0, HID, 0, P * M, HID, K0_PAD,
+             ACT_SOFTPLUS100, 1, prec)
+        sdf = self._f(P * M)
+        call("mli_rowdot_fwd", H0, HID, P * M, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
+        XH = self._f(M, KH_PAD)
+        call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
+             prec)
+        gradients = self._f(M, 3)
+        hessians = self._f(M, 3) if training else None
+        call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
+             pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF)
+        A = [self._f(M, nh * HID) for _ in range(4)]
+        call("mli_linear_fwd", XH, KH_PAD, 0, W["Wh0"], KH_PAD, 0, W["bh"][0], 0, A[0], nh * HID, 0, M, nh * HID, KH_PAD,
+             ACT_RELU, 1, prec)
+        for l in range(3):
+            call("mli_linear_fwd", A[l], nh * HID, HID, W["Whl"][l], HID, HID * HID, W["bh"][l + 1], HID, A[l + 1],
+                 nh * HID, HID, M, HID, HID, ACT_RELU, nh, prec)
+        S = self._f(M, 8)
+        call("mli_rowdot_fwd", A[3], nh * HID, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
+             self.act_mask, S, 8)
+        ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
+                                 min(progress / cfg.anneal_end, 1.0))
+        weights, out = self._f(R, N), self._f(R, self.n_out)
+        extras = self._f(R, 5) if not training else None
+        call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, 8, R, None, weights, out,
+             extras)
+        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
+                   ccfg=ccfg, center=center, ray_unit=ray_unit, dists=dists, far=far, outside=outside)
+        res = dict(out=out, weights=weights, gradients=gradients, hessians=hessians, extras=extras, S=S, sdf=sdf)
+        return res, ctx
+
+    # ------------------------------------------------------------------------------------------------------
+    def backward(self, p, ctx, d_out, d_gradients=None, d_hessians=None, d_weights=None, need=("heads", "sdf", "table",
+                                                                                               "s_var")):
+        """Hand-written backward of forward().  Returns a dict {state-dict name: gradient}."""
+        cfg, W, nh = self.cfg, self.W, self.nh
+        R, M, P, N = ctx["R"], ctx["M"], ctx["P"], cfg.n_samples
+        prec = cfg.precision
+        need_sdf = ("sdf" in need) or ("table" in need)
+        grads = {}
+        d_grad = d_gradients.contiguous().clone() if d_gradients is not None else self._z(M, 3)
+        dS, d_sdf_c = self._f(M, 8), self._f(M)
+        d_svar = self._z(1) if "s_var" in need else None
+        call("mli_composite_bwd", ctx["ccfg"], p["s_var"], ctx["sdf"], ctx["gradients"], ctx["ray_unit"], ctx["dists"], N,
+             ctx["far"], ctx["S"], 8, R, ctx["weights"], d_out, d_weights, self.act_mask, dS, d_sdf_c, d_grad, d_svar, 0,
+             self._f(R) if d_svar is not None else None)
+        if d_svar is not None:
+            grads["s_var"] = d_svar.view(())
+        A = ctx["A"]
+        need_heads = "heads" in need
+        if not (need_heads or need_sdf):
+            return grads
+        # ---- heads ----------------------------------------------------------------------------------------
+        dZ = self._f(M, nh * HID)
+        dWout, dbout = self._f(self.J, HID), self._f(self.J)
+        ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(M, self.J, HID), dtype=torch.uint8, device=self.device)
+        call("mli_rowdot_bwd", dS, 8, A[3], nh * HID, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, nh * HID,
+             nh * HID, 0, dWout if need_heads else None, dbout, ws)
+        dWh = [None] * 3
+        dbh = [None] * 4
+        for l in (2, 1, 0):
+            if need_heads:
+                dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
+                wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, nh)
+                call("mli_linear_wgrad", dZ, nh * HID, HID, A[l], nh * HID, HID, dWh[l], HID, HID * HID, dbh[l + 1], HID,
+                     M, HID, HID, nh, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            dZp = self._f(M, nh * HID)
+            call("mli_linear_dgrad", dZ, nh * HID, HID, W["Whlt"][l], HID, HID * HID, A[l], nh * HID, HID, dZp, nh * HID,
+                 HID, M, HID, HID, ACT_RELU, 0, nh, prec)
+            dZ = dZp
+        if need_heads:
+            dWh0, dbh[0] = self._f(nh * HID, KH_PAD), self._f(nh * HID)
+            wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, nh * HID, KH_PAD, 1)
+            call("mli_linear_wgrad", dZ, nh * HID, 0, ctx["XH"], KH_PAD, 0, dWh0, KH_PAD, 0, dbh[0], 0, M, nh * HID, KH_PAD,
+                 1, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            j0 = 0
+            for hi, (name, kind, odim, _) in enumerate(self.heads):
+                pre = f"neural_rgb.{name}.linears."
+                k_in = len(_col_map(kind))
+                dv, dg = self._f(HID, k_in), self._f(HID, 1)
+                call("mli_weightnorm_unpack_grad", p[pre + "0.weight_v"], p[pre + "0.weight_g"], dWh0, KH_PAD, HID, k_in,
+                     self.map_head[hi], hi * HID, dv, dg)
+                grads[pre + "0.weight_v"], grads[pre + "0.weight_g"] = dv, dg
+                grads[pre + "0.bias"] = dbh[0][hi * HID:(hi + 1) * HID]
+                for l in range(3):
+                    dv, dg = self._f(HID, HID), self._f(HID, 1)
+                    call("mli_weightnorm_unpack_grad", p[pre + f"{l + 1}.weight_v"], p[pre + f"{l + 1}.weight_g"],
+                         dWh[l][hi], HID, HID, HID, None, 0, dv, dg)
+                    grads[pre + f"{l + 1}.weight_v"], grads[pre + f"{l + 1}.weight_g"] = dv, dg
+                    grads[pre + f"{l + 1}.bias"] = dbh[l + 1][hi * HID:(hi + 1) * HID]
+                dv, dg = self._f(odim, HID), self._f(odim, 1)
+                call("mli_weightnorm_unpack_grad", p[pre + "4.weight_v"], p[pre + "4.weight_g"], dWout, HID, odim, HID,
+                     None, j0, dv, dg)
+                grads[pre + "4.weight_v"], grads[pre + "4.weight_g"] = dv, dg
+                grads[pre + "4.bias"] = dbout[j0:j0 + odim]
+                j0 += odim
+        if not need_sdf:
+            return grads
+        # ---- SDF network ------------------------------------------------------------------------------------
+        XH = ctx["XH"]
+        dZ1 = self._f(M, HID)  # d pre-activation of SDF layer 1 = (dZ_head0 . Wh0[:, feat]) * softplus'(feat)
+        call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"], nh * HID, 0, XH, KH_PAD, 0, dZ1, HID, 0, M, nh * HID, HID,
+             ACT_SOFTPLUS100, 0, 1, prec)
+        dXx = self._f(M, KH_PAD - XH_OFF)  # d of the non-feature head inputs (only the normal columns are used)
+        call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"][XH_OFF:], nh * HID, 0, None, 0, 0, dXx, KH_PAD - XH_OFF, 0, M,
+             nh * HID, KH_PAD - XH_OFF, ACT_NONE, 0, 1, prec)
+        d_sdf = self._f(P * M)
+        call("mli_geometry_bwd", ctx["gradients"], M, N, cfg.taps, self.tap_eps, ctx["outside"], d_grad, d_hessians, dXx,
+             KH_PAD - XH_OFF, 0, d_sdf_c, d_sdf)
+        H0 = ctx["H0"]
+        train_mlp = "sdf" in need
+        if train_mlp:
+            dW1, db1 = self._f(HID, HID), self._f(HID)
+            wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, 1)
+            call("mli_linear_wgrad", dZ1, HID, 0, H0, HID, 0, dW1, HID, 0, db1, 0, M, HID, HID, 1, prec,
+                 torch.empty(wsb, dtype=torch.uint8, device=self.device))
+        dZ0 = self._f(P * M, HID)
+        call("mli_linear_dgrad", dZ1, HID, 0, W["W1t"], HID, 0, None, 0, 0, dZ0, HID, 0, M, HID, HID, ACT_NONE, 0, 1, prec)
+        dw_sdf, db_sdf = self._f(1, HID), self._f(1)
+        ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(P * M, 1, HID), dtype=torch.uint8, device=self.device)
+        # centre plane: accumulate onto the layer-1 path; tap planes: SDF head only
+        call("mli_rowdot_bwd", d_sdf, 1, H0, HID, M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100, dZ0, HID, HID, 1, None, None,
+             ws)
+        call("mli_rowdot_bwd", d_sdf[M:], 1, H0[M:], HID, (P - 1) * M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100, dZ0[M:],
+             HID, HID, 0, None, None, ws)
+        if train_mlp:
+            call("mli_rowdot_bwd", d_sdf, 1, H0, HID, P * M, W["w_sdf"], [0], 1, HID, ACT_NONE, None, 0, 0, 0, dw_sdf,
+                 db_sdf, ws)
+            dW0, db0 = self._f(HID, K0_PAD), self._f(HID)
+            wsb = _lib.load().mli_linear_wgrad_ws_bytes(P * M, HID, K0_PAD, 1)
+            call("mli_linear_wgrad", dZ0, HID, 0, ctx["X0"], K0_PAD, 0, dW0, K0_PAD, 0, db0, 0, P * M, HID, K0_PAD, 1, prec,
+                 torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            dv, dg = self._f(HID, 131), self._f(HID, 1)
+            call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.0.weight_v"],
+                 p["neural_sdf.mlp.linears.0.weight_g"], dW0, K0_PAD, HID, 131, self.map_sdf0, 0, dv, dg)
+            grads["neural_sdf.mlp.linears.0.weight_v"], grads["neural_sdf.mlp.linears.0.weight_g"] = dv, dg
+            grads["neural_sdf.mlp.linears.0.bias"] = db0
+            dv, dg = self._f(HID, HID), self._f(HID, 1)
+            call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.1.weight_v"],
+                 p["neural_sdf.mlp.linears.1.weight_g"], dW1, HID, HID, HID, None, 0, dv, dg)
+            grads["neural_sdf.mlp.linears.1.weight_v"], grads["neural_sdf.mlp.linears.1.weight_g"] = dv, dg
+            grads["neural_sdf.mlp.linears.1.bias"] = db1
+            grads["neural_sdf.mlp.linear_sdf.weight"], grads["neural_sdf.mlp.linear_sdf.bias"] = dw_sdf, db_sdf
+        if "table" in need:
+            dX0 = self._f(P * M, 128)
+            call("mli_linear_dgrad", dZ0, HID, 0, W["W0t"], HID, 0, None, 0, 0, dX0, 128, 0, P * M, HID, 128, ACT_NONE, 0,
+                 1, prec)
+            tg = self._z(self.n_table_params())
+            call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
+                 self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg)
+            grads["neural_sdf.tcnn_encoding.params"] = tg
+        return grads
+
+    # ------------------------------------------------------------------------------------------------------
+    def losses(self, lcfg, out, gradients, hessians, outside, targets):
+        """In-kernel losses + gradient seeds (NeuralLumen/trainer.py:133-149)."""
+        R, N = out.shape[0], self.cfg.n_samples
+        M = R * N
+        losses = self._f(8)
+        d_out, d_grad = self._f(R, self.n_out), self._f(M, 3)
+        d_hess = self._f(M, 3) if hessians is not None else None
+        ws = torch.empty(_lib.load().mli_losses_ws_bytes(R, M), dtype=torch.uint8, device=self.device)
+        call("mli_losses_fwd_bwd", lcfg, self.mode, out, gradients, hessians, outside, R, N, targets["image_sampled"],
+             targets.get("pseudo_ref_sampled"), targets.get("pseudo_sha_sampled"),
+             targets.get("pseudo_visibility_certainty_sampled"), losses, d_out, d_grad, d_hess, ws)
+        return losses, d_out, d_grad, d_hess

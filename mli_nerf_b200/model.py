@@ -1,0 +1,362 @@
+"""Drop-in replacement for ``projects.NeuralLumen.model`` (select it with ``--model.type=mli_nerf_b200.model``).
+
+Same constructor, ``forward(data)`` / ``inference(data)`` output dictionaries, trainer-facing attributes and
+``state_dict`` keys as the reference model (/root/reference/projects/NeuralLumen/model.py:17-131,422-438;
+projects/neuralangelo/model.py:29-60) -- but every FLOP of the render path runs in
+libmli_b200.so (hand-written sm_100a CUDA behind a C ABI).  PyTorch provides parameters, device memory, the stream
+and autograd glue only.  There is no CPU fallback: constructing works anywhere (checkpoints can be inspected on a
+CPU box), calling forward/inference without a B200-class GPU raises.
+"""
+import math
+from functools import partial
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import PathCfg, RenderEngine, head_layout, _col_map
+from .hashgrid import Encoding
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers: only hold tensors under the reference's names (no forward of their own)
+# ----------------------------------------------------------------------------------------------------------------
+class _WNLinear(torch.nn.Module):
+    """Old-style torch.nn.utils.weight_norm(Linear): parameters ``bias``, ``weight_g`` [out,1], ``weight_v`` [out,in]."""
+
+    def __init__(self, k_in, k_out, weight=None, bias=None):
+        super().__init__()
+        lin = torch.nn.Linear(k_in, k_out)  # default init (kaiming_uniform a=sqrt(5)), as the reference's heads
+        w = lin.weight.data if weight is None else weight
+        b = lin.bias.data if bias is None else bias
+        self.bias = torch.nn.Parameter(b.clone())
+        self.weight_g = torch.nn.Parameter(w.norm(dim=1, keepdim=True).clone())
+        self.weight_v = torch.nn.Parameter(w.clone())
+
+
+class _Params(torch.nn.Module):
+    pass
+
+
+def _head_mlp(k_in, k_out, hidden, n_hidden):
+    m = _Params()
+    dims = [k_in] + [hidden] * n_hidden + [k_out]
+    m.linears = torch.nn.ModuleList([_WNLinear(a, b) for a, b in zip(dims[:-1], dims[1:])])
+    m.linears[-1].bias.data.fill_(0.0)  # nerf_util.py:182-183
+    return m
+
+
+class NeuralSDF(torch.nn.Module):
+    """Parameter holder + schedule state of projects/neuralangelo/utils/modules.py:24-113 (NeuralSDF)."""
+
+    def __init__(self, cfg_sdf):
+        super().__init__()
+        self.cfg_sdf = cfg_sdf
+        enc, hg = cfg_sdf.encoding, cfg_sdf.encoding.hashgrid
+        if enc.type != "hashgrid":
+            raise NotImplementedError("Unknown encoding type")  # fourier SDF encoding: not on the shipped path
+        r_min, r_max = 2 ** hg.min_logres, 2 ** hg.max_logres
+        self.growth_rate = np.exp((np.log(r_max) - np.log(r_min)) / (enc.levels - 1))
+        self.tcnn_encoding = Encoding(3, dict(otype="HashGrid", n_levels=enc.levels, n_features_per_level=hg.dim,
+                                              log2_hashmap_size=hg.dict_size, base_resolution=r_min,
+                                              per_level_scale=self.growth_rate))
+        self.resolutions = [np.floor(r_min * self.growth_rate ** lv).astype(int) + 1 for lv in range(enc.levels)]
+        cfg_mlp = cfg_sdf.mlp
+        if cfg_mlp.num_layers != 1 or list(cfg_mlp.skip) or cfg_mlp.activ != "softplus" or not cfg_mlp.weight_norm:
+            raise NotImplementedError("SDF MLP variants other than the shipped 1-layer softplus/weight_norm one")
+        k_in, H = 3 + hg.dim * enc.levels, cfg_mlp.hidden_dim
+        # geometric init (mlp.py:71-84)
+        w0 = torch.randn(H, k_in) * math.sqrt(2 / H)
+        w0[:, 3:] = 0.0
+        w1 = torch.randn(H, H) * math.sqrt(2 / H)
+        self.mlp = _Params()
+        self.mlp.linears = torch.nn.ModuleList([_WNLinear(k_in, H, w0, torch.zeros(H)), _WNLinear(H, H, w1, torch.zeros(H))])
+        self.mlp.linear_sdf = torch.nn.Linear(H, 1)
+        torch.nn.init.normal_(self.mlp.linear_sdf.weight, mean=math.sqrt(math.pi / H), std=0.0001)
+        torch.nn.init.constant_(self.mlp.linear_sdf.bias, -cfg_mlp.out_bias)
+        if cfg_mlp.inside_out:
+            self.mlp.linear_sdf.weight.data *= -1
+            self.mlp.linear_sdf.bias.data *= -1
+        self.active_levels = enc.levels
+        self.anneal_levels = enc.levels
+        self.warm_up_end = 0
+        self.normal_eps = 1.0 / self.resolutions[-1]
+
+    def set_active_levels(self, current_iter=None):  # modules.py:97-100
+        c2f = self.cfg_sdf.encoding.coarse2fine
+        anneal_levels = max((current_iter - self.warm_up_end) // c2f.step, 1)
+        self.anneal_levels = min(self.cfg_sdf.encoding.levels, anneal_levels)
+        self.active_levels = max(c2f.init_active_level, self.anneal_levels)
+
+    def set_normal_epsilon(self):  # modules.py:102-107
+        if self.cfg_sdf.encoding.coarse2fine.enabled:
+            epsilon_res = self.resolutions[self.anneal_levels - 1]
+        else:
+            epsilon_res = self.resolutions[-1]
+        self.normal_eps = 1. / epsilon_res
+
+
+class LumenRGB(torch.nn.Module):
+    """Parameter holder of projects/NeuralLumen/utils/modules.py:9-104 (LumenRGB)."""
+
+    def __init__(self, cfg_rgb, feat_dim, appear_embed):
+        super().__init__()
+        if appear_embed.enabled:
+            raise NotImplementedError("appearance embedding (disabled in every NeuralLumen config)")
+        if cfg_rgb.encoding_view.type != "spherical" or cfg_rgb.encoding_view.levels != 3:
+            raise NotImplementedError("Unknown encoding type")
+        self.network_mode = getattr(cfg_rgb, "network_mode", None) or "rgb"
+        if self.network_mode == "rgb" and cfg_rgb.mode != "idr":
+            raise NotImplementedError("rgb mode variants no_view_dir / no_normal")
+        shading_dim = getattr(cfg_rgb, "shading_dim", 3)
+        for name, kind, odim, _ in head_layout(self.network_mode if self.network_mode != "rgb" else None):
+            if self.network_mode == "rgb_r_s" and name == "mlp_s":
+                odim = shading_dim
+                if odim != 1:
+                    raise NotImplementedError("rgb_r_s with shading_dim != 1")
+            setattr(self, name, _head_mlp(len(_col_map(kind)), odim, cfg_rgb.mlp.hidden_dim, cfg_rgb.mlp.num_layers))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class _RenderFunction(torch.autograd.Function):
+    """One autograd node for the whole render: forward and hand-written backward both run in libmli_b200."""
+
+    @staticmethod
+    def forward(ctx, model, center, ray_unit, pts_light, rands, training, names, *params):
+        eng = model.engine
+        p = dict(zip(names, params))
+        with torch.no_grad():
+            eng.pack_weights(p)
+            near, far, outside = eng.bounds(center, ray_unit)
+            dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], center, ray_unit, near, far, rands)
+            res, saved = eng.forward(p, center, ray_unit, pts_light, dists, near, far, outside, training, model.progress)
+        ctx.model, ctx.names, ctx.saved, ctx.params = model, names, saved, params
+        ctx.W = eng.W
+        out = res["out"]
+        hess = res["hessians"] if res["hessians"] is not None else out.new_zeros(0)
+        extras = res["extras"] if res["extras"] is not None else out.new_zeros(0)
+        ctx.mark_non_differentiable(dists, outside, extras)
+        return out, res["weights"], res["gradients"], hess, dists, outside, extras
+
+    @staticmethod
+    def backward(ctx, d_out, d_weights, d_gradients, d_hessians, *_):
+        model, eng, names = ctx.model, ctx.model.engine, ctx.names
+        p = dict(zip(names, ctx.params))
+        need_flags = ctx.needs_input_grad[7:]
+        need = set()
+        for n, f in zip(names, need_flags):
+            if not f:
+                continue
+            if n == "s_var":
+                need.add("s_var")
+            elif n == "neural_sdf.tcnn_encoding.params":
+                need.add("table")
+            elif n.startswith("neural_sdf."):
+                need.add("sdf")
+            else:
+                need.add("heads")
+        eng.W = ctx.W
+        if d_hessians is not None and d_hessians.numel() == 0:
+            d_hessians = None
+        with torch.no_grad():
+            grads = eng.backward(p, ctx.saved, d_out.contiguous() if d_out is not None else eng._z(ctx.saved["R"], eng.n_out),
+                                 d_gradients, d_hessians.contiguous() if d_hessians is not None else None,
+                                 d_weights.contiguous() if d_weights is not None else None, need=tuple(need))
+        ret = [grads.get(n) if f else None for n, f in zip(names, need_flags)]
+        return (None,) * 7 + tuple(ret)
+
+
+class Model(torch.nn.Module):
+
+    def __init__(self, cfg_model, cfg_data):
+        super().__init__()
+        self.cfg_render = cfg_model.render
+        self.white_background = cfg_model.background.white
+        self.with_background = cfg_model.background.enabled
+        self.with_appear_embed = cfg_model.appear_embed.enabled
+        self.anneal_end = cfg_model.object.s_var.anneal_end
+        self.outside_val = 1000. * (-1 if cfg_model.object.sdf.mlp.inside_out else 1)
+        self.image_size_train = cfg_data.train.image_size
+        self.image_size_val = cfg_data.val.image_size
+        if self.with_background:
+            raise NotImplementedError  # NeuralLumen/model.py:247-249 raises for every network_mode as well
+        if self.with_appear_embed:
+            raise NotImplementedError("appearance embedding (disabled in every NeuralLumen config)")
+        sdf_cfg = cfg_model.object.sdf
+        if sdf_cfg.gradient.mode != "numerical":
+            raise NotImplementedError("analytical gradient mode (not used by any shipped config)")
+        if sdf_cfg.gradient.taps not in (4, 6):
+            raise ValueError("Only support 4 or 6 taps.")
+        self.neural_sdf = NeuralSDF(sdf_cfg)
+        self.rgb_network_mode = getattr(cfg_model.object.rgb, "network_mode", None)
+        self.neural_rgb = LumenRGB(cfg_model.object.rgb, feat_dim=sdf_cfg.mlp.hidden_dim,
+                                   appear_embed=cfg_model.appear_embed)
+        self.background_nerf = None
+        self.appear_embed = self.appear_embed_outside = None
+        self.s_var = torch.nn.Parameter(torch.tensor(cfg_model.object.s_var.init_val, dtype=torch.float32))
+        if getattr(cfg_data, "bounding_type", None) == "box":
+            self.bounding_type = "box"
+            self.bounding_box_aabb = torch.tensor(cfg_data.bounding_box_aabb)
+        else:
+            self.bounding_type = "unit_sphere"
+        self.rand_rays_val = getattr(cfg_model.render, "rand_rays_val", cfg_model.render.rand_rays)
+        lv = getattr(cfg_model, "light_visibility", None)
+        self.flag_light_visibility = bool(lv is not None and lv.enabled)
+        if self.flag_light_visibility:
+            raise NotImplementedError("light_visibility (stage-a export) is a SURVEY section 8f 'next' row")
+        hg = sdf_cfg.encoding.hashgrid
+        ns = cfg_model.render.num_samples
+        self.path_cfg = PathCfg(
+            n_levels=sdf_cfg.encoding.levels, feat_per_level=hg.dim, log2_hashmap_size=hg.dict_size,
+            min_logres=hg.min_logres, max_logres=hg.max_logres, vol_range=(float(hg.range[0]), float(hg.range[1])),
+            hidden=sdf_cfg.mlp.hidden_dim, taps=sdf_cfg.gradient.taps, coarse=ns.coarse, fine=ns.fine,
+            hierarchy=cfg_model.render.num_sample_hierarchy, sh_levels=cfg_model.object.rgb.encoding_view.levels,
+            network_mode=self.rgb_network_mode, white_background=bool(self.white_background),
+            anneal_end=self.anneal_end, outside_val=self.outside_val,
+            bounding="box" if self.bounding_type == "box" else "unit_sphere",
+            aabb=tuple(float(v) for v in cfg_data.bounding_box_aabb) if self.bounding_type == "box" else None,
+            c2f_enabled=bool(sdf_cfg.encoding.coarse2fine.enabled),
+            precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[getattr(cfg_model, "mli_precision", "fp32")])
+        self.progress = 1.0
+        self._engine = None
+        self.max_rays_per_launch = 8192
+
+    # -- trainer-facing helpers (imaginaire/models/base.py:16-30; NeuralLumen/model.py:422-438) ---------------------
+    def device(self):
+        return next(self.parameters()).device
+
+    def get_param_groups(self, cfg_optim):
+        if hasattr(cfg_optim, "partial_training"):
+            keyword_list = cfg_optim.partial_training
+            return [param for name, param in self.named_parameters() if any(k in name for k in keyword_list)]
+        return self.parameters()
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            dev = self.device()
+            if dev.type != "cuda" or not _lib.device_ok():
+                raise _lib.MliError("mli_nerf_b200.Model needs a B200-class CUDA device: the render path has no CPU "
+                                    "fallback (parameters live on %s)" % dev)
+            self._engine = RenderEngine(self.path_cfg, dev)
+        eng = self._engine
+        eng.normal_eps = float(self.neural_sdf.normal_eps)
+        eng.set_active_levels(self.neural_sdf.active_levels)
+        return eng
+
+    def _named(self):
+        names, params = [], []
+        for n, p in self.named_parameters():
+            names.append(n)
+            params.append(p)
+        return tuple(names), params
+
+    # -- rays ---------------------------------------------------------------------------------------------------------
+    def _rays(self, pose, intr, pose_light, image_size, ray_idx):
+        B = pose.shape[0]
+        R = ray_idx.shape[1] if ray_idx is not None else image_size[0] * image_size[1]
+        f = partial(torch.empty, dtype=torch.float32, device=pose.device)
+        center, ray_unit, light, norm = f(B * R, 3), f(B * R, 3), f(B * R, 3), f(B * R)
+        _lib.call("mli_rays_from_pose", pose.contiguous().float(), intr.contiguous().float(),
+                  pose_light.contiguous().float(), ray_idx.contiguous() if ray_idx is not None else None, B, R,
+                  int(image_size[1]), center, ray_unit, norm, light)
+        return center, ray_unit, light, norm
+
+    def render_rays_lumen(self, center, ray_unit, pts_light, sample_idx=None, stratified=False, rands=None):
+        """[B,R,3] rays -> the reference's output dict (NeuralLumen/model.py:232-336)."""
+        B, R = center.shape[:2]
+        c, r, l = (t.reshape(B * R, 3).contiguous().float() for t in (center, ray_unit, pts_light))
+        if stratified and rands is None:
+            rands = torch.rand(B, R, self.path_cfg.coarse, 1, device=c.device)  # nerf_util.py:33, same shape/order
+        if rands is not None:
+            rands = rands.reshape(B * R, self.path_cfg.coarse).contiguous()
+        names, params = self._named()
+        out, weights, gradients, hess, dists, outside, extras = _RenderFunction.apply(
+            self, c, r, l, rands, self.training, names, *params)
+        N = self.path_cfg.n_samples
+        res = dict(rgb=out[:, 0:3].view(B, R, 3), opacity=None, outside=outside.view(B, R, 1).bool(),
+                   dists=dists.view(B, R, N, 1), weights=weights.view(B, R, N, 1), gradient=None,
+                   gradients=gradients.view(B, R, N, 3), hessians=hess.view(B, R, N, 3) if self.training else None)
+        m = self.rgb_network_mode
+        if m == "rgb_r_s":
+            res.update(o_r=out[:, 3:6].view(B, R, 3), o_s=out[:, 6:7].view(B, R, 1), o_re=out[:, 7:10].view(B, R, 3))
+        elif m in ("rgb_r", "r_s"):
+            res.update(o_r=out[:, 3:6].view(B, R, 3), o_s=out[:, 6:9].view(B, R, 3))
+        elif m == "r_s_re":
+            res.update(o_r=out[:, 3:6].view(B, R, 3), o_s=out[:, 6:9].view(B, R, 3), o_re=out[:, 9:12].view(B, R, 3))
+        if not self.training:
+            res["opacity"] = extras[:, 0:1].view(B, R, 1)
+            res["gradient"] = extras[:, 1:4].view(B, R, 3)
+            res["_dist"] = extras[:, 4:5].view(B, R, 1)
+        return res
+
+    def forward(self, data):
+        """NeuralLumen/model.py:113-131."""
+        pose = data["pose"]
+        B, R = data["ray_idx"].shape
+        c, r, l, _ = self._rays(pose, data["intr"], data["pose_light"], self.image_size_train, data["ray_idx"])
+        return self.render_rays_lumen(c.view(B, R, 3), r.view(B, R, 3), l.view(B, R, 3), sample_idx=data.get("idx"),
+                                      stratified=self.cfg_render.stratified)
+
+    @torch.no_grad()
+    def fused_train_step(self, data, loss_cfg, accumulate=False):
+        """forward + in-kernel losses + hand-written backward in one pass (no autograd graph).
+
+        Equivalent to ``total = trainer.model_forward(data); total.backward()`` of the reference
+        (projects/nerf/trainers/base.py:99-107, NeuralLumen/trainer.py:133-149,189-196): fills ``.grad`` of every
+        parameter with ``requires_grad`` and returns the device tensor of losses (see _lib.LOSS_NAMES)."""
+        eng = self.engine
+        B, R = data["ray_idx"].shape
+        c, r, l, _ = self._rays(data["pose"], data["intr"], data["pose_light"], self.image_size_train, data["ray_idx"])
+        names, params = self._named()
+        p = dict(zip(names, params))
+        rands = None
+        if self.cfg_render.stratified:
+            rands = torch.rand(B, R, self.path_cfg.coarse, 1, device=c.device).view(B * R, self.path_cfg.coarse)
+        eng.pack_weights(p)
+        near, far, outside = eng.bounds(c, r)
+        dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], c, r, near, far, rands)
+        res, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, self.progress)
+        tg = {k: v.reshape(B * R, -1) for k, v in data.items() if k.endswith("_sampled")}
+        losses, d_out, d_grad, d_hess = eng.losses(loss_cfg, res["out"], res["gradients"], res["hessians"], outside, tg)
+        need = set()
+        for n, q in zip(names, params):
+            if q.requires_grad:
+                need.add("s_var" if n == "s_var" else "table" if n == "neural_sdf.tcnn_encoding.params"
+                         else "sdf" if n.startswith("neural_sdf.") else "heads")
+        grads = eng.backward(p, ctx, d_out, d_grad, d_hess, None, need=tuple(need))
+        for n, q in zip(names, params):
+            if q.requires_grad and n in grads:
+                g = grads[n].view_as(q)
+                if accumulate and q.grad is not None:
+                    q.grad.add_(g)
+                else:
+                    q.grad = g
+        self._last_render = res
+        return losses
+
+    @torch.no_grad()
+    def inference(self, data):
+        """NeuralLumen/model.py:60-111: full-image render in chunks of rand_rays_val rays, eval outputs + *_map."""
+        self.eval()
+        pose = data["pose"]
+        B = pose.shape[0]
+        H, W = self.image_size_val
+        c, r, l, norm = self._rays(pose, data["intr"], data["pose_light"], self.image_size_val, None)
+        c, r, l, norm = c.view(B, H * W, 3), r.view(B, H * W, 3), l.view(B, H * W, 3), norm.view(B, H * W, 1)
+        chunks = []
+        for s in range(0, H * W, self.rand_rays_val):
+            e = min(H * W, s + self.rand_rays_val)
+            o = self.render_rays_lumen(c[:, s:e], r[:, s:e], l[:, s:e], stratified=False)
+            o["depth"] = o.pop("_dist") / norm[:, s:e]
+            chunks.append(o)
+        output = {k: torch.cat([ch[k] for ch in chunks], dim=1) for k, v in chunks[0].items() if v is not None}
+        rot = pose[..., :3, :3]
+        normal_cam = -output["gradient"] @ rot.transpose(-1, -2)
+        to_img = lambda x: x.unflatten(dim=1, sizes=(H, W)).moveaxis(-1, 1)  # misc.py:110-117
+        output.update(rgb_map=to_img(output["rgb"]), opacity_map=to_img(output["opacity"]),
+                      depth_map=to_img(output["depth"]), normal_map=to_img(normal_cam))
+        for key in ("o_r", "o_s", "o_re"):
+            if key in output:
+                output[key + "_map"] = to_img(output[key])
+        return output
