@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/s (forward + backward) of the NeuralLumen render hot path on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W                 (N>1: launched through torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W   CPU reference arm (oracle port, host cores)
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C1"): syn_hotdog_b shape -- Neuralangelo hash grid
+(16 levels x 8 features, 2^22 entries/level), 2048 rays x 128 samples per step and GPU, 4 gradient taps, rgb_r_s heads,
+all five losses, FULL-GRAD (every parameter incl. the 1.46 GB hash table receives a gradient), synthetic rays from a
+pinhole camera at distance 3 (f = 711 px, 512x512), random-init weights (reference init).  One "step" = ray generation
++ bounds + hierarchical sampling + forward + in-kernel losses + full backward (optimizer excluded, as in the metric);
+with N>1 ranks it also includes the NCCL all-reduce(mean) of all parameter gradients.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAYS = 2048
+N_SAMPLES = 128
+METRIC = "train_rays_per_sec_fwd_bwd"
+UNIT = "rays/s"
+# algorithmic MLP flops per ray, fwd+bwd, 4 taps, full-grad (unpadded layer shapes)
+MLP_FLOP_PER_RAY = 806.0e6
+WORKLOAD = "syn_hotdog_b shape: hash grid 16x8 T=2^22, 2048 rays x 128 samples/GPU, 4 taps, rgb_r_s, 5 losses, full-grad"
+
+
+def synthetic_batch(R, seed, H=512, W=512):
+    """One frame worth of training data in the reference's `data` dict format."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    # camera on a radius-3 sphere looking at the origin (world->camera [R|t]), point light at radius 4
+    d = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
+    eye = 3.0 * d
+    z = -d
+    up = torch.tensor([0.0, 0.0, 1.0]) if abs(float(d[2])) < 0.9 else torch.tensor([0.0, 1.0, 0.0])
+    x = torch.nn.functional.normalize(torch.linalg.cross(z, up), dim=0)
+    y = torch.linalg.cross(z, x)
+    Rm = torch.stack([x, y, z])  # rows = camera axes in world coordinates
+    pose = torch.cat([Rm, (-Rm @ eye)[:, None]], dim=1)[None]
+    lp = 4.0 * torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0)
+    pose_light = torch.cat([torch.eye(3), (-lp)[:, None]], dim=1)[None]
+    intr = torch.tensor([[[711.0, 0.0, W / 2], [0.0, 711.0, H / 2], [0.0, 0.0, 1.0]]])
+    ray_idx = torch.randperm(H * W, generator=g)[:R][None]
+    return dict(pose=pose.float(), intr=intr, pose_light=pose_light.float(), ray_idx=ray_idx,
+                idx=torch.zeros(1, dtype=torch.long),
+                image_sampled=torch.rand(1, R, 3, generator=g), pseudo_ref_sampled=torch.rand(1, R, 3, generator=g),
+                pseudo_sha_sampled=torch.rand(1, R, 1, generator=g),
+                pseudo_visibility_certainty_sampled=torch.rand(1, R, 1, generator=g))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop = index, [], set(), threading.Event()
+        self.sm_max = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [v.strip() for v in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.sm_max = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(n_rays, threads, seed=0, state={}):
+    """One fwd+bwd of the oracle port (torch CPU, all host threads) on n_rays rays of the bench workload."""
+    import torch
+    from oracle import port
+    torch.set_num_threads(threads)
+    if "p" not in state:
+        cfg = port.PathConfig(log2_hashmap_size=22)
+        state["cfg"] = cfg
+        state["p"] = {k: v.requires_grad_(True) for k, v in port.init_params(cfg, seed=0, generic=False).items()}
+    cfg, p = state["cfg"], state["p"]
+    b = synthetic_batch(n_rays, seed)
+    c, ray, l = port.rays_from_pose(b["pose"], b["intr"], b["pose_light"], (512, 512), b["ray_idx"])
+    t0 = time.perf_counter()
+    for v in p.values():
+        v.grad = None
+    out = port.render_rays(p, cfg, c, torch.nn.functional.normalize(ray, dim=-1), l,
+                           rands=torch.rand(1, n_rays, cfg.coarse, 1), training=True, progress=0.5)
+    total, _, _ = port.total_loss(cfg, out, b)
+    total.backward()
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm on the host cores (oracle port: the reference is Python that only
+    exists in the build container; port.py is pinned against it by tests/test_oracle_vs_reference.py + tests/golden)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: size the per-step ray count so that warmup+steps finish in ~2.5 minutes
+    n = 64
+    t = cpu_reference_step(n, threads, seed=100)  # also builds the 1.46 GB table
+    t = cpu_reference_step(n, threads, seed=101)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_rays = int(max(32, min(RAYS, n * budget / max(t, 1e-3))))
+    n_rays = 1 << (n_rays.bit_length() - 1)
+    for i in range(args.warmup):
+        cpu_reference_step(n_rays, threads, seed=200 + i)
+    times = [cpu_reference_step(n_rays, threads, seed=300 + i) for i in range(args.steps)]
+    total = sum(times)
+    value = n_rays * args.steps / total
+    sample = f"{n_rays} of the {RAYS} rays of one step (x{N_SAMPLES} samples), fwd+bwd, all 5 losses, fp32 torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step": n_rays},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MLI_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--grad", default="full", choices=["full", "heads"], help="full-grad (primary) or stage-b as shipped")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dict-size", type=int, default=22)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mli_nerf_b200 import _lib, config
+    from mli_nerf_b200.dist import GradReducer
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    from mli_nerf_b200.model import Model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert max(1, args.warmup) >= 1
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert _lib.device_ok(), "bench needs a B200 (no CPU fallback)"
+
+    cfg = config.experiment("syn_hotdog_b", dict_size=args.dict_size, rand_rays=RAYS)
+    cfg.model.mli_precision = args.precision
+    torch.manual_seed(0)
+    model = Model(cfg.model, cfg.data).cuda().train()
+    model.progress = 0.5
+    if args.grad == "heads":
+        for n, p in model.named_parameters():
+            p.requires_grad_("neural_rgb" in n)
+    lcfg = loss_cfg_from_trainer(cfg.trainer)
+    reducer = GradReducer(model, world) if world > 1 else None
+
+    n_batches = 8
+    host = [{k: v.pin_memory() for k, v in synthetic_batch(RAYS, 1000 * rank + i).items()} for i in range(n_batches)]
+    dev = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def step(batch):
+        losses = model.fused_train_step(batch, lcfg)
+        if reducer is not None:
+            reducer.allreduce_grads()
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(dev[i % n_batches])
+    barrier()
+
+    # ---- device-resident timing (value) + per-entry-point CUDA-event profile + clocks ------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.LAUNCH_COUNT = 0
+    _lib.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(dev[i % n_batches])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_end()
+    launches = _lib.LAUNCH_COUNT
+    clocks = sampler.stop()
+
+    # ---- end-to-end timing: pinned host inputs -> H2D, step, loss -> D2H, every step ------------------------------
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    d2h = 0
+    for i in range(args.steps):
+        b = {k: v.cuda(non_blocking=True) for k, v in host[i % n_batches].items()}
+        lv = step(b).cpu()
+        d2h = lv.numel() * lv.element_size()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * RAYS * args.steps / (ms * 1e-3)
+    e2e = world * RAYS * args.steps / (ms_e2e * 1e-3)
+    hbm_peak, tf_peak, peak_src = peaks()
+    dense = [k for k in prof if k.startswith("mli_linear") or k.startswith("mli_rowdot")]
+    dense_ms = sum(prof[k][1] for k in dense)
+    frac_flops = 1.0 if args.grad == "full" else 631.3 / 806.0
+    achieved_tf = MLP_FLOP_PER_RAY * frac_flops * RAYS * args.steps / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "grad": args.grad, "precision": args.precision, "rays_per_gpu": RAYS,
+                   "samples_per_ray": N_SAMPLES, "l2": "inputs larger than L2: 1.46 GB hash table + 1.46 GB gradient "
+                   "buffer streamed every step (L2 = 126 MB), 8 rotating ray batches"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "dense layers (mli_linear_fwd/dgrad/wgrad + rowdot)",
+                     "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "share_of_step": dense_ms / ms if ms > 0 else None},
+        "profile_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n = 256
+        cpu_reference_step(64, threads, seed=1)  # warm-up (allocates the table)
+        t = cpu_reference_step(n, threads, seed=2)
+        line["cpu_baseline"] = {"value": n / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n} of the {RAYS} rays of one step (x{N_SAMPLES} samples), fwd+bwd, all 5 "
+                                          f"losses, oracle port (fp32 torch CPU), {t:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -141,8 +141,52 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-entry-point timing (CUDA events on the launching stream) used by bench.py ---------------------
+_PROFILE = None
+LAUNCH_COUNT = 0
+
+
+def profile_begin():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_end():
+    """-> {entry point: (calls, total ms)}; synchronises."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (prof or {}).items()}
+
+
+def _n_launches(name, args):
+    """How many of our kernels one call launches (for bench.py's gpu_launches claim)."""
+    if name == "mli_linear_wgrad":
+        return 2
+    if name == "mli_rowdot_bwd":
+        return (1 if args[10] is not None else 0) + (2 if args[14] is not None else 0)
+    if name == "mli_composite_bwd":
+        return 1 + (1 if args[18] is not None else 0)
+    if name == "mli_losses_fwd_bwd":
+        return 3 + (1 if args[0].has_intrinsic else 0)
+    return 1
+
+
 def call(name, *args):
     """Invoke an entry point; tensors -> device pointers, 's' slot filled with the current stream when omitted."""
+    global LAUNCH_COUNT
+    if _PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _call(name, *args)
+        b.record()
+        _PROFILE.setdefault(name, []).append((a, b))
+    else:
+        _call(name, *args)
+    LAUNCH_COUNT += _n_launches(name, args)
+
+
+def _call(name, *args):
     lib = load()
     sig = _SIGS[name]
     if len(args) == len(sig) - 1:
