@@ -243,8 +243,13 @@ def test_render_forward_backward_vs_oracle(lib, mode, bounding, taps, white):
     assert torch.allclose(res["sdf"].cpu()[:R * N].view(R, N), out_ref["sdfs"][0, :, :, 0], rtol=1e-3, atol=1e-5)
     g_ref = out_ref["gradients"][0]
     assert rel_err(res["gradients"].cpu().view(R, N, 3)[inside], g_ref[inside]) < 2e-3
+    # Hessian = second difference / e^2 with e^2 ~ 8e-8: every fp32 ulp of |sdf| is worth ulp/e^2 (1.5 at |sdf| = 1) in
+    # BOTH implementations, so the bound is a few ulps of the stencil's SDF magnitude.
     h_ref = out_ref["hessians"][0]
-    assert float((res["hessians"].cpu().view(R, N, 3)[inside] - h_ref[inside]).abs().max()) < 2.0  # atol ~1, see module doc
+    e2 = (ocfg.normal_eps / math.sqrt(3)) ** 2 if taps == 4 else ocfg.normal_eps ** 2
+    tol = 12 * 1.2e-7 * (out_ref["sdfs"][0].abs() + 0.1) / e2 + 2e-3 * h_ref.abs()
+    dh = (res["hessians"].cpu().view(R, N, 3) - h_ref).abs()
+    assert bool((dh[inside] <= tol[inside]).all()), float((dh[inside] / tol[inside]).max())
     assert torch.allclose(res["weights"].cpu(), out_ref["weights"][0, :, :, 0], rtol=1e-3, atol=2e-5)
     # per-ray outputs
     out = res["out"].cpu()
@@ -263,15 +268,40 @@ def test_render_forward_backward_vs_oracle(lib, mode, bounding, taps, white):
         if k in losses_ref:
             assert abs(float(lc[i]) - float(losses_ref[k])) < 1e-3 * abs(float(losses_ref[k])) + 1e-6, k
     assert abs(float(lc[3]) - float(losses_ref["curvature"])) < 2e-3 * abs(float(losses_ref["curvature"])) + 1e-3
-    # backward
-    grads = eng.backward(p, ctx, d_out, d_grad, d_hess, None)
-    worst = {}
-    for k, v in pp.items():
-        assert k in grads, k
-        worst[k] = rel_err(grads[k].cpu().view_as(v.grad), v.grad)
-    bad = {k: e for k, e in worst.items() if e > 5e-3}
-    assert not bad, bad
+
+    def compare(grads, loose=()):
+        worst = {}
+        for k, v in pp.items():
+            assert k in grads, k
+            worst[k] = rel_err(grads[k].cpu().view_as(v.grad), v.grad)
+        bad = {k: e for k, e in worst.items() if e > (1e-1 if any(t in k for t in loose) else 5e-3)}
+        assert not bad, bad
+        return worst
+
+    # (a) every loss term, with the curvature term replaced by a SMOOTH functional of the Hessians
+    #     (sum(hessians * H)): |laplacian| makes the seed sign(lap), which flips on fp32 noise in both implementations.
+    g = torch.Generator().manual_seed(9)
+    Hs = (torch.rand(R, N, 3, generator=g) * 2 - 1) * (5e-4 / (R * N)) * (~out_ref["outside"][0]).float()[:, None, :]
+    for v in pp.values():
+        v.grad = None
+    out2 = port.render_rays(pp, ocfg, case["center"], case["ray_unit"], case["light"], rands=case["rands"],
+                            training=True, progress=case["progress"])
+    ocfg0 = port.PathConfig(**{**ocfg.__dict__, "w_curvature": 0.0})
+    (port.total_loss(ocfg0, out2, targets)[0] + (out2["hessians"][0] * Hs).sum()).backward()
+    lcfg0 = loss_cfg(ocfg0, has_intrinsic=(mode == "rgb_r_s"))
+    _, d_out0, d_grad0, _ = eng.losses(lcfg0, res["out"], res["gradients"], res["hessians"], outside, tg)
+    worst = compare(eng.backward(p, ctx, d_out0, d_grad0, cu(Hs.view(R * N, 3)), None))
     assert sorted(worst.values())[len(worst) // 2] < 1e-3  # median well inside rtol 1e-3
+    # (b) the real 5-term loss incl. curvature: SDF-side gradients inherit the sign(lap) noise
+    for v in pp.values():
+        v.grad = None
+    out3 = port.render_rays(pp, ocfg, case["center"], case["ray_unit"], case["light"], rands=case["rands"],
+                            training=True, progress=case["progress"])
+    port.total_loss(ocfg, out3, targets)[0].backward()
+    compare(eng.backward(p, ctx, d_out, d_grad, d_hess, None), loose=("neural_sdf",))
+    # heads-only backward (stage b as shipped) returns only neural_rgb gradients
+    g_heads = eng.backward(p, ctx, d_out, d_grad, d_hess, None, need=("heads",))
+    assert g_heads and all(k.startswith("neural_rgb") for k in g_heads)
 
 
 def test_model_dropin_end_to_end(lib):
@@ -350,9 +380,17 @@ def test_model_inference_outputs(lib):
     c, ray, l = port.rays_from_pose(pose, intr, pose_light, (40, 50), torch.arange(2000)[None])
     ref = port.render_rays(case["params"], case["ocfg"], c, torch.nn.functional.normalize(ray, dim=-1), l, rands=None,
                            training=False, progress=1.0)
-    close = (out["dists"].cpu()[0, :, :, 0] - ref["dists"][0, :, :, 0]).abs().amax(dim=1) < 1e-3
-    assert close.float().mean() > 0.6
-    for k in ("rgb", "opacity", "o_r", "o_s"):
-        assert torch.allclose(out[k].cpu()[0][close], ref[k][0][close].detach(), rtol=2e-3, atol=1e-4), k
+    # Hierarchical sampling amplifies fp32 rounding (inv_s up to 512 per round), so independently sampled distances
+    # agree exactly on most rays and to ~1e-4..1e-2 on the rest; outputs are compared tightly where the samples agree
+    # and statistically everywhere.
+    same = (out["dists"].cpu()[0, :, :, 0] - ref["dists"][0, :, :, 0]).abs().amax(dim=1) < 1e-6
+    assert same.float().mean() > 0.4
     depth_ref = (ref["dists"] * ref["weights"]).sum(2) / ray.norm(dim=-1, keepdim=True)
-    assert torch.allclose(out["depth"].cpu()[0][close], depth_ref[0][close].detach(), rtol=2e-3, atol=1e-4)
+    refs = dict(rgb=ref["rgb"], opacity=ref["opacity"], o_r=ref["o_r"], o_s=ref["o_s"], o_re=ref["o_re"], depth=depth_ref,
+                gradient=ref["gradient"])
+    for k, v in refs.items():
+        a, b = out[k].cpu()[0], v[0].detach()
+        assert torch.allclose(a[same], b[same], rtol=2e-3, atol=2e-4), k
+        if k != "gradient":
+            assert ((a - b).abs().amax(dim=-1) < 2e-2).float().mean() > 0.97, k
+    assert torch.equal(out["outside"].cpu(), ref["outside"])
