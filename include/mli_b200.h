@@ -114,6 +114,44 @@ int mli_linear_wgrad(const float* dZ, int64_t lddz, int64_t sdz, const float* X,
                      float* dW, int64_t lddw, int64_t sdw, float* db, int64_t sdb, int64_t M, int32_t N_out,
                      int32_t K_in, int32_t batch, int32_t prec, void* ws, void* stream);
 
+/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA bulk copies), see csrc/gemm_tcgen05.cu ---------------------------
+ * Activations and their gradients live in HBM as bf16 in "TCL" (tile-chunk layout): a matrix X[M, C] (C % 8 == 0) is
+ * stored as [ceil(M/128)][C/8][128][8]; element (m, c) -> (((m/128)*(C/8) + c/8)*128 + m%128)*8 + c%8.  Buffers are
+ * padded to whole 128-row tiles; padding rows must be zero wherever the matrix is later contracted over rows.
+ * A "chunk" is 8 columns.  Weights use the same layout with the tile height equal to the N tile (BN) of the GEMM. */
+
+/* fp32 row-major [M, cols] (ld) -> chunks [chunk0, chunk0+n_chunks) of a bf16 TCL matrix with `dst_chunks` chunks per
+ * tile row and `tile_rows`-row tiles; rows >= M / columns >= cols are zero-filled. */
+int mli_tc_to_tcl(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
+                  int32_t dst_chunks, int32_t chunk0, int32_t n_chunks, void* stream);
+int mli_tc_from_tcl(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* dst,
+                    int64_t ld, void* stream);
+/* Forward / data-gradient GEMM on TCL operands, fused epilogue:
+ *   epi 0: out = act(A W^T + bias)           epi 1: out = (A W^T) * act'(aux)   (aux = layer output, TCL bf16, or NULL)
+ * A: TCL-128 activations, columns [8*(a_chunk0 + b*a_batch_chunks), +K) for batch member b.
+ * B: weights [N, K] in TCL with BN-row tiles ([N/BN][K/8][BN][8]), b_batch_elems elements between batch members.
+ * out: bf16 TCL-128 (out_chunks per tile row, first chunk out_chunk0 + b*out_batch_chunks) or, if out_is_f32, fp32
+ * row-major (ldo; first column out_col0 + b*out_batch_cols; rows >= M are not written). */
+int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
+                  int64_t b_batch_elems, int32_t K, int32_t N, int32_t BN, const float* bias, int32_t bias_batch,
+                  const void* aux, int32_t aux_chunks, int32_t aux_chunk0, int32_t aux_batch_chunks, int32_t act,
+                  void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
+                  int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
+                  void* stream);
+/* Weight-gradient GEMM: out[b][r, c] = sum_m L[m, 8*(l_chunk0 + b*l_batch_chunks) + r] * R[m, 8*(r_chunk0 +
+ * b*r_batch_chunks) + c]; r < rows_out (multiple of 128), c < cols_out (multiple of 16; < 256 or a multiple of 256).
+ * L, R: TCL-128 (the same bytes serve as MN-major operands).  Split over row tiles, deterministic reduction.
+ * transpose_out: write out[c, r] instead. */
+int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch);
+int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                 int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                 int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                 int32_t transpose_out, void* ws, void* stream);
+/* Column sums (bias gradients) of chunks [chunk0, chunk0+n_chunks) of a TCL-128 matrix -> out[8*n_chunks]. */
+int64_t mli_tc_colsum_ws_bytes(int64_t M, int32_t n_chunks);
+int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* out, void* ws,
+                  void* stream);
+
 /* Narrow output layers (SDF head 256->1, mlp.py:50,66; head output layers 256->3/3/1, nerf_util.py:191):
  * out[m, j] = act_j(sum_k A[m, col_off[j] + k] * w[j, k] + b[j]),  j < J <= 8, k < K; act_j = act if bit j of
  * act_mask is set, identity otherwise (network_mode r_s leaves o_s without a sigmoid, modules.py:119).

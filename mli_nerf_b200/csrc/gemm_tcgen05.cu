@@ -1,9 +1,585 @@
-// gemm_tcgen05.cu -- bf16 tensor-core (tcgen05 / TMEM / TMA) path of the dense layers.  PLACEHOLDER: filled in
-// once the fp32 path is parity-green on the GPU.
+// gemm_tcgen05.cu -- bf16 dense layers on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands fed by TMA bulk copies, mbarrier pipelines).  sm_100a only.
+//
+// Replaces torch.nn.Linear (+activation) forward/backward of /root/reference/projects/neuralangelo/utils/mlp.py:55-69
+// and /root/reference/projects/nerf/utils/nerf_util.py:186-196 in the "bf16 MLP tile" mode of the north star.
+//
+// HBM layout ("TCL", tile-chunk layout) of every activation / gradient matrix X[M, C] in this mode:
+//     bf16 [M/128][C/8][128][8]         element (m, c) -> (((m/128)*(C/8) + c/8)*128 + m%128)*8 + c%8
+// i.e. per 128-row tile, per 8-column chunk, 128 rows x 16 bytes contiguous.  This is exactly the un-swizzled UMMA
+// "core matrix" arrangement, so
+//   * a [128 rows x 8j columns] operand block is ONE contiguous byte range -> one cp.async.bulk (TMA, UBLKCP) per
+//     operand per pipeline stage, landing in shared memory already in canonical K-major layout (LBO = 2048 B between
+//     8-column chunks, SBO = 128 B between 8-row groups);
+//   * the SAME bytes are a canonical MN-major operand for the weight-gradient GEMM (contraction over the 128 rows:
+//     LBO = 128 B between 8-row groups, SBO = 2048 B between 8-column chunks), so dW = dZ^T X needs no transposed copy;
+//   * epilogues write 16 B per thread with the 32 lanes of a warp covering 512 contiguous bytes.
+// Weights use the same layout with the tile height equal to the CTA's N tile (BN <= 256).
+//
+// NT kernel (forward / data gradient): one CTA = one [128 x BN] output tile, K streamed in stages of 64 through a
+// 2-stage smem ring; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator), warps 2..5 = epilogue
+// (tcgen05.ld -> bias/activation or activation-derivative -> bf16 TCL or fp32 row-major store).  Two CTAs per SM
+// (2 x 96 KB smem, 2 x 256 TMEM columns) so one tile's epilogue overlaps the other's MMAs.
+// TN kernel (weight gradient): one CTA = one [128 x BN] tile of dW^T-free dW, contraction over row tiles split across
+// CTAs, fp32 partials + fixed-order reduction (deterministic).
+// Roofline: tensor pipe (2 * M * N * K flops per call); operands stream from L2/HBM at (128+BN)*2 B per 128*BN MACs.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-int mli_tc_linear_fwd(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const float*, int64_t, float*,
-                      int64_t, int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, void*) {
-  mli_set_error("bf16 tcgen05 path not built yet");
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kStageChunks = 8;   // 8 chunks x 8 columns = 64-wide K stage
+constexpr int kNT_Stages = 2;
+constexpr int kThreads = 192;     // 6 warps
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// un-swizzled ("interleave") shared-memory matrix descriptor, sm_100 version bits set
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : 256; }
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+  o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
+  return o;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NT kernel: out[128 x BN tile] = epi(A[128 x K] . B[BN x K]^T)
+// ---------------------------------------------------------------------------------------------------------------
+enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1 };
+
+struct TcNT {
+  const __nv_bfloat16* A; int a_chunks, a_chunk0, a_batch_chunks;   // TCL-128, chunks per tile row, first chunk
+  const __nv_bfloat16* B; int64_t b_batch_elems;                    // TCL-BN [N/BN][K/8][BN][8] per batch
+  int k_chunks, BN;
+  const float* bias; int bias_batch;
+  const __nv_bfloat16* aux; int aux_chunks, aux_chunk0, aux_batch_chunks;
+  void* out; int out_chunks, out_chunk0, out_batch_chunks;          // bf16 TCL-128 ...
+  int64_t ldo; int out_col0, out_batch_cols;                        // ... or fp32 row-major
+  int64_t M;
+  int act;
+};
+
+template <int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * kNT_Stages + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, batch = blockIdx.z;
+  const int BN = p.BN;
+  const uint32_t a_stage_bytes = kStageChunks * kTileM * 16, b_stage_bytes = kStageChunks * BN * 16;
+  const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kNT_Stages]), accum_bar = smem_u32(&bars[2 * kNT_Stages]);
+  const int n_kt = (p.k_chunks + kStageChunks - 1) / kStageChunks;
+  const uint32_t tmem_cols = tmem_cols_pow2(BN);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kNT_Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const __nv_bfloat16* a_src = p.A + ((int64_t)tile_m * p.a_chunks + p.a_chunk0 + (int64_t)batch * p.a_batch_chunks) * (kTileM * 8);
+      const __nv_bfloat16* b_src = p.B + batch * p.b_batch_elems + (int64_t)tile_n * p.k_chunks * BN * 8;
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int s = kt % kNT_Stages;
+        if (kt >= kNT_Stages) mbar_wait(empty0 + 8 * s, ((kt / kNT_Stages) - 1) & 1);
+        const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+        const uint32_t bytes_a = nch * kTileM * 16, bytes_b = nch * BN * 16;
+        mbar_expect_tx(full0 + 8 * s, bytes_a + bytes_b);
+        bulk_g2s(smem_base + s * stage_bytes, a_src + (int64_t)kt * kStageChunks * kTileM * 8, bytes_a, full0 + 8 * s);
+        bulk_g2s(smem_base + s * stage_bytes + a_stage_bytes, b_src + (int64_t)kt * kStageChunks * BN * 8, bytes_b, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, 0, 0);
+      const uint32_t lbo_a = kTileM * 16, lbo_b = BN * 16;
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int s = kt % kNT_Stages;
+        mbar_wait(full0 + 8 * s, (kt / kNT_Stages) & 1);
+        tc_fence_after();
+        const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+        const uint32_t sa = smem_base + s * stage_bytes, sb = sa + a_stage_bytes;
+        for (int kk = 0; kk < nch / 2; ++kk) {  // one MMA = K 16 = 2 chunks
+          umma(tmem_base, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb + kk * 2 * lbo_b, lbo_b, 128), idesc,
+               (kt | kk) != 0);
+        }
+        umma_commit(empty0 + 8 * s);  // slot reusable once these MMAs have read it
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    const int r_local = q * 32 + lane;
+    const int64_t row = (int64_t)tile_m * kTileM + r_local;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int n0 = tile_n * BN;
+    const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? p.bias + batch * p.bias_batch + n0 : nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      const int ncol = min(32, BN - c0);  // BN is a multiple of 16
+      if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < ncol) v[i] = mli_act(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), p.act);
+      } else if (p.aux) {
+        const __nv_bfloat16* aux = p.aux + ((int64_t)tile_m * p.aux_chunks + p.aux_chunk0 + (int64_t)batch * p.aux_batch_chunks +
+                                            (n0 + c0) / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < ncol) {
+            float y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(aux + (int64_t)g * kTileM * 8)), y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[g * 8 + i] *= mli_dact_from_out(y[i], p.act);
+          }
+        }
+      }
+      if (OUT_F32) {
+        if (row < p.M) {
+          float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                             ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
+                             r_local * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TN kernel: part[split][128 x BN tile] = sum over row tiles of  L[tile]^T (128 rows x 128 cols)  R[tile] (128 rows x BN cols)
+//   L, R are TCL-128 matrices read as MN-major operands (contraction over the 128 rows of each tile).
+// ---------------------------------------------------------------------------------------------------------------
+struct TcTN {
+  const __nv_bfloat16* L; int l_chunks, l_chunk0, l_batch_chunks;  // "dZ" side -> output rows (128 per CTA)
+  const __nv_bfloat16* R; int r_chunks, r_chunk0, r_batch_chunks;  // "X" side  -> output cols (BN per CTA)
+  int BN, n_row_tiles, tiles_per_split, S;
+  float* part; int rows_out, cols_out;                             // [batch*S][rows_out][cols_out] fp32
+};
+
+constexpr int kTN_Stages = 2;
+
+__global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(TcTN p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2 * kTN_Stages + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_c = blockIdx.x, tile_r = blockIdx.y;
+  const int batch = blockIdx.z / p.S, split = blockIdx.z % p.S;
+  const int BN = p.BN;
+  const uint32_t l_stage_bytes = 16 * kTileM * 16;       // 16 chunks (128 output rows) x 128 k-rows x 16 B
+  const uint32_t r_stage_bytes = (BN / 8) * kTileM * 16;
+  const uint32_t stage_bytes = l_stage_bytes + r_stage_bytes;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kTN_Stages]), accum_bar = smem_u32(&bars[2 * kTN_Stages]);
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(p.n_row_tiles, t_begin + p.tiles_per_split);
+  const int n_t = max(0, t_end - t_begin);
+  const uint32_t tmem_cols = tmem_cols_pow2(BN);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTN_Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_t; ++i) {
+        const int s = i % kTN_Stages;
+        if (i >= kTN_Stages) mbar_wait(empty0 + 8 * s, ((i / kTN_Stages) - 1) & 1);
+        const int64_t t = t_begin + i;
+        const __nv_bfloat16* l_src = p.L + (t * p.l_chunks + p.l_chunk0 + (int64_t)batch * p.l_batch_chunks + tile_r * 16) * (kTileM * 8);
+        const __nv_bfloat16* r_src = p.R + (t * p.r_chunks + p.r_chunk0 + (int64_t)batch * p.r_batch_chunks + tile_c * (BN / 8)) * (kTileM * 8);
+        mbar_expect_tx(full0 + 8 * s, stage_bytes);
+        bulk_g2s(smem_base + s * stage_bytes, l_src, l_stage_bytes, full0 + 8 * s);
+        bulk_g2s(smem_base + s * stage_bytes + l_stage_bytes, r_src, r_stage_bytes, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, 1, 1);  // both operands MN-major
+      for (int i = 0; i < n_t; ++i) {
+        const int s = i % kTN_Stages;
+        mbar_wait(full0 + 8 * s, (i / kTN_Stages) & 1);
+        tc_fence_after();
+        const uint32_t sl = smem_base + s * stage_bytes, sr = sl + l_stage_bytes;
+        // MN-major un-swizzled: LBO = 128 B between 8-row (K) groups, SBO = 2048 B between 8-column (MN) chunks
+        for (int kk = 0; kk < kTileM / 16; ++kk)
+          umma(tmem_base, make_desc(sl + kk * 256, 128, kTileM * 16), make_desc(sr + kk * 256, 128, kTileM * 16), idesc, (i | kk) != 0);
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r_out = tile_r * kTileM + q * 32 + lane;
+    if (n_t > 0) {
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+    }
+    float* dst_base = p.part + ((size_t)blockIdx.z * p.rows_out + r_out) * p.cols_out + tile_c * BN;
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (n_t > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+      }
+      const int ncol = min(32, min(BN - c0, p.cols_out - tile_c * BN - c0));
+      if (r_out < p.rows_out) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (g * 4 < ncol) *reinterpret_cast<float4*>(dst_base + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+__global__ void tn_reduce_kernel(const float* __restrict__ part, int S, int rows, int cols, float* __restrict__ out,
+                                 int64_t ldo, int64_t batch_stride, int transpose) {
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)rows * cols;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float v = 0.0f;
+  for (int s = 0; s < S; ++s) v += part[((size_t)(b * S + s)) * total + e];  // fixed order: deterministic
+  const int r = (int)(e / cols), c = (int)(e % cols);
+  if (transpose) out[b * batch_stride + (int64_t)c * ldo + r] = v;
+  else out[b * batch_stride + (int64_t)r * ldo + c] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout converters / small TCL helpers
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 row-major [M, cols] (ld) -> bf16 TCL with `tile_rows`-row tiles, chunks [chunk0, chunk0 + n_chunks) of a matrix
+// that has `dst_chunks` chunks per tile.  Rows >= M and columns >= cols are zero-filled.
+__global__ void __launch_bounds__(256) to_tcl_kernel(const float* __restrict__ src, int64_t ld, int64_t M, int cols,
+                                                     __nv_bfloat16* __restrict__ dst, int tile_rows, int dst_chunks,
+                                                     int chunk0, int n_chunks, int64_t m_padded) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= m_padded * n_chunks) return;
+  const int64_t tile = e / ((int64_t)tile_rows * n_chunks);
+  const int rem = (int)(e % ((int64_t)tile_rows * n_chunks));
+  const int j = rem / tile_rows, r = rem % tile_rows;  // consecutive threads -> consecutive rows of one chunk
+  const int64_t m = tile * tile_rows + r;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = j * 8 + i;
+    v[i] = (m < M && c < cols) ? src[m * ld + c] : 0.0f;
+  }
+  *reinterpret_cast<uint4*>(dst + ((tile * dst_chunks + chunk0 + j) * tile_rows + r) * 8) = pack8(v);
+}
+
+__global__ void __launch_bounds__(256) from_tcl_kernel(const __nv_bfloat16* __restrict__ src, int src_chunks, int chunk0,
+                                                       int n_chunks, int64_t M, float* __restrict__ dst, int64_t ld) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m_padded = (M + kTileM - 1) / kTileM * kTileM;
+  if (e >= m_padded * n_chunks) return;
+  const int64_t tile = e / ((int64_t)kTileM * n_chunks);
+  const int rem = (int)(e % ((int64_t)kTileM * n_chunks));
+  const int j = rem / kTileM, r = rem % kTileM;
+  const int64_t m = tile * kTileM + r;
+  if (m >= M) return;
+  float v[8];
+  unpack8(*reinterpret_cast<const uint4*>(src + ((tile * src_chunks + chunk0 + j) * kTileM + r) * 8), v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[m * ld + j * 8 + i] = v[i];
+}
+
+// column sums of a TCL-128 matrix (bias gradients): grid (n_chunks, S); 128 threads = rows of a tile
+__global__ void __launch_bounds__(128) colsum_tcl_kernel(const __nv_bfloat16* __restrict__ src, int src_chunks, int chunk0,
+                                                         int n_row_tiles, int tiles_per_split, float* __restrict__ part) {
+  __shared__ float red[4][8];
+  const int j = blockIdx.x, s = blockIdx.y;
+  const int t0 = s * tiles_per_split, t1 = min(n_row_tiles, t0 + tiles_per_split);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int t = t0; t < t1; ++t) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + (((int64_t)t * src_chunks + chunk0 + j) * kTileM + threadIdx.x) * 8)), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x >> 5][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 8)
+    part[((size_t)s * gridDim.x + j) * 8 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ part, int S, int n, float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float v = 0.0f;
+  for (int s = 0; s < S; ++s) v += part[(size_t)s * n + e];
+  out[e] = v;
+}
+
+int tn_splits(int n_row_tiles, int out_tiles) {
+  int s = (2 * MLI_NUM_SMS + out_tiles - 1) / out_tiles;
+  if (s > n_row_tiles) s = n_row_tiles;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : s;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  MLI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return MLI_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI (declared in include/mli_b200.h, "bf16 tensor-core path")
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mli_tc_to_tcl(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
+                             int32_t dst_chunks, int32_t chunk0, int32_t n_chunks, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 0 && cols >= 0 && n_chunks >= 1 && chunk0 >= 0 && chunk0 + n_chunks <= dst_chunks, "to_tcl: bad chunk range");
+  MLI_REQUIRE(tile_rows >= 16 && tile_rows <= 256 && tile_rows % 16 == 0, "to_tcl: tile_rows must be a multiple of 16 <= 256");
+  const int64_t m_padded = (M + tile_rows - 1) / tile_rows * tile_rows;
+  if (m_padded == 0) return MLI_OK;
+  to_tcl_kernel<<<mli_cdiv(m_padded * n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld, M, cols, (__nv_bfloat16*)dst, tile_rows, dst_chunks, chunk0, n_chunks, m_padded);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_tc_from_tcl(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* dst,
+                               int64_t ld, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 0 && n_chunks >= 1 && chunk0 >= 0 && chunk0 + n_chunks <= src_chunks && ld >= n_chunks * 8, "from_tcl: bad range");
+  if (M == 0) return MLI_OK;
+  const int64_t m_padded = (M + kTileM - 1) / kTileM * kTileM;
+  from_tcl_kernel<<<mli_cdiv(m_padded * n_chunks, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_chunks,
+                                                                                      chunk0, n_chunks, M, dst, ld);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
+                             int64_t b_batch_elems, int32_t K, int32_t N, int32_t BN, const float* bias, int32_t bias_batch,
+                             const void* aux, int32_t aux_chunks, int32_t aux_chunk0, int32_t aux_batch_chunks, int32_t act,
+                             void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
+                             int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
+                             void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 1 && batch >= 1 && K >= 16 && K % 16 == 0, "tc_linear: K must be a positive multiple of 16");
+  MLI_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "tc_linear: BN multiple of 16 <= 256 dividing N");
+  MLI_REQUIRE(a_chunk0 >= 0 && a_chunk0 + (batch - 1) * a_batch_chunks + K / 8 <= a_chunks, "tc_linear: A chunk range");
+  MLI_REQUIRE(epi == EPI_BIAS_ACT || epi == EPI_MUL_DACT, "tc_linear: unknown epilogue");
+  MLI_REQUIRE(act >= MLI_ACT_NONE && act <= MLI_ACT_SIGMOID, "tc_linear: unknown activation");
+  if (!out_is_f32) MLI_REQUIRE(out_chunk0 >= 0 && out_chunk0 + (batch - 1) * out_batch_chunks + N / 8 <= out_chunks, "tc_linear: out chunk range");
+  if (aux) MLI_REQUIRE(aux_chunk0 >= 0 && aux_chunk0 + (batch - 1) * aux_batch_chunks + N / 8 <= aux_chunks, "tc_linear: aux chunk range");
+  TcNT p;
+  p.A = (const __nv_bfloat16*)A; p.a_chunks = a_chunks; p.a_chunk0 = a_chunk0; p.a_batch_chunks = a_batch_chunks;
+  p.B = (const __nv_bfloat16*)B; p.b_batch_elems = b_batch_elems; p.k_chunks = K / 8; p.BN = BN;
+  p.bias = bias; p.bias_batch = bias_batch;
+  p.aux = (const __nv_bfloat16*)aux; p.aux_chunks = aux_chunks; p.aux_chunk0 = aux_chunk0; p.aux_batch_chunks = aux_batch_chunks;
+  p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks;
+  p.ldo = ldo; p.out_col0 = out_col0; p.out_batch_cols = out_batch_cols; p.M = M; p.act = act;
+  const size_t smem = (size_t)kNT_Stages * (kStageChunks * kTileM * 16 + kStageChunks * BN * 16);
+  dim3 grid(N / BN, mli_cdiv(M, kTileM), batch);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_NT(E, F)                                                        \
+  do {                                                                         \
+    if (int e = set_smem(tc_gemm_nt_kernel<E, F>, smem)) return e;             \
+    tc_gemm_nt_kernel<E, F><<<grid, kThreads, smem, st>>>(p);                  \
+  } while (0)
+  if (epi == EPI_BIAS_ACT) { if (out_is_f32) LAUNCH_NT(EPI_BIAS_ACT, true); else LAUNCH_NT(EPI_BIAS_ACT, false); }
+  else { if (out_is_f32) LAUNCH_NT(EPI_MUL_DACT, true); else LAUNCH_NT(EPI_MUL_DACT, false); }
+#undef LAUNCH_NT
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch) {
+  const int n_row_tiles = (int)((M + kTileM - 1) / kTileM);
+  const int out_tiles = ((rows_out + 127) / 128) * ((cols_out + 255) / 256) * batch;
+  return (int64_t)batch * tn_splits(n_row_tiles, out_tiles) * rows_out * cols_out * sizeof(float);
+}
+
+// out[b][r, c] (or transposed) = sum_m L[m, l0 + r] * R[m, r0 + c],  r < rows_out (multiple of 128), c < cols_out
+extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                            int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                            int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                            int32_t transpose_out, void* ws, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 1 && batch >= 1 && rows_out >= 128 && rows_out % 128 == 0, "tc_wgrad: rows_out must be a multiple of 128");
+  MLI_REQUIRE(cols_out >= 16 && cols_out % 16 == 0, "tc_wgrad: cols_out must be a multiple of 16");
+  MLI_REQUIRE(ws != nullptr, "tc_wgrad: workspace is NULL");
+  // column tiling: 256-wide tiles, the remainder tile must also be a legal UMMA N (multiple of 16)
+  const int BN = cols_out >= 256 ? 256 : cols_out;
+  MLI_REQUIRE(cols_out % BN == 0 || cols_out < 256, "tc_wgrad: cols_out must be < 256 or a multiple of 256 (call per column block)");
+  const int n_row_tiles = (int)((M + kTileM - 1) / kTileM);
+  const int out_tiles = (rows_out / 128) * ((cols_out + 255) / 256) * batch;
+  const int S = tn_splits(n_row_tiles, out_tiles);
+  TcTN p;
+  p.L = (const __nv_bfloat16*)L; p.l_chunks = l_chunks; p.l_chunk0 = l_chunk0; p.l_batch_chunks = l_batch_chunks;
+  p.R = (const __nv_bfloat16*)R; p.r_chunks = r_chunks; p.r_chunk0 = r_chunk0; p.r_batch_chunks = r_batch_chunks;
+  p.BN = BN; p.n_row_tiles = n_row_tiles; p.tiles_per_split = (n_row_tiles + S - 1) / S; p.S = S;
+  p.part = (float*)ws; p.rows_out = rows_out; p.cols_out = cols_out;
+  const size_t smem = (size_t)kTN_Stages * (16 * kTileM * 16 + (BN / 8) * kTileM * 16);
+  if (int e = set_smem(tc_gemm_tn_kernel, smem)) return e;
+  dim3 grid(cols_out / BN, rows_out / 128, S * batch);
+  tc_gemm_tn_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  MLI_LAUNCH_OK();
+  dim3 g2(mli_cdiv((int64_t)rows_out * cols_out, 256), batch);
+  tn_reduce_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(p.part, S, rows_out, cols_out, out, ldo, out_batch_stride, transpose_out);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int64_t mli_tc_colsum_ws_bytes(int64_t M, int32_t n_chunks) {
+  (void)M;
+  return (int64_t)64 * n_chunks * 8 * sizeof(float);
+}
+
+extern "C" int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* out,
+                             void* ws, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 1 && n_chunks >= 1 && chunk0 >= 0 && chunk0 + n_chunks <= src_chunks && ws, "tc_colsum: bad arguments");
+  const int n_row_tiles = (int)((M + kTileM - 1) / kTileM);
+  int S = n_row_tiles < 64 ? n_row_tiles : 64;
+  const int tps = (n_row_tiles + S - 1) / S;
+  S = (n_row_tiles + tps - 1) / tps;
+  colsum_tcl_kernel<<<dim3(n_chunks, S), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_chunks, chunk0,
+                                                                        n_row_tiles, tps, (float*)ws);
+  MLI_LAUNCH_OK();
+  colsum_reduce_kernel<<<mli_cdiv(n_chunks * 8, 256), 256, 0, (cudaStream_t)stream>>>((const float*)ws, S, n_chunks * 8, out);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+// legacy hook used by mli_linear_fwd(prec = BF16) on row-major fp32 operands: not supported, use the TCL entry points
+int mli_tc_linear_fwd(const float*, int64_t, int64_t, const float*, int64_t, int64_t, const float*, int64_t, float*, int64_t,
+                      int64_t, int64_t, int32_t, int32_t, int32_t, int32_t, void*) {
+  mli_set_error("bf16 mode works on TCL operands: use mli_tc_linear / mli_tc_wgrad");
   return MLI_ENOTSUP;
 }
