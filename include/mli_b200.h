@@ -152,6 +152,15 @@ int64_t mli_tc_colsum_ws_bytes(int64_t M, int32_t n_chunks);
 int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* out, void* ws,
                   void* stream);
 
+/* Narrow output layers on TCL activations (same maths as mli_rowdot_*): A is TCL-128 with a_chunks chunks per tile row;
+ * col_off (host array, multiples of 8, non-decreasing) selects the K-wide column window of each output.
+ * bwd_data writes dZ = (dS W) * act_prev'(A) as bf16 TCL with the same geometry as A (all a_chunks chunks). */
+int mli_tc_rowdot_fwd(const void* A, int32_t a_chunks, int64_t M, const float* w, const float* b,
+                      const int32_t* host_col_off, int32_t J, int32_t K, int32_t act, uint32_t act_mask, float* out,
+                      int64_t ldo, void* stream);
+int mli_tc_rowdot_bwd_data(const float* dS, int64_t lds, const void* A, int32_t a_chunks, int64_t M, const float* w,
+                           const int32_t* host_col_off, int32_t J, int32_t K, int32_t act_prev, void* dZ, void* stream);
+
 /* Narrow output layers (SDF head 256->1, mlp.py:50,66; head output layers 256->3/3/1, nerf_util.py:191):
  * out[m, j] = act_j(sum_k A[m, col_off[j] + k] * w[j, k] + b[j]),  j < J <= 8, k < K; act_j = act if bit j of
  * act_mask is set, identity otherwise (network_mode r_s leaves o_s without a sigmoid, modules.py:119).

@@ -133,6 +133,19 @@ class RenderEngine:
     def _z(self, *shape):
         return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
+    def _tcl(self, rows, chunks, tile=128):
+        """bf16 tile-chunk-layout buffer for a [rows, 8*chunks] matrix (see csrc/gemm_tcgen05.cu)."""
+        return torch.empty((rows + tile - 1) // tile, chunks, tile, 8, dtype=torch.bfloat16, device=self.device)
+
+    def _to_tcl(self, src, ld, rows, cols, dst, tile=128, chunk0=0, n_chunks=None):
+        call("mli_tc_to_tcl", src, ld, rows, cols, dst, tile, dst.shape[1], chunk0,
+             n_chunks if n_chunks is not None else (cols + 7) // 8)
+        return dst
+
+    @property
+    def tc(self):
+        return self.cfg.precision == _lib.PREC_BF16
+
     @property
     def tap_eps(self):  # modules.py:133,158
         return self.normal_eps / math.sqrt(3) if self.cfg.taps == 4 else self.normal_eps
@@ -167,8 +180,37 @@ class RenderEngine:
             j0 += odim
         W["bh"] = [torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for h in self.heads]) for l in range(4)]
         W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
+        if self.tc:  # bf16 TCL copies (tile height = the GEMM's N tile) for the tensor-core layers
+            T = {}
+            T["W1"] = self._to_tcl(W["W1"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
+            T["W1t"] = self._to_tcl(W["W1t"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
+            T["Wh0"] = self._to_tcl(W["Wh0"], KH_PAD, nh * HID, KH_PAD, self._tcl(nh * HID, KH_PAD // 8, 256), 256)
+            T["Wh0t_feat"] = self._to_tcl(W["Wh0t"], nh * HID, HID, nh * HID, self._tcl(HID, nh * 32, 256), 256)
+            T["Wh0t_x"] = self._to_tcl(W["Wh0t"][XH_OFF:], nh * HID, KH_PAD - XH_OFF, nh * HID,
+                                       self._tcl(KH_PAD - XH_OFF, nh * 32, KH_PAD - XH_OFF), KH_PAD - XH_OFF)
+            T["Whl"] = [self._to_tcl(W["Whl"][l], HID, nh * HID, HID, self._tcl(nh * HID, 32, 256), 256) for l in range(3)]
+            T["Whlt"] = [self._to_tcl(W["Whlt"][l], HID, nh * HID, HID, self._tcl(nh * HID, 32, 256), 256) for l in range(3)]
+            W["T"] = T
         self.W = W
         return W
+
+    # ---- tensor-core (bf16 TCL) building blocks -------------------------------------------------------------------
+    def _tc_linear(self, A, a_chunk0, a_bchunks, B, b_belems, K, N, BN, bias, bias_b, aux, aux_chunk0, aux_bchunks, act,
+                   out, out_f32, out_chunk0, out_bchunks, ldo, M, batch, epi):
+        call("mli_tc_linear", A, A.shape[1], a_chunk0, a_bchunks, B, b_belems, K, N, BN, bias, bias_b, aux,
+             aux.shape[1] if aux is not None else 0, aux_chunk0, aux_bchunks, act, out, int(out_f32),
+             0 if out_f32 else out.shape[1], out_chunk0, out_bchunks, ldo, 0, 0, M, batch, epi)
+
+    def _tc_wgrad(self, L, l_chunk0, l_b, R, r_chunk0, r_b, M, rows, cols, batch, out, ldo, bstride, transpose=0):
+        ws = torch.empty(_lib.load().mli_tc_wgrad_ws_bytes(M, rows, cols, batch), dtype=torch.uint8, device=self.device)
+        call("mli_tc_wgrad", L, L.shape[1], l_chunk0, l_b, R, R.shape[1], r_chunk0, r_b, M, rows, cols, batch, out, ldo,
+             bstride, transpose, ws)
+
+    def _tc_colsum(self, X, chunk0, n_chunks, M):
+        out = self._f(n_chunks * 8)
+        ws = torch.empty(_lib.load().mli_tc_colsum_ws_bytes(M, n_chunks), dtype=torch.uint8, device=self.device)
+        call("mli_tc_colsum", X, X.shape[1], chunk0, n_chunks, M, out, ws)
+        return out
 
     # ------------------------------------------------------------------------------------------------------
     def bounds(self, center, ray_unit):
@@ -187,7 +229,7 @@ class RenderEngine:
              self.cfg.vol_range[1], X, K0_PAD)
         H = self._f(R * n, HID)
         call("mli_linear_fwd", X, K0_PAD, 0, W["W0"], K0_PAD, 0, W["b0"], 0, H, HID, 0, R * n, HID, K0_PAD,
-             ACT_SOFTPLUS100, 1, self.cfg.precision)
+             ACT_SOFTPLUS100, 1, _lib.PREC_FP32)
         sdf = self._f(R * n)
         call("mli_rowdot_fwd", H, HID, R * n, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
         return sdf
@@ -219,7 +261,7 @@ class RenderEngine:
         R, N = center.shape[0], cfg.n_samples
         M, P = R * N, 1 + cfg.taps
         table = p["neural_sdf.tcnn_encoding.params"]
-        prec = cfg.precision
+        prec = _lib.PREC_FP32  # the CUDA-core entry points; tensor-core layers go through _tc_*
         X0 = self._f(P * M, K0_PAD)
         call("mli_encode_rays", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
              cfg.vol_range[0], cfg.vol_range[1], X0, K0_PAD)
@@ -228,29 +270,50 @@ class RenderEngine:
              ACT_SOFTPLUS100, 1, prec)
         sdf = self._f(P * M)
         call("mli_rowdot_fwd", H0, HID, P * M, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
-        XH = self._f(M, KH_PAD)
-        call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
-             prec)
         gradients = self._f(M, 3)
         hessians = self._f(M, 3) if training else None
-        call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
-             pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF)
-        A = [self._f(M, nh * HID) for _ in range(4)]
-        call("mli_linear_fwd", XH, KH_PAD, 0, W["Wh0"], KH_PAD, 0, W["bh"][0], 0, A[0], nh * HID, 0, M, nh * HID, KH_PAD,
-             ACT_RELU, 1, prec)
-        for l in range(3):
-            call("mli_linear_fwd", A[l], nh * HID, HID, W["Whl"][l], HID, HID * HID, W["bh"][l + 1], HID, A[l + 1],
-                 nh * HID, HID, M, HID, HID, ACT_RELU, nh, prec)
         S = self._f(M, 8)
-        call("mli_rowdot_fwd", A[3], nh * HID, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
-             self.act_mask, S, 8)
+        if not self.tc:
+            XH = self._f(M, KH_PAD)
+            call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
+                 prec)
+            call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
+                 pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF)
+            A = [self._f(M, nh * HID) for _ in range(4)]
+            call("mli_linear_fwd", XH, KH_PAD, 0, W["Wh0"], KH_PAD, 0, W["bh"][0], 0, A[0], nh * HID, 0, M, nh * HID,
+                 KH_PAD, ACT_RELU, 1, prec)
+            for l in range(3):
+                call("mli_linear_fwd", A[l], nh * HID, HID, W["Whl"][l], HID, HID * HID, W["bh"][l + 1], HID, A[l + 1],
+                     nh * HID, HID, M, HID, HID, ACT_RELU, nh, prec)
+            call("mli_rowdot_fwd", A[3], nh * HID, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
+                 self.act_mask, S, 8)
+            H0c = None
+        else:
+            # layer 1 + all head layers on the tensor cores; activations in bf16 TCL (never leave that layout)
+            T = W["T"]
+            H0c = self._to_tcl(H0, HID, M, HID, self._tcl(M, 32))
+            XH = self._tcl(M, KH_PAD // 8)
+            self._tc_linear(H0c, 0, 0, T["W1"], 0, HID, HID, 256, W["b1"], 0, None, 0, 0, ACT_SOFTPLUS100, XH, False, 0, 0,
+                            0, M, 1, 0)
+            XHx = self._f(M, KH_PAD - XH_OFF)
+            call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
+                 pts_light, dists, N, gradients, hessians, XHx, KH_PAD - XH_OFF, 0)
+            self._to_tcl(XHx, KH_PAD - XH_OFF, M, KH_PAD - XH_OFF, XH, 128, XH_OFF // 8)
+            A = [self._tcl(M, nh * 32) for _ in range(4)]
+            self._tc_linear(XH, 0, 0, T["Wh0"], 0, KH_PAD, nh * HID, 256, W["bh"][0], 0, None, 0, 0, ACT_RELU, A[0], False,
+                            0, 0, 0, M, 1, 0)
+            for l in range(3):
+                self._tc_linear(A[l], 0, 32, T["Whl"][l], HID * HID, HID, HID, 256, W["bh"][l + 1], HID, None, 0, 0,
+                                ACT_RELU, A[l + 1], False, 0, 32, 0, M, nh, 0)
+            call("mli_tc_rowdot_fwd", A[3], nh * 32, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
+                 self.act_mask, S, 8)
         ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
                                  min(progress / cfg.anneal_end, 1.0))
         weights, out = self._f(R, N), self._f(R, self.n_out)
         extras = self._f(R, 5) if not training else None
         call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, 8, R, None, weights, out,
              extras)
-        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
+        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
                    ccfg=ccfg, center=center, ray_unit=ray_unit, dists=dists, far=far, outside=outside)
         res = dict(out=out, weights=weights, gradients=gradients, hessians=hessians, extras=extras, S=S, sdf=sdf)
         return res, ctx
@@ -261,7 +324,7 @@ class RenderEngine:
         """Hand-written backward of forward().  Returns a dict {state-dict name: gradient}."""
         cfg, W, nh = self.cfg, self.W, self.nh
         R, M, P, N = ctx["R"], ctx["M"], ctx["P"], cfg.n_samples
-        prec = cfg.precision
+        prec = _lib.PREC_FP32  # the CUDA-core entry points; tensor-core layers go through _tc_*
         need_sdf = ("sdf" in need) or ("table" in need)
         grads = {}
         d_grad = d_gradients.contiguous().clone() if d_gradients is not None else self._z(M, 3)
@@ -276,29 +339,85 @@ class RenderEngine:
         need_heads = "heads" in need
         if not (need_heads or need_sdf):
             return grads
-        # ---- heads ----------------------------------------------------------------------------------------
-        dZ = self._f(M, nh * HID)
+        train_mlp = "sdf" in need
+        H0 = ctx["H0"]
+        dWh, dbh = [None] * 3, [None] * 4
         dWout, dbout = self._f(self.J, HID), self._f(self.J)
-        ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(M, self.J, HID), dtype=torch.uint8, device=self.device)
-        call("mli_rowdot_bwd", dS, 8, A[3], nh * HID, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, nh * HID,
-             nh * HID, 0, dWout if need_heads else None, dbout, ws)
-        dWh = [None] * 3
-        dbh = [None] * 4
-        for l in (2, 1, 0):
+        dWh0 = self._f(nh * HID, KH_PAD) if need_heads else None
+        dZ0 = self._f(P * M, HID) if need_sdf else None  # rows [0, M) first receive dL/dH0 of the centre plane
+        dXx = self._f(M, KH_PAD - XH_OFF) if need_sdf else None
+        dW1, db1 = (self._f(HID, HID), None) if (need_sdf and train_mlp) else (None, None)
+        if not self.tc:
+            # ---- heads, fp32 CUDA-core path -------------------------------------------------------------------------
+            dZ = self._f(M, nh * HID)
+            ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(M, self.J, HID), dtype=torch.uint8, device=self.device)
+            call("mli_rowdot_bwd", dS, 8, A[3], nh * HID, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, nh * HID,
+                 nh * HID, 0, dWout if need_heads else None, dbout, ws)
+            for l in (2, 1, 0):
+                if need_heads:
+                    dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
+                    wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, nh)
+                    call("mli_linear_wgrad", dZ, nh * HID, HID, A[l], nh * HID, HID, dWh[l], HID, HID * HID, dbh[l + 1],
+                         HID, M, HID, HID, nh, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
+                dZp = self._f(M, nh * HID)
+                call("mli_linear_dgrad", dZ, nh * HID, HID, W["Whlt"][l], HID, HID * HID, A[l], nh * HID, HID, dZp,
+                     nh * HID, HID, M, HID, HID, ACT_RELU, 0, nh, prec)
+                dZ = dZp
+            XH = ctx["XH"]
             if need_heads:
-                dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
-                wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, nh)
-                call("mli_linear_wgrad", dZ, nh * HID, HID, A[l], nh * HID, HID, dWh[l], HID, HID * HID, dbh[l + 1], HID,
-                     M, HID, HID, nh, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
-            dZp = self._f(M, nh * HID)
-            call("mli_linear_dgrad", dZ, nh * HID, HID, W["Whlt"][l], HID, HID * HID, A[l], nh * HID, HID, dZp, nh * HID,
-                 HID, M, HID, HID, ACT_RELU, 0, nh, prec)
-            dZ = dZp
+                dbh[0] = self._f(nh * HID)
+                wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, nh * HID, KH_PAD, 1)
+                call("mli_linear_wgrad", dZ, nh * HID, 0, XH, KH_PAD, 0, dWh0, KH_PAD, 0, dbh[0], 0, M, nh * HID, KH_PAD,
+                     1, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            if need_sdf:
+                dZ1 = self._f(M, HID)  # d pre-activation of SDF layer 1 = (dZ_head0 . Wh0[:, feat]) * softplus'(feat)
+                call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"], nh * HID, 0, XH, KH_PAD, 0, dZ1, HID, 0, M, nh * HID,
+                     HID, ACT_SOFTPLUS100, 0, 1, prec)
+                call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"][XH_OFF:], nh * HID, 0, None, 0, 0, dXx, KH_PAD - XH_OFF,
+                     0, M, nh * HID, KH_PAD - XH_OFF, ACT_NONE, 0, 1, prec)
+                if train_mlp:
+                    db1 = self._f(HID)
+                    wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, 1)
+                    call("mli_linear_wgrad", dZ1, HID, 0, H0, HID, 0, dW1, HID, 0, db1, 0, M, HID, HID, 1, prec,
+                         torch.empty(wsb, dtype=torch.uint8, device=self.device))
+                call("mli_linear_dgrad", dZ1, HID, 0, W["W1t"], HID, 0, None, 0, 0, dZ0, HID, 0, M, HID, HID, ACT_NONE, 0,
+                     1, prec)
+        else:
+            # ---- heads + SDF layer 1 on the tensor cores (bf16 TCL operands, fp32 accumulation in TMEM) ---------------
+            T, XH = W["T"], ctx["XH"]
+            dZ = self._tcl(M, nh * 32)
+            call("mli_tc_rowdot_bwd_data", dS, 8, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ)
+            if need_heads:
+                dSt = self._to_tcl(dS, 8, M, 8, self._tcl(M, 2), 128, 0, 2)
+                outT = self._f(nh, 16, HID)  # [head][j][k] = sum_m dS[m, j] A4[m, head*256 + k]
+                self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1)
+                dWout = torch.stack([outT[self.col_off[j] // HID, j] for j in range(self.J)])
+                dbout = self._tc_colsum(dSt, 0, 1, M)[:self.J]
+            for l in (2, 1, 0):
+                if need_heads:
+                    dWh[l] = self._f(nh, HID, HID)
+                    self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID, HID * HID)
+                    dbh[l + 1] = self._tc_colsum(dZ, 0, nh * 32, M)
+                dZp = self._tcl(M, nh * 32)
+                self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0, A[l], 0, 32, ACT_RELU, dZp,
+                                False, 0, 32, 0, M, nh, 1)
+                dZ = dZp
+            if need_heads:
+                self._tc_wgrad(dZ, 0, 0, XH, 0, 0, M, nh * HID, 256, 1, dWh0, KH_PAD, 0)
+                self._tc_wgrad(dZ, 0, 0, XH, XH_OFF // 8, 0, M, nh * HID, KH_PAD - XH_OFF, 1, dWh0[:, XH_OFF:], KH_PAD, 0)
+                dbh[0] = self._tc_colsum(dZ, 0, nh * 32, M)
+            if need_sdf:
+                dZ1 = self._tcl(M, 32)
+                self._tc_linear(dZ, 0, 0, T["Wh0t_feat"], 0, nh * HID, HID, 256, None, 0, XH, 0, 0, ACT_SOFTPLUS100, dZ1,
+                                False, 0, 0, 0, M, 1, 1)
+                self._tc_linear(dZ, 0, 0, T["Wh0t_x"], 0, nh * HID, KH_PAD - XH_OFF, KH_PAD - XH_OFF, None, 0, None, 0, 0,
+                                ACT_NONE, dXx, True, 0, 0, KH_PAD - XH_OFF, M, 1, 1)
+                if train_mlp:
+                    self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0)
+                    db1 = self._tc_colsum(dZ1, 0, 32, M)
+                self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dZ0, True, 0, 0, HID,
+                                M, 1, 1)
         if need_heads:
-            dWh0, dbh[0] = self._f(nh * HID, KH_PAD), self._f(nh * HID)
-            wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, nh * HID, KH_PAD, 1)
-            call("mli_linear_wgrad", dZ, nh * HID, 0, ctx["XH"], KH_PAD, 0, dWh0, KH_PAD, 0, dbh[0], 0, M, nh * HID, KH_PAD,
-                 1, prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
             j0 = 0
             for hi, (name, kind, odim, _) in enumerate(self.heads):
                 pre = f"neural_rgb.{name}.linears."
@@ -322,26 +441,10 @@ class RenderEngine:
                 j0 += odim
         if not need_sdf:
             return grads
-        # ---- SDF network ------------------------------------------------------------------------------------
-        XH = ctx["XH"]
-        dZ1 = self._f(M, HID)  # d pre-activation of SDF layer 1 = (dZ_head0 . Wh0[:, feat]) * softplus'(feat)
-        call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"], nh * HID, 0, XH, KH_PAD, 0, dZ1, HID, 0, M, nh * HID, HID,
-             ACT_SOFTPLUS100, 0, 1, prec)
-        dXx = self._f(M, KH_PAD - XH_OFF)  # d of the non-feature head inputs (only the normal columns are used)
-        call("mli_linear_dgrad", dZ, nh * HID, 0, W["Wh0t"][XH_OFF:], nh * HID, 0, None, 0, 0, dXx, KH_PAD - XH_OFF, 0, M,
-             nh * HID, KH_PAD - XH_OFF, ACT_NONE, 0, 1, prec)
+        # ---- SDF network layer 0 + SDF head (fp32: the 4-tap stencil needs it) ---------------
         d_sdf = self._f(P * M)
         call("mli_geometry_bwd", ctx["gradients"], M, N, cfg.taps, self.tap_eps, ctx["outside"], d_grad, d_hessians, dXx,
              KH_PAD - XH_OFF, 0, d_sdf_c, d_sdf)
-        H0 = ctx["H0"]
-        train_mlp = "sdf" in need
-        if train_mlp:
-            dW1, db1 = self._f(HID, HID), self._f(HID)
-            wsb = _lib.load().mli_linear_wgrad_ws_bytes(M, HID, HID, 1)
-            call("mli_linear_wgrad", dZ1, HID, 0, H0, HID, 0, dW1, HID, 0, db1, 0, M, HID, HID, 1, prec,
-                 torch.empty(wsb, dtype=torch.uint8, device=self.device))
-        dZ0 = self._f(P * M, HID)
-        call("mli_linear_dgrad", dZ1, HID, 0, W["W1t"], HID, 0, None, 0, 0, dZ0, HID, 0, M, HID, HID, ACT_NONE, 0, 1, prec)
         dw_sdf, db_sdf = self._f(1, HID), self._f(1)
         ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(P * M, 1, HID), dtype=torch.uint8, device=self.device)
         # centre plane: accumulate onto the layer-1 path; tap planes: SDF head only

@@ -395,3 +395,37 @@ def test_model_inference_outputs(lib):
         if k != "gradient":
             assert ((a - b).abs().amax(dim=-1) < 2e-2).float().mean() > 0.97, k
     assert torch.equal(out["outside"].cpu(), ref["outside"])
+
+
+def test_render_bf16_tensor_core_mode(lib):
+    """bf16 MLP-tile mode (layer 1 + all head layers on tcgen05): the looser, stated bound of the north star.
+    Bounds: per-ray colours |err| <= 2e-2 (mean <= 3e-3); parameter gradients: relative L2 error <= 6e-2."""
+    from mli_nerf_b200.engine import RenderEngine
+    case = make_case(R=256, progress=0.5)
+    ocfg, params = case["ocfg"], case["params"]
+    pp = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out_ref = port.render_rays(pp, ocfg, case["center"], case["ray_unit"], case["light"], rands=case["rands"],
+                               training=True, progress=case["progress"], keep=True)
+    ocfg0 = port.PathConfig(**{**ocfg.__dict__, "w_curvature": 0.0})
+    port.total_loss(ocfg0, out_ref, case["targets"])[0].backward()
+    eng = RenderEngine(product_cfg(ocfg, precision=1))
+    p = {k: cu(v) for k, v in params.items()}
+    eng.pack_weights(p)
+    c, r, l = cu(case["center"][0]), cu(case["ray_unit"][0]), cu(case["light"][0])
+    near, far, outside = eng.bounds(c, r)
+    res, ctx = eng.forward(p, c, r, l, cu(out_ref["dists"][0, :, :, 0]), near, far, outside, True, case["progress"])
+    out = res["out"].cpu()
+    for k, (a, b) in dict(rgb=(0, 3), o_r=(3, 6), o_s=(6, 7), o_re=(7, 10)).items():
+        err = (out[:, a:b] - out_ref[k][0].detach()).abs()
+        assert float(err.max()) < 2e-2 and float(err.mean()) < 3e-3, (k, float(err.max()), float(err.mean()))
+    # SDF trunk layer 0 stays fp32, so geometry is unchanged
+    assert torch.allclose(res["sdf"].cpu()[:256 * 128].view(256, 128), out_ref["sdfs"][0, :, :, 0], rtol=1e-3, atol=1e-5)
+    tg = {k: cu(v[0]) for k, v in case["targets"].items()}
+    _, d_out, d_grad, d_hess = eng.losses(loss_cfg(ocfg0), res["out"], res["gradients"], res["hessians"], outside, tg)
+    grads = eng.backward(p, ctx, d_out, d_grad, d_hess, None)
+    worst = {}
+    for k, v in pp.items():
+        g = grads[k].cpu().view_as(v.grad)
+        worst[k] = float((g - v.grad).norm() / (v.grad.norm() + 1e-30))
+    bad = {k: e for k, e in worst.items() if e > 6e-2}
+    assert not bad, bad
