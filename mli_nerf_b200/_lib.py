@@ -141,6 +141,8 @@ def _ptr(x):
 
 
 def stream_ptr():
+    if not torch.cuda.is_available():
+        raise MliError("libmli_b200 needs a B200-class CUDA device: the render path has no CPU fallback")
     return torch.cuda.current_stream().cuda_stream
 
 
