@@ -447,9 +447,15 @@ int tn_splits(int n_row_tiles, int out_tiles) {
   return s < 1 ? 1 : s;
 }
 
+// raise the dynamic-smem limit of a kernel only when it has to grow (keeps the call out of CUDA-graph captures
+// after the first eager step)
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-  MLI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  static size_t current = 0;  // one instance per kernel instantiation
+  if (bytes > current) {
+    MLI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    current = bytes;
+  }
   return MLI_OK;
 }
 

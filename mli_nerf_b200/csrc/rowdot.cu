@@ -69,27 +69,44 @@ __global__ void __launch_bounds__(256) rowdot_bwd_data_kernel(const float* __res
   *reinterpret_cast<float4*>(dA + m * ldda + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// partial dw[j,k] / db[j] over a contiguous chunk of rows; blockDim.x == K
+// partial dw[j,k] / db[j] over a contiguous chunk of rows; blockDim.x == K.  Rows are processed 8 at a time with all
+// loads issued before the FMAs so that 8*J independent 1 KB row reads are in flight per CTA (the loop is otherwise one
+// dependent global load per iteration).
+template <int J>
 __global__ void rowdot_bwd_weight_kernel(const float* __restrict__ dS, int64_t lds, const float* __restrict__ A,
                                          int64_t lda, int64_t M, RowdotArgs a, int64_t rows_per_block,
                                          float* __restrict__ part) {
+  constexpr int U = 8;
   const int k = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-  float acc[kMaxJ], accb[kMaxJ];
+  float acc[J], accb[J];
 #pragma unroll
-  for (int j = 0; j < kMaxJ; ++j) acc[j] = accb[j] = 0.0f;
-  for (int64_t m = m0; m < m1; ++m) {
+  for (int j = 0; j < J; ++j) acc[j] = accb[j] = 0.0f;
+  int64_t m = m0;
+  for (; m + U <= m1; m += U) {
+    float d[U][J], x[U][J];
 #pragma unroll
-    for (int j = 0; j < kMaxJ; ++j) {
-      if (j < a.J) {
-        const float d = __ldg(dS + m * lds + j);
-        acc[j] = fmaf(d, __ldg(A + m * lda + a.col_off[j] + k), acc[j]);
-        accb[j] += d;
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        d[u][j] = __ldg(dS + (m + u) * lds + j);
+        x[u][j] = __ldg(A + (m + u) * lda + a.col_off[j] + k);
       }
-    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < J; ++j) { acc[j] = fmaf(d[u][j], x[u][j], acc[j]); accb[j] += d[u][j]; }
   }
-  float* dst = part + (size_t)blockIdx.x * a.J * (a.K + 1);
-  for (int j = 0; j < a.J; ++j) {
+  for (; m < m1; ++m)
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float d = __ldg(dS + m * lds + j);
+      acc[j] = fmaf(d, __ldg(A + m * lda + a.col_off[j] + k), acc[j]);
+      accb[j] += d;
+    }
+  float* dst = part + (size_t)blockIdx.x * J * (a.K + 1);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
     dst[j * (a.K + 1) + k] = acc[j];
     if (k == 0) dst[j * (a.K + 1) + a.K] = accb[j];
   }
@@ -106,7 +123,7 @@ __global__ void rowdot_bwd_reduce_kernel(const float* __restrict__ part, int n_b
   else if (db) db[j] = v;
 }
 
-constexpr int kRowdotBlocks = 2 * MLI_NUM_SMS;
+constexpr int kRowdotBlocks = 8 * MLI_NUM_SMS;
 
 // ---------------------------------------------------------------------------------------------------------
 // weight_norm: one CTA per output row
@@ -251,7 +268,12 @@ extern "C" int mli_rowdot_bwd(const float* dS, int64_t lds, const float* A, int6
     int blocks = kRowdotBlocks;
     int64_t rows = (M + blocks - 1) / blocks;
     blocks = (int)((M + rows - 1) / rows);
-    rowdot_bwd_weight_kernel<<<blocks, K, 0, (cudaStream_t)stream>>>(dS, lds, A, lda, M, a, rows, (float*)ws);
+#define LAUNCH_W(JJ) rowdot_bwd_weight_kernel<JJ><<<blocks, K, 0, (cudaStream_t)stream>>>(dS, lds, A, lda, M, a, rows, (float*)ws)
+    switch (J) {
+      case 1: LAUNCH_W(1); break; case 2: LAUNCH_W(2); break; case 3: LAUNCH_W(3); break; case 4: LAUNCH_W(4); break;
+      case 5: LAUNCH_W(5); break; case 6: LAUNCH_W(6); break; case 7: LAUNCH_W(7); break; default: LAUNCH_W(8); break;
+    }
+#undef LAUNCH_W
     MLI_LAUNCH_OK();
     rowdot_bwd_reduce_kernel<<<mli_cdiv(J * (K + 1), 256), 256, 0, (cudaStream_t)stream>>>((const float*)ws, blocks, J,
                                                                                           K, dw, db);

@@ -8,6 +8,7 @@ and autograd glue only.  There is no CPU fallback: constructing works anywhere (
 CPU box), calling forward/inference without a B200-class GPU raises.
 """
 import math
+import os
 from functools import partial
 
 import numpy as np
@@ -216,7 +217,8 @@ class Model(torch.nn.Module):
             bounding="box" if self.bounding_type == "box" else "unit_sphere",
             aabb=tuple(float(v) for v in cfg_data.bounding_box_aabb) if self.bounding_type == "box" else None,
             c2f_enabled=bool(sdf_cfg.encoding.coarse2fine.enabled),
-            precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[getattr(cfg_model, "mli_precision", "fp32")])
+            precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[
+                getattr(cfg_model, "mli_precision", os.environ.get("MLI_PRECISION", "fp32"))])
         self.progress = 1.0
         self._engine = None
         self.max_rays_per_launch = 8192
@@ -299,12 +301,16 @@ class Model(torch.nn.Module):
                                       stratified=self.cfg_render.stratified)
 
     @torch.no_grad()
-    def fused_train_step(self, data, loss_cfg, accumulate=False):
+    def fused_train_step(self, data, loss_cfg, accumulate=False, use_graph=False):
         """forward + in-kernel losses + hand-written backward in one pass (no autograd graph).
 
         Equivalent to ``total = trainer.model_forward(data); total.backward()`` of the reference
         (projects/nerf/trainers/base.py:99-107, NeuralLumen/trainer.py:133-149,189-196): fills ``.grad`` of every
-        parameter with ``requires_grad`` and returns the device tensor of losses (see _lib.LOSS_NAMES)."""
+        parameter with ``requires_grad`` and returns the device tensor of losses (see _lib.LOSS_NAMES).
+        ``use_graph``: replay the ~130 kernel launches of the step from a CUDA graph (captured on first use and
+        re-captured whenever a host-side scalar baked into the launches changes)."""
+        if use_graph and not accumulate:
+            return self._graphed_train_step(data, loss_cfg)
         eng = self.engine
         B, R = data["ray_idx"].shape
         c, r, l, _ = self._rays(data["pose"], data["intr"], data["pose_light"], self.image_size_train, data["ray_idx"])
@@ -333,6 +339,39 @@ class Model(torch.nn.Module):
                 else:
                     q.grad = g
         self._last_render = res
+        return losses
+
+    def _graphed_train_step(self, data, loss_cfg):
+        tensors = {k: v for k, v in data.items() if isinstance(v, torch.Tensor) and v.is_cuda}
+        eng = self.engine
+        key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())),
+               min(self.progress / self.anneal_end, 1.0), float(self.neural_sdf.normal_eps), int(eng.grid.active_levels),
+               tuple(p.requires_grad for p in self.parameters()), bytes(loss_cfg), self.path_cfg.precision)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        st = self._graphs.get(key)
+        if st is None:
+            static = {k: v.clone() for k, v in tensors.items()}
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # eager warm-up off the capture stream (lazy loads, smem attributes)
+                for _ in range(2):
+                    self.fused_train_step(static, loss_cfg)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                losses = self.fused_train_step(static, loss_cfg)
+            grads = {n: p.grad for n, p in self.named_parameters() if p.grad is not None}
+            st = (graph, static, losses, grads)
+            self._graphs[key] = st
+        graph, static, losses, grads = st
+        for k, v in tensors.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        for n, p in self.named_parameters():
+            if n in grads:
+                p.grad = grads[n]
         return losses
 
     @torch.no_grad()
