@@ -448,13 +448,20 @@ int tn_splits(int n_row_tiles, int out_tiles) {
 }
 
 // raise the dynamic-smem limit of a kernel only when it has to grow (keeps the call out of CUDA-graph captures
-// after the first eager step)
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-  static size_t current = 0;  // one instance per kernel instantiation
-  if (bytes > current) {
+// after the first eager step); keyed by the kernel's address (all NT instantiations share one function type)
+int set_smem(const void* kernel, size_t bytes) {
+  static const void* keys[16];
+  static size_t vals[16];
+  static int n = 0;
+  int i = 0;
+  for (; i < n; ++i) if (keys[i] == kernel) break;
+  if (i == n) {
+    if (n == 16) { mli_set_error("set_smem: table full"); return MLI_EINVAL; }
+    keys[n] = kernel; vals[n] = 0; ++n;
+  }
+  if (bytes > vals[i]) {
     MLI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    current = bytes;
+    vals[i] = bytes;
   }
   return MLI_OK;
 }
@@ -515,7 +522,7 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_NT(E, F)                                                        \
   do {                                                                         \
-    if (int e = set_smem(tc_gemm_nt_kernel<E, F>, smem)) return e;             \
+    if (int e = set_smem((const void*)tc_gemm_nt_kernel<E, F>, smem)) return e;             \
     tc_gemm_nt_kernel<E, F><<<grid, kThreads, smem, st>>>(p);                  \
   } while (0)
   if (epi == EPI_BIAS_ACT) { if (out_is_f32) LAUNCH_NT(EPI_BIAS_ACT, true); else LAUNCH_NT(EPI_BIAS_ACT, false); }
@@ -552,7 +559,7 @@ extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, i
   p.BN = BN; p.n_row_tiles = n_row_tiles; p.tiles_per_split = (n_row_tiles + S - 1) / S; p.S = S;
   p.part = (float*)ws; p.rows_out = rows_out; p.cols_out = cols_out;
   const size_t smem = (size_t)kTN_Stages * (16 * kTileM * 16 + (BN / 8) * kTileM * 16);
-  if (int e = set_smem(tc_gemm_tn_kernel, smem)) return e;
+  if (int e = set_smem((const void*)tc_gemm_tn_kernel, smem)) return e;
   dim3 grid(cols_out / BN, rows_out / 128, S * batch);
   tc_gemm_tn_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   MLI_LAUNCH_OK();
