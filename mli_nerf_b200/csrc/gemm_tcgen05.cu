@@ -251,6 +251,169 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Persistent, weight-stationary NT kernel.  One CTA per SM keeps its [BN x K] weight tile resident in shared memory
+// (loaded once by TMA), streams 128-row activation tiles through a 4-stage ring, accumulates into one of TWO TMEM
+// buffers so the epilogue of tile i overlaps the MMAs of tile i+1, and prefetches the epilogue's `aux` operand
+// (previous layer's output, for the activation derivative) into registers before it waits for the accumulator.
+// Used whenever K*BN*2 B + 64 KB fits in shared memory (every layer except the K = 768 feature data-gradient).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kP_Stages = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_persist_kernel(TcNT p, int n_row_tiles, int n_tiles_n) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * kP_Stages + 4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.y % n_tiles_n, batch = blockIdx.y / n_tiles_n;
+  const int BN = p.BN;
+  const uint32_t b_bytes = (uint32_t)p.k_chunks * BN * 16;
+  const uint32_t a_stage_bytes = kStageChunks * kTileM * 16;
+  const uint32_t sB = smem_u32(smem), sA = sB + b_bytes;
+  const uint32_t b_full = smem_u32(&bars[0]);
+  const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kP_Stages]);
+  const uint32_t t_full0 = smem_u32(&bars[1 + 2 * kP_Stages]), t_empty0 = smem_u32(&bars[1 + 2 * kP_Stages + 2]);
+  const int n_kt = (p.k_chunks + kStageChunks - 1) / kStageChunks;
+  const uint32_t tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    for (int s = 0; s < kP_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(t_full0 + 8 * a, 1); mbar_init(t_empty0 + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights: resident for the whole kernel
+      const __nv_bfloat16* b_src = p.B + batch * p.b_batch_elems + (int64_t)tile_n * p.k_chunks * BN * 8;
+      mbar_expect_tx(b_full, b_bytes);
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+        bulk_g2s(sB + kt * kStageChunks * BN * 16, b_src + (int64_t)kt * kStageChunks * BN * 8, nch * BN * 16, b_full);
+      }
+      uint32_t cnt = 0;
+      for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x) {
+        const __nv_bfloat16* a_src = p.A + ((int64_t)tile_m * p.a_chunks + p.a_chunk0 + (int64_t)batch * p.a_batch_chunks) * (kTileM * 8);
+        for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
+          const uint32_t s = cnt % kP_Stages;
+          if (cnt >= kP_Stages) mbar_wait(a_empty0 + 8 * s, ((cnt / kP_Stages) - 1) & 1);
+          const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+          mbar_expect_tx(a_full0 + 8 * s, nch * kTileM * 16);
+          bulk_g2s(sA + s * a_stage_bytes, a_src + (int64_t)kt * kStageChunks * kTileM * 8, nch * kTileM * 16, a_full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN, 0, 0);
+      const uint32_t lbo_a = kTileM * 16, lbo_b = BN * 16;
+      mbar_wait(b_full, 0);
+      uint32_t cnt = 0, it = 0;
+      for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        if (it >= 2) mbar_wait(t_empty0 + 8 * acc, ((it >> 1) - 1) & 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
+          const uint32_t s = cnt % kP_Stages;
+          mbar_wait(a_full0 + 8 * s, (cnt / kP_Stages) & 1);
+          tc_fence_after();
+          const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+          const uint32_t sa = sA + s * a_stage_bytes, sb = sB + kt * kStageChunks * lbo_b;
+          for (int kk = 0; kk < nch / 2; ++kk)
+            umma(d_tmem, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb + kk * 2 * lbo_b, lbo_b, 128), idesc, (kt | kk) != 0);
+          umma_commit(a_empty0 + 8 * s);
+        }
+        umma_commit(t_full0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r_local = q * 32 + lane;
+    const int n0 = tile_n * BN;
+    const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? p.bias + batch * p.bias_batch + n0 : nullptr;
+    uint32_t it = 0;
+    for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      const int64_t row = (int64_t)tile_m * kTileM + r_local;
+      uint4 auxr[32];
+      if (EPI == EPI_MUL_DACT) {
+        if (p.aux) {  // issue every load of this row before waiting: latency hides behind the tile's MMAs
+          const __nv_bfloat16* aux = p.aux + ((int64_t)tile_m * p.aux_chunks + p.aux_chunk0 + (int64_t)batch * p.aux_batch_chunks + n0 / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+          for (int g = 0; g < 32; ++g)
+            if (g * 8 < BN) auxr[g] = __ldg(reinterpret_cast<const uint4*>(aux + (int64_t)g * kTileM * 8));
+        }
+      }
+      mbar_wait(t_full0 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int c0 = cc * 32;
+        if (c0 < BN) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+          if (c0 + 32 >= BN) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(t_empty0 + 8 * acc);
+          }
+          const int ncol = min(32, BN - c0);
+          if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncol) v[i] = mli_act(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), p.act);
+          } else if (p.aux) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncol) {
+                float y[8];
+                unpack8(auxr[cc * 4 + g], y);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[g * 8 + i] *= mli_dact_from_out(y[i], p.act);
+              }
+            }
+          }
+          if (OUT_F32) {
+            if (row < p.M) {
+              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                 ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
+                                 r_local * 8;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // TN kernel: part[split][128 x BN tile] = sum over row tiles of  L[tile]^T (128 rows x 128 cols)  R[tile] (128 rows x BN cols)
 //   L, R are TCL-128 matrices read as MN-major operands (contraction over the 128 rows of each tile).
 // ---------------------------------------------------------------------------------------------------------------
@@ -517,9 +680,28 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
   p.aux = (const __nv_bfloat16*)aux; p.aux_chunks = aux_chunks; p.aux_chunk0 = aux_chunk0; p.aux_batch_chunks = aux_batch_chunks;
   p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks;
   p.ldo = ldo; p.out_col0 = out_col0; p.out_batch_cols = out_batch_cols; p.M = M; p.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem_p = (size_t)(K / 8) * BN * 16 + (size_t)kP_Stages * kStageChunks * kTileM * 16;
+  if (smem_p <= 225 * 1024) {  // persistent weight-stationary kernel
+    const int n_tiles_n = N / BN, groups = n_tiles_n * batch;
+    const int n_row_tiles = (int)mli_cdiv(M, kTileM);
+    int per_group = MLI_NUM_SMS / groups;
+    if (per_group < 1) per_group = 1;
+    if (per_group > n_row_tiles) per_group = n_row_tiles;
+    dim3 pgrid(per_group, groups);
+#define LAUNCH_P(E, F)                                                                        \
+  do {                                                                                        \
+    if (int e = set_smem((const void*)tc_gemm_nt_persist_kernel<E, F>, smem_p)) return e;     \
+    tc_gemm_nt_persist_kernel<E, F><<<pgrid, kThreads, smem_p, st>>>(p, n_row_tiles, n_tiles_n); \
+  } while (0)
+    if (epi == EPI_BIAS_ACT) { if (out_is_f32) LAUNCH_P(EPI_BIAS_ACT, true); else LAUNCH_P(EPI_BIAS_ACT, false); }
+    else { if (out_is_f32) LAUNCH_P(EPI_MUL_DACT, true); else LAUNCH_P(EPI_MUL_DACT, false); }
+#undef LAUNCH_P
+    MLI_LAUNCH_OK();
+    return MLI_OK;
+  }
   const size_t smem = (size_t)kNT_Stages * (kStageChunks * kTileM * 16 + kStageChunks * BN * 16);
   dim3 grid(N / BN, mli_cdiv(M, kTileM), batch);
-  cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_NT(E, F)                                                        \
   do {                                                                         \
     if (int e = set_smem((const void*)tc_gemm_nt_kernel<E, F>, smem)) return e;             \
