@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLI_ABI_VERSION 1
+#define MLI_ABI_VERSION 2
 
 enum {
   MLI_OK = 0,
@@ -84,10 +84,22 @@ int mli_hashgrid_corners(const mli_grid_t* grid, uint32_t level, const float* x0
 int mli_encode_rays(const mli_grid_t* grid, const float* table, const float* center, const float* ray_unit,
                     const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps,
                     float vol_min, float vol_max, float* X, int64_t ldx, void* stream);
-/* backward of mli_encode_rays w.r.t. the table: dX rows as above, enc columns only. */
+/* backward of mli_encode_rays w.r.t. the table: dX rows as above, enc columns only.
+ * delta_basis != 0: dX is the gradient w.r.t. the delta-basis rows of mli_encode_rays_tcl (plane 0 = SUM over the
+ * stencil planes of the per-plane gradients, plane i = tap i's own gradient). */
 int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, const float* ray_unit, const float* dists,
                         int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps, float vol_min,
-                        float vol_max, const float* dX, int64_t ldx, float* table_grad, void* stream);
+                        float vol_max, const float* dX, int64_t ldx, float* table_grad, int32_t delta_basis,
+                        void* stream);
+/* Tensor-core variant of mli_encode_rays (bf16 MLP-tile mode): writes the SDF trunk's input as split-bf16 TCL in the
+ * DELTA basis -- plane 0 rows = [enc | xyz | 0] of the centre point, plane i rows = row(tap i) - row(centre), the
+ * difference formed in fp32 BEFORE the down-cast (the 4-tap stencil does not survive bf16
+ * values, it does survive bf16 deltas).  X is TCL-128 with x_chunks >= 2*k_chunks chunks per tile row: chunks
+ * [0, k_chunks) = bf16(x), chunks [k_chunks, 2 k_chunks) = bf16(x - bf16(x)); chunk l < L is level l (F = 8),
+ * chunk L = [xyz | 0], the rest zero.  With taps, R*n must be a multiple of 128. */
+int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, const float* center, const float* ray_unit,
+                        const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps,
+                        float vol_min, float vol_max, void* X, int32_t x_chunks, int32_t k_chunks, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Dense layers (replace torch.nn.Linear + weight_norm + activation: mlp.py:55-69, nerf_util.py:186-196)
@@ -124,6 +136,9 @@ int mli_linear_wgrad(const float* dZ, int64_t lddz, int64_t sdz, const float* X,
  * tile row and `tile_rows`-row tiles; rows >= M / columns >= cols are zero-filled. */
 int mli_tc_to_tcl(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
                   int32_t dst_chunks, int32_t chunk0, int32_t n_chunks, void* stream);
+/* split-bf16 variant: chunks [chunk0, +n_chunks) = bf16(x), chunks [lo_chunk0, +n_chunks) = bf16(x - bf16(x)). */
+int mli_tc_to_tcl_split(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
+                        int32_t dst_chunks, int32_t chunk0, int32_t lo_chunk0, int32_t n_chunks, void* stream);
 int mli_tc_from_tcl(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* dst,
                     int64_t ld, void* stream);
 /* Forward / data-gradient GEMM on TCL operands, fused epilogue:
@@ -138,6 +153,31 @@ int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_b
                   void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
                   int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
                   void* stream);
+/* SDF trunk on the tensor cores (replaces MLPforNeuralSDF layer 0 + softplus + linear_sdf, mlp.py:55-69, for every
+ * stencil plane; the numerical-gradient taps of modules.py:131-177 go through as fp32-formed deltas).
+ *   X      split-bf16 TCL rows from mli_encode_rays_tcl (x_chunks chunks per tile row, K = 8*k_chunks padded inputs)
+ *   W0s    layer-0 weights [256, K] as split-bf16 TCL with 256-row tiles (mli_tc_to_tcl_split), b0 [256]
+ *   three tcgen05 products per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) ~ 16 mantissa bits
+ * mode 0 (centre rows):  z0 = x0 W0^T + b0;  sigma0 = sigmoid(100 z0) -> fp32 "TCL32" [rows/128][64][128][4];
+ *                        h0 = softplus100(z0) -> bf16 TCL (32 chunks);  vec_out[row] = w_sdf . h0 + b_sdf
+ * mode 1 (tap rows, `rows` = taps * rows_per_plane):  dz = dx W0^T;  dh = log1p(expm1(100 dz) sigma0) / 100
+ *                        (= softplus(z0 + dz) - softplus(z0));  vec_out[row] = w_sdf . dh  (= sdf_tap - sdf_centre);
+ *                        dz -> bf16 TCL at h_or_dz unless NULL (only the backward pass needs it)
+ * mode 2 (SDF only, e.g. sampling queries): vec_out[row] = w_sdf . softplus100(x W0^T + b0) + b_sdf */
+int mli_tc_sdf_trunk_fwd(const void* X, int32_t x_chunks, int32_t K, const void* W0s, const float* b0,
+                         const float* w_sdf, const float* b_sdf, int64_t rows, int32_t mode, int64_t rows_per_plane,
+                         float* sigma0, void* h_or_dz, float* vec_out, void* stream);
+/* Backward of the trunk's activation / SDF head in the delta basis.  g [(1+taps)*M] = dL/d sdf of every stencil plane
+ * (mli_geometry_bwd), dH0 = dL/d h0 arriving through layer 1 (bf16 TCL, 32 chunks, may be NULL).  Writes Ed (bf16 TCL,
+ * (1+taps)*M rows x 32 chunks): plane 0 = E = sum over planes of e_p, plane i = e_i, with
+ *   e_0 = (g_0 w_sdf + dH0) sigma0,   e_i = g_i w_sdf sigmoid(100 (z0 + dz_i))
+ * so that dW0 = Ed^T Xd, d Xd = Ed W0, db0 = colsum(E) in the basis of mli_encode_rays_tcl.
+ * dw_sdf [256] / db_sdf [1] may be NULL (heads-only training). ws: mli_tc_sdf_trunk_bwd_ws_bytes(). M % 128 == 0. */
+int64_t mli_tc_sdf_trunk_bwd_ws_bytes(int64_t M);
+int mli_tc_sdf_trunk_bwd(const float* g, int64_t M, int32_t taps, const float* sigma0, const void* dz, const void* dH0,
+                         const void* h0, const float* w_sdf, void* Ed, float* dw_sdf, float* db_sdf, void* ws,
+                         void* stream);
+
 /* Weight-gradient GEMM: out[b][r, c] = sum_m L[m, 8*(l_chunk0 + b*l_batch_chunks) + r] * R[m, 8*(r_chunk0 +
  * b*r_batch_chunks) + c]; r < rows_out (multiple of 128), c < cols_out (multiple of 16; < 256 or a multiple of 256).
  * L, R: TCL-128 (the same bytes serve as MN-major operands).  Split over row tiles, deterministic reduction.
@@ -220,10 +260,12 @@ int mli_sample_merge(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n
  * [pts(3) | SH(view)(16) | normal(3) | SH(light position)(16)]; columns beyond that up to ldxh are zeroed.
  * tap_eps is the per-axis offset as a double (eps/sqrt(3) for 4 taps); the float32 divisors 4e, e^2 are derived
  * from it exactly as torch derives them from the Python float. */
+/* sdf_is_delta != 0: planes >= 1 of `sdf` hold sdf_tap - sdf_centre (mli_tc_sdf_trunk_fwd mode 1) instead of
+ * absolute values; they are left as deltas. */
 int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, double tap_eps, const uint8_t* outside,
                      float outside_val, const float* center, const float* ray_unit, const float* pts_light,
                      const float* dists, int64_t ld_d, float* gradients, float* hessians, float* XH, int64_t ldxh,
-                     int32_t xh_off, void* stream);
+                     int32_t xh_off, int32_t sdf_is_delta, void* stream);
 /* d_sdf [planes*M] = backward of gradients/hessians/normals (+ d_sdf_center_in from the alpha path).
  * d_grad_in / d_hess_in [M,3] may be NULL; dXH supplies d normal at columns xh_off+19..21 (may be NULL). */
 int mli_geometry_bwd(const float* gradients, int64_t M, int32_t N, int32_t taps, double tap_eps,

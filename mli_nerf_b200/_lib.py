@@ -106,10 +106,11 @@ def load():
         fn.argtypes = [_CTYPE[c] for c in sig]
         fn.restype = C.c_int
     for name in ("mli_linear_wgrad_ws_bytes", "mli_rowdot_bwd_ws_bytes", "mli_losses_ws_bytes", "mli_tc_wgrad_ws_bytes",
-                 "mli_tc_colsum_ws_bytes"):
+                 "mli_tc_colsum_ws_bytes", "mli_tc_sdf_trunk_bwd_ws_bytes"):
         getattr(lib, name).restype = C.c_int64
     lib.mli_tc_wgrad_ws_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
     lib.mli_tc_colsum_ws_bytes.argtypes = [C.c_int64, C.c_int32]
+    lib.mli_tc_sdf_trunk_bwd_ws_bytes.argtypes = [C.c_int64]
     lib.mli_linear_wgrad_ws_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
     lib.mli_rowdot_bwd_ws_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
     lib.mli_losses_ws_bytes.argtypes = [C.c_int64, C.c_int64]
@@ -168,6 +169,8 @@ def _n_launches(name, args):
     """How many of our kernels one call launches (for bench.py's gpu_launches claim)."""
     if name in ("mli_linear_wgrad", "mli_tc_wgrad", "mli_tc_colsum"):
         return 2
+    if name == "mli_tc_sdf_trunk_bwd":
+        return 2 if args[9] is not None else 1
     if name == "mli_rowdot_bwd":
         return (1 if args[10] is not None else 0) + (2 if args[14] is not None else 0)
     if name == "mli_composite_bwd":

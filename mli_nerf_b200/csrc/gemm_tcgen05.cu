@@ -24,6 +24,7 @@
 // CTAs, fp32 partials + fixed-order reduction (deterministic).
 // Roofline: tensor pipe (2 * M * N * K flops per call); operands stream from L2/HBM at (128+BN)*2 B per 128*BN MACs.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -118,9 +119,11 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// NT kernel: out[128 x BN tile] = epi(A[128 x K] . B[BN x K]^T)
+// NT kernels: out[128 x BN tile] = epi(A[128 x K] . B[BN x K]^T)
+// Epilogues are compile-time (EPI, ACT, OUT_F32): a runtime activation switch inlined into the unrolled column loop
+// made the first version 23k instructions long and instruction-cache bound (profiles/r01_summary.md).
 // ---------------------------------------------------------------------------------------------------------------
-enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1 };
+enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_SDF_CENTER = 2, EPI_SDF_TAP = 3, EPI_SDF_ONLY = 4 };
 
 struct TcNT {
   const __nv_bfloat16* A; int a_chunks, a_chunk0, a_batch_chunks;   // TCL-128, chunks per tile row, first chunk
@@ -131,10 +134,81 @@ struct TcNT {
   void* out; int out_chunks, out_chunk0, out_batch_chunks;          // bf16 TCL-128 ...
   int64_t ldo; int out_col0, out_batch_cols;                        // ... or fp32 row-major
   int64_t M;
-  int act;
+  // split-bf16 operands: A and B both hold [hi | lo] halves of k_chunks chunks each; the MMA warp issues the three
+  // products hi*hi + hi*lo + lo*hi (~16 mantissa bits) into the same fp32 accumulator
+  int split, stage_chunks;
+  // SDF trunk epilogues (EPI_SDF_*): SDF head weights, per-row output, sigma(100 z0) in fp32 TCL32
+  const float* w2; const float* b2; float* vec_out; float* s0; int tiles_per_plane;
 };
 
-template <int EPI, bool OUT_F32>
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float x) {
+  if constexpr (ACT == MLI_ACT_RELU) return x > 0.0f ? x : 0.0f;
+  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return mli_softplus100(x);
+  else if constexpr (ACT == MLI_ACT_SIGMOID) return mli_sigmoid(x);
+  else return x;
+}
+template <int ACT>
+__device__ __forceinline__ float act_dfo(float y) {
+  if constexpr (ACT == MLI_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
+  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return y > 0.2f ? 1.0f : 1.0f - __expf(-100.0f * y);  // y is bf16 anyway
+  else if constexpr (ACT == MLI_ACT_SIGMOID) return y * (1.0f - y);
+  else return 1.0f;
+}
+
+// one 32-column chunk of the generic epilogues: v[] = accumulator row slice -> global memory
+template <int EPI, int ACT, bool OUT_F32>
+__device__ __forceinline__ void epi_generic_chunk(const TcNT& p, float* v, int ncol, int c0, int n0, int batch, int tile_m,
+                                                  int r_local, int64_t row, const float* bias, const uint4* auxr) {
+  if constexpr (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g * 4 < ncol) {
+        float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[g * 4 + 0] = act_fwd<ACT>(v[g * 4 + 0] + b4.x);
+        v[g * 4 + 1] = act_fwd<ACT>(v[g * 4 + 1] + b4.y);
+        v[g * 4 + 2] = act_fwd<ACT>(v[g * 4 + 2] + b4.z);
+        v[g * 4 + 3] = act_fwd<ACT>(v[g * 4 + 3] + b4.w);
+      }
+    }
+  } else if (auxr != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < ncol) {
+        float y[8];
+        unpack8(auxr[g], y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[g * 8 + i] *= act_dfo<ACT>(y[i]);
+      }
+    }
+  }
+  if constexpr (OUT_F32) {
+    if (row < p.M) {
+      float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+  } else {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                         ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
+                         r_local * 8;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+  }
+}
+
+__device__ __forceinline__ void load_aux_chunk(const TcNT& p, int batch, int tile_m, int r_local, int col, int ncol, uint4* auxr) {
+  const __nv_bfloat16* aux = p.aux + ((int64_t)tile_m * p.aux_chunks + p.aux_chunk0 + (int64_t)batch * p.aux_batch_chunks + col / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g * 8 < ncol) auxr[g] = __ldg(reinterpret_cast<const uint4*>(aux + (int64_t)g * kTileM * 8));
+}
+
+// Non-persistent variant (used when the weight tile does not fit in shared memory next to the activation ring):
+// one CTA = one [128 x BN] output tile, K streamed in stages of 64 through a 2-stage ring, two CTAs per SM.
+template <int EPI, int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * kNT_Stages + 1];
@@ -147,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kNT_Stages]), accum_bar = smem_u32(&bars[2 * kNT_Stages]);
   const int n_kt = (p.k_chunks + kStageChunks - 1) / kStageChunks;
-  const uint32_t tmem_cols = tmem_cols_pow2(BN);
+  const uint32_t tmem_cols = tmem_cols_pow2((BN + 31) / 32 * 32);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kNT_Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -200,46 +274,23 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
     const int q = warp & 3;
     const int r_local = q * 32 + lane;
     const int64_t row = (int64_t)tile_m * kTileM + r_local;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const int n0 = tile_n * BN;
     const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? p.bias + batch * p.bias_batch + n0 : nullptr;
+    const bool has_aux = (EPI == EPI_MUL_DACT) && p.aux != nullptr;
+    uint4 auxr[4];
+    if (has_aux) load_aux_chunk(p, batch, tile_m, r_local, n0, min(32, BN), auxr);
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
       const int ncol = min(32, BN - c0);  // BN is a multiple of 16
-      if (EPI == EPI_BIAS_ACT) {
+      uint4 cur[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (i < ncol) v[i] = mli_act(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), p.act);
-      } else if (p.aux) {
-        const __nv_bfloat16* aux = p.aux + ((int64_t)tile_m * p.aux_chunks + p.aux_chunk0 + (int64_t)batch * p.aux_batch_chunks +
-                                            (n0 + c0) / 8) * (kTileM * 8) + r_local * 8;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 < ncol) {
-            float y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(aux + (int64_t)g * kTileM * 8)), y);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[g * 8 + i] *= mli_dact_from_out(y[i], p.act);
-          }
-        }
-      }
-      if (OUT_F32) {
-        if (row < p.M) {
-          float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        }
-      } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                             ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
-                             r_local * 8;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
-      }
+      for (int g = 0; g < 4; ++g) cur[g] = auxr[g];
+      if (has_aux && c0 + 32 < BN) load_aux_chunk(p, batch, tile_m, r_local, n0 + c0 + 32, min(32, BN - c0 - 32), auxr);
+      epi_generic_chunk<EPI, ACT, OUT_F32>(p, v, ncol, c0, n0, batch, tile_m, r_local, row, bias, has_aux ? cur : nullptr);
     }
   }
   tc_fence_before();
@@ -255,36 +306,64 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
 // (loaded once by TMA), streams 128-row activation tiles through a 4-stage ring, accumulates into one of TWO TMEM
 // buffers so the epilogue of tile i overlaps the MMAs of tile i+1, and prefetches the epilogue's `aux` operand
 // (previous layer's output, for the activation derivative) into registers before it waits for the accumulator.
-// Used whenever K*BN*2 B + 64 KB fits in shared memory (every layer except the K = 768 feature data-gradient).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..9 = epilogue.  A warp may only touch the TMEM
+// lane quarter warp%4, so two warps share each quarter and take alternate 32-column chunks.
+// The same main loop serves the SDF trunk (EPI_SDF_*): split-bf16 operands (3 MMA passes per k-step), epilogue =
+// softplus + the 256->1 SDF head as an in-register row dot (the hidden activations of the tap planes never reach HBM).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kP_Stages = 4;
+constexpr int kP_EpiWarps = 8;
+constexpr int kP_Threads = 64 + 32 * kP_EpiWarps;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kP_EpiWarps) : "memory"); }
 
-template <int EPI, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_persist_kernel(TcNT p, int n_row_tiles, int n_tiles_n) {
+// expm1 / log1p for the tap epilogue: MUFU-based away from 0, 4-term Taylor near 0 (relative error < 3e-6 either way)
+__device__ __forceinline__ float fast_expm1(float t) {
+  const float big = __expf(t) - 1.0f;
+  const float small = t * (1.0f + t * (0.5f + t * (0.16666667f + t * 0.041666668f)));
+  return fabsf(t) < 0.03f ? small : big;
+}
+__device__ __forceinline__ float fast_log1p(float q) {
+  const float big = __logf(1.0f + q);
+  const float small = q * (1.0f + q * (-0.5f + q * (0.33333334f - q * 0.25f)));
+  return fabsf(q) < 0.03f ? small : big;
+}
+
+template <int EPI, int ACT, bool OUT_F32>
+__global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT p, int n_row_tiles, int n_tiles_n) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * kP_Stages + 4];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_b0[256];
+  __shared__ __align__(16) float s_w2[256];
+  __shared__ float s_part[2][kTileM];
+  constexpr bool kSdf = EPI >= EPI_SDF_CENTER;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.y % n_tiles_n, batch = blockIdx.y / n_tiles_n;
   const int BN = p.BN;
-  const uint32_t b_bytes = (uint32_t)p.k_chunks * BN * 16;
+  const int kc_total = p.split ? 2 * p.k_chunks : p.k_chunks;   // A (and B) chunks per tile incl. the lo half
+  const int stage_chunks = p.stage_chunks;
+  const uint32_t b_bytes = (uint32_t)kc_total * BN * 16;
   const uint32_t a_stage_bytes = kStageChunks * kTileM * 16;
   const uint32_t sB = smem_u32(smem), sA = sB + b_bytes;
   const uint32_t b_full = smem_u32(&bars[0]);
   const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kP_Stages]);
   const uint32_t t_full0 = smem_u32(&bars[1 + 2 * kP_Stages]), t_empty0 = smem_u32(&bars[1 + 2 * kP_Stages + 2]);
-  const int n_kt = (p.k_chunks + kStageChunks - 1) / kStageChunks;
-  const uint32_t tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  const int n_kt = (kc_total + stage_chunks - 1) / stage_chunks;
+  const uint32_t acc_stride = (BN + 31) / 32 * 32;
+  const uint32_t tmem_cols = 2 * acc_stride <= 32 ? 32 : 2 * acc_stride <= 64 ? 64 : 2 * acc_stride <= 128 ? 128 : 2 * acc_stride <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
     for (int s = 0; s < kP_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(t_full0 + 8 * a, 1); mbar_init(t_empty0 + 8 * a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(t_full0 + 8 * a, 1); mbar_init(t_empty0 + 8 * a, kP_EpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (kSdf) {
+    for (int i = threadIdx.x; i < 256; i += kP_Threads) { s_b0[i] = p.bias[i]; s_w2[i] = p.w2[i]; }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
@@ -298,11 +377,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_persist_kernel(TcNT p,
   if (warp == 0) {
     if (lane == 0) {
       // weights: resident for the whole kernel
-      const __nv_bfloat16* b_src = p.B + batch * p.b_batch_elems + (int64_t)tile_n * p.k_chunks * BN * 8;
+      const __nv_bfloat16* b_src = p.B + batch * p.b_batch_elems + (int64_t)tile_n * kc_total * BN * 8;
       mbar_expect_tx(b_full, b_bytes);
-      for (int kt = 0; kt < n_kt; ++kt) {
-        const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
-        bulk_g2s(sB + kt * kStageChunks * BN * 16, b_src + (int64_t)kt * kStageChunks * BN * 8, nch * BN * 16, b_full);
+      for (int c = 0; c < kc_total; c += kStageChunks) {
+        const int nch = min(kStageChunks, kc_total - c);
+        bulk_g2s(sB + c * BN * 16, b_src + (int64_t)c * BN * 8, nch * BN * 16, b_full);
       }
       uint32_t cnt = 0;
       for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x) {
@@ -310,9 +389,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_persist_kernel(TcNT p,
         for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
           const uint32_t s = cnt % kP_Stages;
           if (cnt >= kP_Stages) mbar_wait(a_empty0 + 8 * s, ((cnt / kP_Stages) - 1) & 1);
-          const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
+          const int nch = min(stage_chunks, kc_total - kt * stage_chunks);
           mbar_expect_tx(a_full0 + 8 * s, nch * kTileM * 16);
-          bulk_g2s(sA + s * a_stage_bytes, a_src + (int64_t)kt * kStageChunks * kTileM * 8, nch * kTileM * 16, a_full0 + 8 * s);
+          bulk_g2s(sA + s * a_stage_bytes, a_src + (int64_t)kt * stage_chunks * kTileM * 8, nch * kTileM * 16, a_full0 + 8 * s);
         }
       }
     }
@@ -326,81 +405,150 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_nt_persist_kernel(TcNT p,
         const uint32_t acc = it & 1;
         if (it >= 2) mbar_wait(t_empty0 + 8 * acc, ((it >> 1) - 1) & 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        uint32_t first = 1;
         for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
           const uint32_t s = cnt % kP_Stages;
           mbar_wait(a_full0 + 8 * s, (cnt / kP_Stages) & 1);
           tc_fence_after();
-          const int nch = min(kStageChunks, p.k_chunks - kt * kStageChunks);
-          const uint32_t sa = sA + s * a_stage_bytes, sb = sB + kt * kStageChunks * lbo_b;
-          for (int kk = 0; kk < nch / 2; ++kk)
-            umma(d_tmem, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb + kk * 2 * lbo_b, lbo_b, 128), idesc, (kt | kk) != 0);
+          const int c_begin = kt * stage_chunks;
+          const int nch = min(stage_chunks, kc_total - c_begin);
+          const uint32_t sa = sA + s * a_stage_bytes;
+          if (!p.split) {
+            const uint32_t sb = sB + c_begin * lbo_b;
+            for (int kk = 0; kk < nch / 2; ++kk) {
+              umma(d_tmem, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb + kk * 2 * lbo_b, lbo_b, 128), idesc, first ^ 1u);
+              first = 0;
+            }
+          } else if (c_begin < p.k_chunks) {  // A hi stage: x B hi and x B lo
+            const uint32_t sb_hi = sB + c_begin * lbo_b, sb_lo = sB + (p.k_chunks + c_begin) * lbo_b;
+            for (int kk = 0; kk < nch / 2; ++kk) {
+              const uint64_t da = make_desc(sa + kk * 2 * lbo_a, lbo_a, 128);
+              umma(d_tmem, da, make_desc(sb_hi + kk * 2 * lbo_b, lbo_b, 128), idesc, first ^ 1u);
+              first = 0;
+              umma(d_tmem, da, make_desc(sb_lo + kk * 2 * lbo_b, lbo_b, 128), idesc, 1u);
+            }
+          } else {                            // A lo stage: x B hi
+            const uint32_t sb_hi = sB + (c_begin - p.k_chunks) * lbo_b;
+            for (int kk = 0; kk < nch / 2; ++kk)
+              umma(d_tmem, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb_hi + kk * 2 * lbo_b, lbo_b, 128), idesc, 1u);
+          }
           umma_commit(a_empty0 + 8 * s);
         }
         umma_commit(t_full0 + 8 * acc);
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which of the two warps of this quarter (takes chunks half, half+2, ..)
     const int r_local = q * 32 + lane;
     const int n0 = tile_n * BN;
+    const int n_cc = (BN + 31) / 32;
     const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? p.bias + batch * p.bias_batch + n0 : nullptr;
+    const bool has_aux = (EPI == EPI_MUL_DACT) && p.aux != nullptr;
     uint32_t it = 0;
     for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       const int64_t row = (int64_t)tile_m * kTileM + r_local;
-      uint4 auxr[32];
-      if (EPI == EPI_MUL_DACT) {
-        if (p.aux) {  // issue every load of this row before waiting: latency hides behind the tile's MMAs
-          const __nv_bfloat16* aux = p.aux + ((int64_t)tile_m * p.aux_chunks + p.aux_chunk0 + (int64_t)batch * p.aux_batch_chunks + n0 / 8) * (kTileM * 8) + r_local * 8;
+      uint4 auxr[4][4];
+      if constexpr (EPI == EPI_MUL_DACT) {
+        if (has_aux) {  // issue every load of this row before waiting: latency hides behind the tile's MMAs
 #pragma unroll
-          for (int g = 0; g < 32; ++g)
-            if (g * 8 < BN) auxr[g] = __ldg(reinterpret_cast<const uint4*>(aux + (int64_t)g * kTileM * 8));
+          for (int k = 0; k < 4; ++k) {
+            const int cc = half + 2 * k;
+            if (cc < n_cc) load_aux_chunk(p, batch, tile_m, r_local, n0 + cc * 32, min(32, BN - cc * 32), auxr[k]);
+          }
         }
       }
+      // sigma(100 z0) of the centre sample of each tap row (fp32 TCL32: [tile][256/4][128][4])
+      const float* s0_src = nullptr;
+      float4 s0r[8];
+      if constexpr (EPI == EPI_SDF_TAP) {
+        s0_src = p.s0 + ((int64_t)(tile_m % p.tiles_per_plane) * 64 * kTileM + r_local) * 4;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s0r[g] = __ldg(reinterpret_cast<const float4*>(s0_src + (int64_t)(half * 8 + g) * kTileM * 4));
+      }
+      float dot = 0.0f;
       mbar_wait(t_full0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int c0 = cc * 32;
-        if (c0 < BN) {
+      bool released = false;
+      // MUL_DACT indexes its prefetched aux registers by k (must unroll); the math-heavy epilogues stay rolled to keep
+      // the kernel inside the instruction cache
+#pragma unroll (EPI == EPI_MUL_DACT ? 4 : 1)
+      for (int k = 0; k < 4; ++k) {
+        const int cc = half + 2 * k;
+        if (cc < n_cc) {
+          const int c0 = cc * 32;
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
-          if (c0 + 32 >= BN) {  // last read of this accumulator: hand it back to the MMA warp
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride + c0, v);
+          if (cc + 2 >= n_cc) {  // last read of this accumulator by this warp: hand it back to the MMA warp
             tc_fence_before();
-            mbar_arrive(t_empty0 + 8 * acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty0 + 8 * acc);
+            released = true;
           }
           const int ncol = min(32, BN - c0);
-          if (EPI == EPI_BIAS_ACT) {
+          if constexpr (!kSdf) {
+            epi_generic_chunk<EPI, ACT, OUT_F32>(p, v, ncol, c0, n0, batch, tile_m, r_local, row, bias, has_aux ? auxr[k] : nullptr);
+          } else if constexpr (EPI == EPI_SDF_TAP) {
+            // v = dz = W0 (x_tap - x_centre).  dh = softplus(z0 + dz) - softplus(z0) = log1p(expm1(100 dz) * sigma0) / 100
+            float4 cur[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncol) v[i] = mli_act(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), p.act);
-          } else if (p.aux) {
+            for (int g = 0; g < 8; ++g) cur[g] = s0r[g];
+            if (k < 3) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncol) {
-                float y[8];
-                unpack8(auxr[cc * 4 + g], y);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[g * 8 + i] *= mli_dact_from_out(y[i], p.act);
-              }
+              for (int g = 0; g < 8; ++g) s0r[g] = __ldg(reinterpret_cast<const float4*>(s0_src + (int64_t)((cc + 2) * 8 + g) * kTileM * 4));
             }
-          }
-          if (OUT_F32) {
-            if (row < p.M) {
-              float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
+            const float* sg = reinterpret_cast<const float*>(cur);
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            for (int i = 0; i < 32; ++i) {
+              const float t = fminf(fmaxf(100.0f * v[i], -80.0f), 80.0f);
+              const float dh = fast_log1p(fast_expm1(t) * sg[i]) * 0.01f;
+              dot = fmaf(s_w2[c0 + i], dh, dot);
+            }
+            if (p.out) {  // dz (bf16 TCL) for the backward pass
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)tile_m * p.out_chunks + c0 / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
             }
           } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                 ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
-                                 r_local * 8;
+            // centre / sdf-only rows: z = acc + b0, h = softplus100(z), sdf += w_sdf . h
+            float sg[32];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+            for (int i = 0; i < 32; ++i) {
+              const float z = v[i] + s_b0[c0 + i];
+              const float bz = 100.0f * z;
+              float h, s;
+              if (bz > 20.0f) { h = z; s = 1.0f / (1.0f + __expf(-bz)); }
+              else { const float e = expf(bz); h = log1pf(e) * 0.01f; s = e / (1.0f + e); }
+              dot = fmaf(s_w2[c0 + i], h, dot);
+              v[i] = h;
+              sg[i] = s;
+            }
+            if constexpr (EPI == EPI_SDF_CENTER) {
+              float* sdst = p.s0 + ((int64_t)tile_m * 64 * kTileM + (int64_t)(c0 / 4) * kTileM + r_local) * 4;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(sdst + (int64_t)g * kTileM * 4) = make_float4(sg[g * 4], sg[g * 4 + 1], sg[g * 4 + 2], sg[g * 4 + 3]);
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)tile_m * p.out_chunks + c0 / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+            }
           }
+        }
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty0 + 8 * acc);
+      }
+      if constexpr (kSdf) {  // combine the two column halves of each row (fixed order: deterministic)
+        if (half == 1) s_part[it & 1][r_local] = dot;
+        epi_bar_sync();
+        if (half == 0 && row < p.M) {
+          float r = dot + s_part[it & 1][r_local];
+          if constexpr (EPI != EPI_SDF_TAP) r += p.b2[0];
+          p.vec_out[row] = r;
         }
       }
     }
@@ -538,7 +686,7 @@ __global__ void tn_reduce_kernel(const float* __restrict__ part, int S, int rows
 // that has `dst_chunks` chunks per tile.  Rows >= M and columns >= cols are zero-filled.
 __global__ void __launch_bounds__(256) to_tcl_kernel(const float* __restrict__ src, int64_t ld, int64_t M, int cols,
                                                      __nv_bfloat16* __restrict__ dst, int tile_rows, int dst_chunks,
-                                                     int chunk0, int n_chunks, int64_t m_padded) {
+                                                     int chunk0, int n_chunks, int64_t m_padded, int lo_chunk0) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m_padded * n_chunks) return;
   const int64_t tile = e / ((int64_t)tile_rows * n_chunks);
@@ -552,6 +700,11 @@ __global__ void __launch_bounds__(256) to_tcl_kernel(const float* __restrict__ s
     v[i] = (m < M && c < cols) ? src[m * ld + c] : 0.0f;
   }
   *reinterpret_cast<uint4*>(dst + ((tile * dst_chunks + chunk0 + j) * tile_rows + r) * 8) = pack8(v);
+  if (lo_chunk0 >= 0) {  // split-bf16: second half holds x - bf16(x)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] -= __bfloat162float(__float2bfloat16_rn(v[i]));
+    *reinterpret_cast<uint4*>(dst + ((tile * dst_chunks + lo_chunk0 + j) * tile_rows + r) * 8) = pack8(v);
+  }
 }
 
 __global__ void __launch_bounds__(256) from_tcl_kernel(const __nv_bfloat16* __restrict__ src, int src_chunks, int chunk0,
@@ -642,7 +795,22 @@ extern "C" int mli_tc_to_tcl(const float* src, int64_t ld, int64_t M, int32_t co
   const int64_t m_padded = (M + tile_rows - 1) / tile_rows * tile_rows;
   if (m_padded == 0) return MLI_OK;
   to_tcl_kernel<<<mli_cdiv(m_padded * n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, ld, M, cols, (__nv_bfloat16*)dst, tile_rows, dst_chunks, chunk0, n_chunks, m_padded);
+      src, ld, M, cols, (__nv_bfloat16*)dst, tile_rows, dst_chunks, chunk0, n_chunks, m_padded, -1);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+// split-bf16 variant: chunks [chunk0, +n) receive bf16(x), chunks [lo_chunk0, +n) receive bf16(x - bf16(x))
+extern "C" int mli_tc_to_tcl_split(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
+                                   int32_t dst_chunks, int32_t chunk0, int32_t lo_chunk0, int32_t n_chunks, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 0 && cols >= 0 && n_chunks >= 1 && chunk0 >= 0 && chunk0 + n_chunks <= dst_chunks, "to_tcl_split: bad chunk range");
+  MLI_REQUIRE(lo_chunk0 >= chunk0 + n_chunks && lo_chunk0 + n_chunks <= dst_chunks, "to_tcl_split: bad lo chunk range");
+  MLI_REQUIRE(tile_rows >= 16 && tile_rows <= 256 && tile_rows % 16 == 0, "to_tcl_split: tile_rows must be a multiple of 16 <= 256");
+  const int64_t m_padded = (M + tile_rows - 1) / tile_rows * tile_rows;
+  if (m_padded == 0) return MLI_OK;
+  to_tcl_kernel<<<mli_cdiv(m_padded * n_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld, M, cols, (__nv_bfloat16*)dst, tile_rows, dst_chunks, chunk0, n_chunks, m_padded, lo_chunk0);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }
@@ -659,6 +827,46 @@ extern "C" int mli_tc_from_tcl(const void* src, int32_t src_chunks, int32_t chun
   return MLI_OK;
 }
 
+namespace {
+
+template <int EPI, int ACT, bool OUT_F32>
+int launch_nt(const TcNT& p, int N, int batch, cudaStream_t st) {
+  const int BN = p.BN;
+  const int kc_total = p.split ? 2 * p.k_chunks : p.k_chunks;
+  const size_t smem_p = (size_t)kc_total * BN * 16 + (size_t)kP_Stages * kStageChunks * kTileM * 16;
+  if (smem_p <= 220 * 1024) {  // persistent weight-stationary kernel
+    const int n_tiles_n = N / BN, groups = n_tiles_n * batch;
+    const int n_row_tiles = (int)mli_cdiv(p.M, kTileM);
+    int per_group = MLI_NUM_SMS / groups;
+    if (per_group < 1) per_group = 1;
+    if (per_group > n_row_tiles) per_group = n_row_tiles;
+    dim3 pgrid(per_group, groups);
+    if (int e = set_smem((const void*)tc_gemm_nt_persist_kernel<EPI, ACT, OUT_F32>, smem_p)) return e;
+    tc_gemm_nt_persist_kernel<EPI, ACT, OUT_F32><<<pgrid, kP_Threads, smem_p, st>>>(p, n_row_tiles, n_tiles_n);
+    MLI_LAUNCH_OK();
+    return MLI_OK;
+  }
+  if constexpr (EPI <= EPI_MUL_DACT) {
+    MLI_REQUIRE(!p.split, "tc_linear: split operands need the weight tile to fit in shared memory");
+    const size_t smem = (size_t)kNT_Stages * (kStageChunks * kTileM * 16 + kStageChunks * BN * 16);
+    dim3 grid(N / BN, mli_cdiv(p.M, kTileM), batch);
+    if (int e = set_smem((const void*)tc_gemm_nt_kernel<EPI, ACT, OUT_F32>, smem)) return e;
+    tc_gemm_nt_kernel<EPI, ACT, OUT_F32><<<grid, kThreads, smem, st>>>(p);
+    MLI_LAUNCH_OK();
+    return MLI_OK;
+  } else {
+    mli_set_error("tc_sdf_trunk: weight tile does not fit in shared memory");
+    return MLI_EINVAL;
+  }
+}
+
+template <int EPI, int ACT>
+int launch_nt_f(const TcNT& p, int N, int batch, bool f32, cudaStream_t st) {
+  return f32 ? launch_nt<EPI, ACT, true>(p, N, batch, st) : launch_nt<EPI, ACT, false>(p, N, batch, st);
+}
+
+}  // namespace
+
 extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
                              int64_t b_batch_elems, int32_t K, int32_t N, int32_t BN, const float* bias, int32_t bias_batch,
                              const void* aux, int32_t aux_chunks, int32_t aux_chunk0, int32_t aux_batch_chunks, int32_t act,
@@ -671,47 +879,64 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
   MLI_REQUIRE(a_chunk0 >= 0 && a_chunk0 + (batch - 1) * a_batch_chunks + K / 8 <= a_chunks, "tc_linear: A chunk range");
   MLI_REQUIRE(epi == EPI_BIAS_ACT || epi == EPI_MUL_DACT, "tc_linear: unknown epilogue");
   MLI_REQUIRE(act >= MLI_ACT_NONE && act <= MLI_ACT_SIGMOID, "tc_linear: unknown activation");
+  MLI_REQUIRE(epi == EPI_BIAS_ACT || act != MLI_ACT_SIGMOID || aux == nullptr, "tc_linear: sigmoid derivative epilogue is not built");
+  MLI_REQUIRE(bias == nullptr || (((uintptr_t)bias & 15) == 0 && bias_batch % 4 == 0), "tc_linear: bias must be 16-byte aligned");
   if (!out_is_f32) MLI_REQUIRE(out_chunk0 >= 0 && out_chunk0 + (batch - 1) * out_batch_chunks + N / 8 <= out_chunks, "tc_linear: out chunk range");
   if (aux) MLI_REQUIRE(aux_chunk0 >= 0 && aux_chunk0 + (batch - 1) * aux_batch_chunks + N / 8 <= aux_chunks, "tc_linear: aux chunk range");
   TcNT p;
+  memset(&p, 0, sizeof(p));
   p.A = (const __nv_bfloat16*)A; p.a_chunks = a_chunks; p.a_chunk0 = a_chunk0; p.a_batch_chunks = a_batch_chunks;
   p.B = (const __nv_bfloat16*)B; p.b_batch_elems = b_batch_elems; p.k_chunks = K / 8; p.BN = BN;
   p.bias = bias; p.bias_batch = bias_batch;
   p.aux = (const __nv_bfloat16*)aux; p.aux_chunks = aux_chunks; p.aux_chunk0 = aux_chunk0; p.aux_batch_chunks = aux_batch_chunks;
   p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks;
-  p.ldo = ldo; p.out_col0 = out_col0; p.out_batch_cols = out_batch_cols; p.M = M; p.act = act;
+  p.ldo = ldo; p.out_col0 = out_col0; p.out_batch_cols = out_batch_cols; p.M = M;
+  p.split = 0; p.stage_chunks = kStageChunks;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem_p = (size_t)(K / 8) * BN * 16 + (size_t)kP_Stages * kStageChunks * kTileM * 16;
-  if (smem_p <= 225 * 1024) {  // persistent weight-stationary kernel
-    const int n_tiles_n = N / BN, groups = n_tiles_n * batch;
-    const int n_row_tiles = (int)mli_cdiv(M, kTileM);
-    int per_group = MLI_NUM_SMS / groups;
-    if (per_group < 1) per_group = 1;
-    if (per_group > n_row_tiles) per_group = n_row_tiles;
-    dim3 pgrid(per_group, groups);
-#define LAUNCH_P(E, F)                                                                        \
-  do {                                                                                        \
-    if (int e = set_smem((const void*)tc_gemm_nt_persist_kernel<E, F>, smem_p)) return e;     \
-    tc_gemm_nt_persist_kernel<E, F><<<pgrid, kThreads, smem_p, st>>>(p, n_row_tiles, n_tiles_n); \
-  } while (0)
-    if (epi == EPI_BIAS_ACT) { if (out_is_f32) LAUNCH_P(EPI_BIAS_ACT, true); else LAUNCH_P(EPI_BIAS_ACT, false); }
-    else { if (out_is_f32) LAUNCH_P(EPI_MUL_DACT, true); else LAUNCH_P(EPI_MUL_DACT, false); }
-#undef LAUNCH_P
-    MLI_LAUNCH_OK();
-    return MLI_OK;
+  const bool f32 = out_is_f32 != 0;
+  if (epi == EPI_BIAS_ACT) {
+    switch (act) {
+      case MLI_ACT_RELU: return launch_nt_f<EPI_BIAS_ACT, MLI_ACT_RELU>(p, N, batch, f32, st);
+      case MLI_ACT_SOFTPLUS100: return launch_nt_f<EPI_BIAS_ACT, MLI_ACT_SOFTPLUS100>(p, N, batch, f32, st);
+      case MLI_ACT_SIGMOID: return launch_nt_f<EPI_BIAS_ACT, MLI_ACT_SIGMOID>(p, N, batch, f32, st);
+      default: return launch_nt_f<EPI_BIAS_ACT, MLI_ACT_NONE>(p, N, batch, f32, st);
+    }
   }
-  const size_t smem = (size_t)kNT_Stages * (kStageChunks * kTileM * 16 + kStageChunks * BN * 16);
-  dim3 grid(N / BN, mli_cdiv(M, kTileM), batch);
-#define LAUNCH_NT(E, F)                                                        \
-  do {                                                                         \
-    if (int e = set_smem((const void*)tc_gemm_nt_kernel<E, F>, smem)) return e;             \
-    tc_gemm_nt_kernel<E, F><<<grid, kThreads, smem, st>>>(p);                  \
-  } while (0)
-  if (epi == EPI_BIAS_ACT) { if (out_is_f32) LAUNCH_NT(EPI_BIAS_ACT, true); else LAUNCH_NT(EPI_BIAS_ACT, false); }
-  else { if (out_is_f32) LAUNCH_NT(EPI_MUL_DACT, true); else LAUNCH_NT(EPI_MUL_DACT, false); }
-#undef LAUNCH_NT
-  MLI_LAUNCH_OK();
-  return MLI_OK;
+  if (aux == nullptr) act = MLI_ACT_NONE;
+  switch (act) {
+    case MLI_ACT_RELU: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_RELU>(p, N, batch, f32, st);
+    case MLI_ACT_SOFTPLUS100: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_SOFTPLUS100>(p, N, batch, f32, st);
+    default: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_NONE>(p, N, batch, f32, st);
+  }
+}
+
+// SDF trunk layer 0 + SDF head on split-bf16 operands (see the persistent kernel).  N = 256 hidden units.
+extern "C" int mli_tc_sdf_trunk_fwd(const void* X, int32_t x_chunks, int32_t K, const void* W0s, const float* b0,
+                                    const float* w_sdf, const float* b_sdf, int64_t rows, int32_t mode,
+                                    int64_t rows_per_plane, float* sigma0, void* h_or_dz, float* vec_out, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(rows >= 1 && K >= 16 && K % 16 == 0 && x_chunks >= K / 4, "tc_sdf_trunk: X must hold [hi | lo] halves of K/8 chunks each");
+  MLI_REQUIRE(mode >= 0 && mode <= 2, "tc_sdf_trunk: mode 0 (centre), 1 (taps) or 2 (sdf only)");
+  MLI_REQUIRE(b0 && w_sdf && b_sdf && vec_out, "tc_sdf_trunk: NULL argument");
+  MLI_REQUIRE(mode == 2 || sigma0 != nullptr, "tc_sdf_trunk: sigma0 is NULL");
+  MLI_REQUIRE(mode != 0 || h_or_dz != nullptr, "tc_sdf_trunk: centre mode needs the h0 output");
+  MLI_REQUIRE(mode != 1 || (rows_per_plane >= kTileM && rows_per_plane % kTileM == 0 && rows % rows_per_plane == 0),
+              "tc_sdf_trunk: tap rows must be whole planes of a multiple of 128 samples");
+  TcNT p;
+  memset(&p, 0, sizeof(p));
+  p.A = (const __nv_bfloat16*)X; p.a_chunks = x_chunks; p.B = (const __nv_bfloat16*)W0s;
+  p.k_chunks = K / 8; p.BN = 256; p.bias = b0; p.out = h_or_dz; p.out_chunks = 32; p.M = rows;
+  p.split = 1;
+  int sc = kStageChunks;  // even divisor of k_chunks, so that no stage straddles the hi/lo boundary
+  while (sc > 2 && (p.k_chunks % sc) != 0) sc -= 2;
+  MLI_REQUIRE(p.k_chunks % sc == 0, "tc_sdf_trunk: K/8 must be even");
+  p.stage_chunks = sc;
+  p.w2 = w_sdf; p.b2 = b_sdf; p.vec_out = vec_out; p.s0 = sigma0;
+  p.tiles_per_plane = mode == 1 ? (int)(rows_per_plane / kTileM) : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) return launch_nt<EPI_SDF_CENTER, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
+  if (mode == 1) return launch_nt<EPI_SDF_TAP, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
+  return launch_nt<EPI_SDF_ONLY, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
 }
 
 extern "C" int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch) {

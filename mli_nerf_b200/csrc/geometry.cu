@@ -23,16 +23,26 @@ __global__ void __launch_bounds__(256) geometry_fwd_kernel(float* __restrict__ s
                                                            const float* __restrict__ pts_light,
                                                            const float* __restrict__ dists, int64_t ld_d,
                                                            float* __restrict__ gradients, float* __restrict__ hessians,
-                                                           float* __restrict__ XH, int64_t ldxh, int xh_off) {
+                                                           float* __restrict__ XH, int64_t ldxh, int xh_off,
+                                                           int sdf_is_delta) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int64_t ray = m / g.N;
   const int i = (int)(m - ray * g.N);
   float s0 = sdf[m];
-  if (outside[ray]) { s0 = g.outside_val; sdf[m] = s0; }  // model.py:343 (in place, before the stencil)
+  // delta mode: the tap planes hold d_i = sdf_i - sdf_centre.  Gradient and Hessian only depend on sdf_i - s0 (the
+  // tap vectors sum to zero), so evaluate the reference's formulas on (d_i + shift, 0 + shift') with the centre
+  // moved to the origin; `shift` restores the literal behaviour for outside rays, whose centre alone is overwritten.
+  float shift = 0.0f;
+  if (outside[ray]) {  // model.py:343 (in place, before the stencil)
+    if (sdf_is_delta) shift = s0 - g.outside_val;
+    s0 = g.outside_val;
+    sdf[m] = s0;
+  }
+  if (sdf_is_delta) s0 = 0.0f;
   float grad[3], hess[3];
   if (g.taps == 4) {
-    const float s1 = sdf[M + m], s2 = sdf[2 * M + m], s3 = sdf[3 * M + m], s4 = sdf[4 * M + m];
+    const float s1 = sdf[M + m] + shift, s2 = sdf[2 * M + m] + shift, s3 = sdf[3 * M + m] + shift, s4 = sdf[4 * M + m] + shift;
     // (k1*s1 + k2*s2 + k3*s3 + k4*s4) / (4e), summed left to right (modules.py:167)
     grad[0] = mli_div(mli_add(mli_add(mli_add(s1, -s2), -s3), s4), g.div_grad);
     grad[1] = mli_div(mli_add(mli_add(mli_add(-s1, -s2), s3), s4), g.div_grad);
@@ -44,7 +54,7 @@ __global__ void __launch_bounds__(256) geometry_fwd_kernel(float* __restrict__ s
   } else {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float sp = sdf[(1 + 2 * a) * M + m], sn = sdf[(2 + 2 * a) * M + m];
+      const float sp = sdf[(1 + 2 * a) * M + m] + shift, sn = sdf[(2 + 2 * a) * M + m] + shift;
       grad[a] = mli_div(mli_sub(sp, sn), g.div_grad);
       hess[a] = mli_div(mli_sub(mli_add(sp, sn), mli_mul(2.0f, s0)), g.div_hess);
     }
@@ -143,7 +153,7 @@ int make_const(GeoConst* g, int32_t N, int32_t taps, double tap_eps, float outsi
 extern "C" int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, double tap_eps, const uint8_t* outside,
                                 float outside_val, const float* center, const float* ray_unit, const float* pts_light,
                                 const float* dists, int64_t ld_d, float* gradients, float* hessians, float* XH,
-                                int64_t ldxh, int32_t xh_off, void* stream) {
+                                int64_t ldxh, int32_t xh_off, int32_t sdf_is_delta, void* stream) {
   MLI_ENTRY();
   GeoConst g;
   if (int e = make_const(&g, N, taps, tap_eps, outside_val)) return e;
@@ -151,7 +161,7 @@ extern "C" int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, 
   MLI_REQUIRE(XH == nullptr || ldxh >= xh_off + 38, "geometry: XH row too short");
   if (M == 0) return MLI_OK;
   geometry_fwd_kernel<<<mli_cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(sdf, M, g, outside, center, ray_unit, pts_light,
-                                                                         dists, ld_d, gradients, hessians, XH, ldxh, xh_off);
+                                                                         dists, ld_d, gradients, hessians, XH, ldxh, xh_off, sdf_is_delta);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

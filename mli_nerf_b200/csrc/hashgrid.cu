@@ -9,6 +9,8 @@
 // stencil planes inside the thread: the 5 points of Neuralangelo's 4-tap stencil are < 0.3 fine cells
 // apart, so their corner sectors mostly coincide and are served by L1 instead of a second trip to L2/HBM.
 // Bound: HBM/L2 gather bandwidth (16 levels * 8 corners * 32 B = 4 KB per query).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) encode_rays_kernel(mli_grid_t grid, 
 template <int F>
 __global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t grid, RayArgs a,
                                                                    const float* __restrict__ dX, int64_t ldx,
-                                                                   float* __restrict__ table_grad) {
+                                                                   float* __restrict__ table_grad, int delta_basis) {
   const int level = blockIdx.y;
   const int64_t M = a.R * a.n;
   const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -194,9 +196,23 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t gr
   const int planes = 1 + a.taps;
   // Aggregate the stencil planes that fall into the centre's cell before touching memory: their 8 corner
   // rows are identical, so one vector reduction per corner carries all of them (up to 5x fewer atomics).
+  //
+  // delta_basis: the rows of dX are gradients w.r.t. the DELTA-basis inputs of the tensor-core SDF trunk
+  // (plane 0: x_centre, plane i: x_tap_i - x_centre), i.e. plane 0 carries the SUM over all planes of the
+  // per-plane gradients and plane i the tap's own.  Then  sum_p d_p w_p(c) = d_sum w_0(c) + sum_i d_i (w_i(c) - w_0(c)):
+  // the large, mutually cancelling tap gradients only ever multiply weight DIFFERENCES, so their bf16 rounding
+  // error is not amplified by the stencil's 1/eps.
   float p[3], x01[3];
   ray_point01(a, ray, i, 0, p, x01);
   const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+  float w0[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell0.w[k] : 1.0f - cell0.w[k];
+    w0[c] = w;
+  }
   float agg[8][F];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -213,12 +229,14 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t gr
 #pragma unroll
     for (int f = 0; f < F; ++f) d[f] = src[f];
     const bool same = cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2];
+    const bool sub0 = delta_basis && pl > 0;  // tap plane in the delta basis: its gradient also leaves the centre
     if (same) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float w = 1.0f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell.w[k] : 1.0f - cell.w[k];
+        if (sub0) w -= w0[c];
 #pragma unroll
         for (int f = 0; f < F; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
       }
@@ -229,6 +247,10 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t gr
         float w;
         mli_corner(lv, cell, c, &row, &w);
         scatter_entry<F>(table_grad, row, w, d);
+        if (sub0) {
+#pragma unroll
+          for (int f = 0; f < F; ++f) agg[c][f] = fmaf(-w0[c], d[f], agg[c][f]);
+        }
       }
     }
   }
@@ -238,6 +260,74 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_kernel(mli_grid_t gr
     float w;
     mli_corner(lv, cell0, c, &row, &w);
     scatter_entry<F>(table_grad, row, 1.0f, agg[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor-core variant of encode_rays: writes the SDF trunk's input directly as split-bf16 TCL in the delta basis
+//   plane 0   : x0 = [enc(x) | xyz | 0]                      rows [0, M)
+//   plane i>0 : x_i - x0 (formed in fp32, then split)          rows [i*M, (i+1)*M)
+// TCL-128 with x_chunks chunks per tile row: chunk l (l < L) = level l's 8 features, chunk L = [xyz | 0], remaining
+// chunks up to kc = 0; chunks [kc, 2 kc) hold the bf16 remainders x - bf16(x) (the "lo" half).
+// One (sample, level) thread writes 16 contiguous bytes per plane and half; a warp writes 512 contiguous bytes.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split8(__nv_bfloat16* __restrict__ X, int x_chunks, int kc, int64_t grow, int chunk,
+                                             const float* v) {
+  const int64_t tile = grow >> 7;
+  const int r = (int)(grow & 127);
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * f], v[2 * f + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * f] - hf.x, v[2 * f + 1] - hf.y);
+    hi[f] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[f] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  *reinterpret_cast<uint4*>(X + ((tile * x_chunks + chunk) * 128 + r) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(X + ((tile * x_chunks + kc + chunk) * 128 + r) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+__global__ void __launch_bounds__(kThreads) encode_rays_tcl_kernel(mli_grid_t grid, const float* __restrict__ table,
+                                                                   RayArgs a, __nv_bfloat16* __restrict__ X,
+                                                                   int x_chunks, int kc) {
+  constexpr int F = 8;
+  const int level = blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M) return;
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  const int planes = 1 + a.taps;
+  const int L = grid.n_levels;
+  const bool active = level < (int)grid.active_levels;
+  float p0[3] = {0.f, 0.f, 0.f}, acc0[F];
+  for (int pl = 0; pl < planes; ++pl) {
+    float p[3], x01[3], acc[F];
+    ray_point01(a, ray, i, pl, p, x01);
+    if (active) {
+      interp<F>(grid.level[level], table, x01[0], x01[1], x01[2], acc);
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+    }
+    const int64_t grow = (int64_t)pl * M + m;
+    if (pl == 0) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc0[f] = acc[f];
+      p0[0] = p[0]; p0[1] = p[1]; p0[2] = p[2];
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] -= acc0[f];
+      p[0] -= p0[0]; p[1] -= p0[1]; p[2] -= p0[2];
+    }
+    store_split8(X, x_chunks, kc, grow, level, acc);
+    if (level == 0) {  // xyz chunk + zero padding chunks, once per row
+      float v[8] = {p[0], p[1], p[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_split8(X, x_chunks, kc, grow, L, v);
+      v[0] = v[1] = v[2] = 0.0f;
+      for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, grow, c, v);
+    }
   }
 }
 
@@ -325,7 +415,7 @@ extern "C" int mli_encode_rays(const mli_grid_t* grid, const float* table, const
 extern "C" int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, const float* ray_unit,
                                    const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps,
                                    float tap_eps, float vol_min, float vol_max, const float* dX, int64_t ldx,
-                                   float* table_grad, void* stream) {
+                                   float* table_grad, int32_t delta_basis, void* stream) {
   MLI_ENTRY();
   if (int e = check_grid(grid)) return e;
   RayArgs a;
@@ -333,7 +423,27 @@ extern "C" int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, 
   if (R == 0) return MLI_OK;
   dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
   DISPATCH_F(grid->feat,
-             (encode_rays_bwd_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, a, dX, ldx, table_grad)));
+             (encode_rays_bwd_kernel<F><<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, a, dX, ldx, table_grad,
+                                                                                  delta_basis)));
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, const float* center,
+                                   const float* ray_unit, const float* dists, int64_t ld_d, int64_t R, int32_t n,
+                                   int32_t taps, float tap_eps, float vol_min, float vol_max, void* X, int32_t x_chunks,
+                                   int32_t k_chunks, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  RayArgs a;
+  if (int e = make_ray_args(&a, center, ray_unit, dists, ld_d, R, n, taps, tap_eps, vol_min, vol_max)) return e;
+  MLI_REQUIRE(grid->feat == 8, "encode_rays_tcl: n_features_per_level must be 8 (one level = one 8-column chunk)");
+  MLI_REQUIRE(k_chunks >= (int32_t)grid->n_levels + 1 && k_chunks % 2 == 0 && x_chunks >= 2 * k_chunks,
+              "encode_rays_tcl: need k_chunks >= levels+1 (even) and x_chunks >= 2*k_chunks");
+  MLI_REQUIRE(taps == 0 || (R * n) % 128 == 0, "encode_rays_tcl: with taps, R*n must be a multiple of 128 (plane-major tiles)");
+  if (R == 0) return MLI_OK;
+  dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
+  encode_rays_tcl_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

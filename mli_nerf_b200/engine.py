@@ -29,6 +29,7 @@ from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS100, call
 
 K0_PAD = 144      # 128 + 3 -> multiple of 16
+K0_CH = K0_PAD // 8   # chunks of one bf16 half of a trunk input row (the row holds [hi | lo] = 2*K0_CH chunks)
 KH_PAD = 304      # 256 + 38 -> multiple of 16
 XH_OFF = 256      # first non-feature column of XH
 HID = 256
@@ -182,6 +183,11 @@ class RenderEngine:
         W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
         if self.tc:  # bf16 TCL copies (tile height = the GEMM's N tile) for the tensor-core layers
             T = {}
+            # SDF layer 0 as split-bf16 (hi | lo) for the 3-product trunk GEMM; its transpose (encoding columns only)
+            # in plain bf16 for the data-gradient GEMM
+            T["W0s"] = self._tcl(HID, 2 * K0_CH, 256)
+            call("mli_tc_to_tcl_split", W["W0"], K0_PAD, HID, K0_PAD, T["W0s"], 256, 2 * K0_CH, 0, K0_CH, K0_CH)
+            T["W0t_enc"] = self._to_tcl(W["W0t"], HID, 128, HID, self._tcl(128, 32, 128), 128)
             T["W1"] = self._to_tcl(W["W1"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
             T["W1t"] = self._to_tcl(W["W1t"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
             T["Wh0"] = self._to_tcl(W["Wh0"], KH_PAD, nh * HID, KH_PAD, self._tcl(nh * HID, KH_PAD // 8, 256), 256)
@@ -224,6 +230,14 @@ class RenderEngine:
     def sdf_query(self, table, center, ray_unit, dists, ld, n):
         """SDF-only network query at n samples per ray (NeuralSDF.sdf, modules.py:73-74)."""
         R, W = center.shape[0], self.W
+        if self.tc:  # encode -> split-bf16 TCL -> tcgen05 trunk with the SDF head fused into the epilogue
+            X = self._tcl(R * n, 2 * K0_CH)
+            call("mli_encode_rays_tcl", self.grid, table, center, ray_unit, dists, ld, R, n, 0, 0.0,
+                 self.cfg.vol_range[0], self.cfg.vol_range[1], X, 2 * K0_CH, K0_CH)
+            sdf = self._f(R * n)
+            call("mli_tc_sdf_trunk_fwd", X, 2 * K0_CH, K0_PAD, W["T"]["W0s"], W["b0"], W["w_sdf"], W["b_sdf"], R * n, 2,
+                 0, None, None, sdf)
+            return sdf
         X = self._f(R * n, K0_PAD)
         call("mli_encode_rays", self.grid, table, center, ray_unit, dists, ld, R, n, 0, 0.0, self.cfg.vol_range[0],
              self.cfg.vol_range[1], X, K0_PAD)
@@ -255,21 +269,37 @@ class RenderEngine:
         return dists
 
     # ------------------------------------------------------------------------------------------------------
-    def forward(self, p, center, ray_unit, pts_light, dists, near, far, outside, training, progress):
+    def forward(self, p, center, ray_unit, pts_light, dists, near, far, outside, training, progress, keep_dz=True):
         """render_rays_object_lumen + compositing for R rays with given sample distances.  Returns (out, ctx)."""
         cfg, W, nh = self.cfg, self.W, self.nh
         R, N = center.shape[0], cfg.n_samples
         M, P = R * N, 1 + cfg.taps
         table = p["neural_sdf.tcnn_encoding.params"]
         prec = _lib.PREC_FP32  # the CUDA-core entry points; tensor-core layers go through _tc_*
-        X0 = self._f(P * M, K0_PAD)
-        call("mli_encode_rays", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
-             cfg.vol_range[0], cfg.vol_range[1], X0, K0_PAD)
-        H0 = self._f(P * M, HID)
-        call("mli_linear_fwd", X0, K0_PAD, 0, W["W0"], K0_PAD, 0, W["b0"], 0, H0, HID, 0, P * M, HID, K0_PAD,
-             ACT_SOFTPLUS100, 1, prec)
         sdf = self._f(P * M)
-        call("mli_rowdot_fwd", H0, HID, P * M, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
+        X0 = H0 = Xd = S0 = DZ = H0c = None
+        if not self.tc:
+            X0 = self._f(P * M, K0_PAD)
+            call("mli_encode_rays", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
+                 cfg.vol_range[0], cfg.vol_range[1], X0, K0_PAD)
+            H0 = self._f(P * M, HID)
+            call("mli_linear_fwd", X0, K0_PAD, 0, W["W0"], K0_PAD, 0, W["b0"], 0, H0, HID, 0, P * M, HID, K0_PAD,
+                 ACT_SOFTPLUS100, 1, prec)
+            call("mli_rowdot_fwd", H0, HID, P * M, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
+        else:
+            # SDF trunk on the tensor cores in the delta basis: plane 0 = centre rows, planes 1.. = tap - centre
+            # (formed in fp32 by the encode kernel); the tap planes' hidden activations never reach HBM
+            T = W["T"]
+            Xd = self._tcl(P * M, 2 * K0_CH)
+            call("mli_encode_rays_tcl", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
+                 cfg.vol_range[0], cfg.vol_range[1], Xd, 2 * K0_CH, K0_CH)
+            S0 = torch.empty(M // 128, 64, 128, 4, dtype=torch.float32, device=self.device)
+            H0c = self._tcl(M, 32)
+            DZ = self._tcl(cfg.taps * M, 32) if keep_dz else None
+            call("mli_tc_sdf_trunk_fwd", Xd, 2 * K0_CH, K0_PAD, T["W0s"], W["b0"], W["w_sdf"], W["b_sdf"], M, 0, M, S0,
+                 H0c, sdf)
+            call("mli_tc_sdf_trunk_fwd", Xd[M // 128:], 2 * K0_CH, K0_PAD, T["W0s"], W["b0"], W["w_sdf"], W["b_sdf"],
+                 cfg.taps * M, 1, M, S0, DZ, sdf[M:])
         gradients = self._f(M, 3)
         hessians = self._f(M, 3) if training else None
         S = self._f(M, 8)
@@ -278,7 +308,7 @@ class RenderEngine:
             call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
                  prec)
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
-                 pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF)
+                 pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF, 0)
             A = [self._f(M, nh * HID) for _ in range(4)]
             call("mli_linear_fwd", XH, KH_PAD, 0, W["Wh0"], KH_PAD, 0, W["bh"][0], 0, A[0], nh * HID, 0, M, nh * HID,
                  KH_PAD, ACT_RELU, 1, prec)
@@ -290,14 +320,12 @@ class RenderEngine:
             H0c = None
         else:
             # layer 1 + all head layers on the tensor cores; activations in bf16 TCL (never leave that layout)
-            T = W["T"]
-            H0c = self._to_tcl(H0, HID, M, HID, self._tcl(M, 32))
             XH = self._tcl(M, KH_PAD // 8)
             self._tc_linear(H0c, 0, 0, T["W1"], 0, HID, HID, 256, W["b1"], 0, None, 0, 0, ACT_SOFTPLUS100, XH, False, 0, 0,
                             0, M, 1, 0)
             XHx = self._f(M, KH_PAD - XH_OFF)
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
-                 pts_light, dists, N, gradients, hessians, XHx, KH_PAD - XH_OFF, 0)
+                 pts_light, dists, N, gradients, hessians, XHx, KH_PAD - XH_OFF, 0, 1)
             self._to_tcl(XHx, KH_PAD - XH_OFF, M, KH_PAD - XH_OFF, XH, 128, XH_OFF // 8)
             A = [self._tcl(M, nh * 32) for _ in range(4)]
             self._tc_linear(XH, 0, 0, T["Wh0"], 0, KH_PAD, nh * HID, 256, W["bh"][0], 0, None, 0, 0, ACT_RELU, A[0], False,
@@ -313,7 +341,7 @@ class RenderEngine:
         extras = self._f(R, 5) if not training else None
         call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, 8, R, None, weights, out,
              extras)
-        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
+        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, Xd=Xd, S0=S0, DZ=DZ, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
                    ccfg=ccfg, center=center, ray_unit=ray_unit, dists=dists, far=far, outside=outside)
         res = dict(out=out, weights=weights, gradients=gradients, hessians=hessians, extras=extras, S=S, sdf=sdf)
         return res, ctx
@@ -344,7 +372,8 @@ class RenderEngine:
         dWh, dbh = [None] * 3, [None] * 4
         dWout, dbout = self._f(self.J, HID), self._f(self.J)
         dWh0 = self._f(nh * HID, KH_PAD) if need_heads else None
-        dZ0 = self._f(P * M, HID) if need_sdf else None  # rows [0, M) first receive dL/dH0 of the centre plane
+        dZ0 = self._f(P * M, HID) if (need_sdf and not self.tc) else None  # rows [0, M) first receive dL/dH0 (centre)
+        dH0 = self._tcl(M, 32) if (need_sdf and self.tc) else None            # same quantity, bf16 TCL
         dXx = self._f(M, KH_PAD - XH_OFF) if need_sdf else None
         dW1, db1 = (self._f(HID, HID), None) if (need_sdf and train_mlp) else (None, None)
         if not self.tc:
@@ -415,7 +444,7 @@ class RenderEngine:
                 if train_mlp:
                     self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0)
                     db1 = self._tc_colsum(dZ1, 0, 32, M)
-                self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dZ0, True, 0, 0, HID,
+                self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dH0, False, 0, 0, 0,
                                 M, 1, 1)
         if need_heads:
             j0 = 0
@@ -441,24 +470,47 @@ class RenderEngine:
                 j0 += odim
         if not need_sdf:
             return grads
-        # ---- SDF network layer 0 + SDF head (fp32: the 4-tap stencil needs it) ---------------
         d_sdf = self._f(P * M)
         call("mli_geometry_bwd", ctx["gradients"], M, N, cfg.taps, self.tap_eps, ctx["outside"], d_grad, d_hessians, dXx,
              KH_PAD - XH_OFF, 0, d_sdf_c, d_sdf)
-        dw_sdf, db_sdf = self._f(1, HID), self._f(1)
-        ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(P * M, 1, HID), dtype=torch.uint8, device=self.device)
-        # centre plane: accumulate onto the layer-1 path; tap planes: SDF head only
-        call("mli_rowdot_bwd", d_sdf, 1, H0, HID, M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100, dZ0, HID, HID, 1, None, None,
-             ws)
-        call("mli_rowdot_bwd", d_sdf[M:], 1, H0[M:], HID, (P - 1) * M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100, dZ0[M:],
-             HID, HID, 0, None, None, ws)
-        if train_mlp:
-            call("mli_rowdot_bwd", d_sdf, 1, H0, HID, P * M, W["w_sdf"], [0], 1, HID, ACT_NONE, None, 0, 0, 0, dw_sdf,
+        dw_sdf, db_sdf = (self._f(1, HID), self._f(1)) if train_mlp else (None, None)
+        dW0, db0 = (self._f(HID, K0_PAD), None) if train_mlp else (None, None)
+        if self.tc:
+            # ---- SDF trunk backward on the tensor cores, delta basis (csrc/sdf_trunk.cu) -------------------------------
+            T = W["T"]
+            if ctx["DZ"] is None:
+                raise _lib.MliError("forward() was run with keep_dz=False: the SDF trunk cannot be differentiated")
+            Ed = self._tcl(P * M, 32)
+            ws = torch.empty(_lib.load().mli_tc_sdf_trunk_bwd_ws_bytes(M), dtype=torch.uint8, device=self.device)
+            call("mli_tc_sdf_trunk_bwd", d_sdf, M, cfg.taps, ctx["S0"], ctx["DZ"], dH0, ctx["H0c"], W["w_sdf"], Ed, dw_sdf,
                  db_sdf, ws)
-            dW0, db0 = self._f(HID, K0_PAD), self._f(HID)
-            wsb = _lib.load().mli_linear_wgrad_ws_bytes(P * M, HID, K0_PAD, 1)
-            call("mli_linear_wgrad", dZ0, HID, 0, ctx["X0"], K0_PAD, 0, dW0, K0_PAD, 0, db0, 0, P * M, HID, K0_PAD, 1, prec,
-                 torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            if train_mlp:
+                self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0)
+                db0 = self._tc_colsum(Ed, 0, 32, M)  # plane 0 = E = sum of the per-plane gradients
+            if "table" in need:
+                dX0 = self._f(P * M, 128)
+                self._tc_linear(Ed, 0, 0, T["W0t_enc"], 0, HID, 128, 128, None, 0, None, 0, 0, ACT_NONE, dX0, True, 0, 0,
+                                128, P * M, 1, 1)
+        else:
+            # ---- SDF network layer 0 + SDF head in fp32 on the CUDA cores (the rtol-1e-3 parity mode) -------------------
+            ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(P * M, 1, HID), dtype=torch.uint8, device=self.device)
+            # centre plane: accumulate onto the layer-1 path; tap planes: SDF head only
+            call("mli_rowdot_bwd", d_sdf, 1, H0, HID, M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100, dZ0, HID, HID, 1, None,
+                 None, ws)
+            call("mli_rowdot_bwd", d_sdf[M:], 1, H0[M:], HID, (P - 1) * M, W["w_sdf"], [0], 1, HID, ACT_SOFTPLUS100,
+                 dZ0[M:], HID, HID, 0, None, None, ws)
+            if train_mlp:
+                call("mli_rowdot_bwd", d_sdf, 1, H0, HID, P * M, W["w_sdf"], [0], 1, HID, ACT_NONE, None, 0, 0, 0, dw_sdf,
+                     db_sdf, ws)
+                db0 = self._f(HID)
+                wsb = _lib.load().mli_linear_wgrad_ws_bytes(P * M, HID, K0_PAD, 1)
+                call("mli_linear_wgrad", dZ0, HID, 0, ctx["X0"], K0_PAD, 0, dW0, K0_PAD, 0, db0, 0, P * M, HID, K0_PAD, 1,
+                     prec, torch.empty(wsb, dtype=torch.uint8, device=self.device))
+            if "table" in need:
+                dX0 = self._f(P * M, 128)
+                call("mli_linear_dgrad", dZ0, HID, 0, W["W0t"], HID, 0, None, 0, 0, dX0, 128, 0, P * M, HID, 128, ACT_NONE,
+                     0, 1, prec)
+        if train_mlp:
             dv, dg = self._f(HID, 131), self._f(HID, 1)
             call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.0.weight_v"],
                  p["neural_sdf.mlp.linears.0.weight_g"], dW0, K0_PAD, HID, 131, self.map_sdf0, 0, dv, dg)
@@ -471,12 +523,9 @@ class RenderEngine:
             grads["neural_sdf.mlp.linears.1.bias"] = db1
             grads["neural_sdf.mlp.linear_sdf.weight"], grads["neural_sdf.mlp.linear_sdf.bias"] = dw_sdf, db_sdf
         if "table" in need:
-            dX0 = self._f(P * M, 128)
-            call("mli_linear_dgrad", dZ0, HID, 0, W["W0t"], HID, 0, None, 0, 0, dX0, 128, 0, P * M, HID, 128, ACT_NONE, 0,
-                 1, prec)
             tg = self._z(self.n_table_params())
             call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
-                 self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg)
+                 self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg, int(self.tc))
             grads["neural_sdf.tcnn_encoding.params"] = tg
         return grads
 

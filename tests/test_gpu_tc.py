@@ -115,3 +115,217 @@ def test_tc_colsum(lib):
     lib.call("mli_tc_colsum", to_tcl_host(X).cuda(), C // 8, 32, 32, M, out, ws)
     ref = bf(X)[:, 256:512].sum(0)
     assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SDF trunk on the tensor cores: split-bf16 operands, delta basis (gemm_tcgen05.cu EPI_SDF_*, sdf_trunk.cu, hashgrid.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def split_tcl_host(x, tile_rows=128):
+    """[M, C] fp32 -> bf16 TCL with 2*C/8 chunks: [bf16(x) | bf16(x - bf16(x))]."""
+    hi = bf(x)
+    return torch.cat([to_tcl_host(hi, tile_rows), to_tcl_host(x - hi, tile_rows)], dim=1)
+
+
+def tcl32_host_to_rows(t, M):
+    """fp32 TCL32 [tiles][C/4][128][4] -> [M, C]."""
+    nt, nc, tr, _ = t.shape
+    return t.permute(0, 2, 1, 3).reshape(nt * tr, nc * 4)[:M]
+
+
+def rows_to_tcl32_host(x):
+    M, C = x.shape
+    return x.view(M // 128, 128, C // 4, 4).permute(0, 2, 1, 3).contiguous()
+
+
+def test_to_tcl_split(lib):
+    torch.manual_seed(5)
+    x = torch.randn(256, 144)
+    dst = torch.zeros(1, 36, 256, 8, dtype=torch.bfloat16, device="cuda")
+    lib.call("mli_tc_to_tcl_split", x.cuda(), 144, 256, 144, dst, 256, 36, 0, 18, 18)
+    assert torch.equal(dst.cpu(), split_tcl_host(x, 256))
+    rec = from_tcl_host(dst.cpu()[:, :18], 256) + from_tcl_host(dst.cpu()[:, 18:], 256)
+    assert float((rec - x).abs().max()) < 2e-5 * float(x.abs().max())
+
+
+def _trunk_case(M, seed=6):
+    torch.manual_seed(seed)
+    K = 144
+    W0 = torch.randn(256, K) * 0.15
+    b0 = torch.randn(256) * 0.05
+    w_sdf = torch.randn(256) * 0.1 + 0.1
+    b_sdf = torch.tensor([-0.5])
+    x0 = torch.randn(M, K) * 0.3
+    x0[:, 131:] = 0
+    return K, W0, b0, w_sdf, b_sdf, x0
+
+
+def _softplus100(z):
+    return torch.nn.functional.softplus(z, beta=100)
+
+
+def test_sdf_trunk_fwd_center_and_sdf_only(lib):
+    M = 640
+    K, W0, b0, w_sdf, b_sdf, x0 = _trunk_case(M)
+    Xs, Ws = split_tcl_host(x0).cuda(), split_tcl_host(W0, 256).cuda()
+    s0 = torch.zeros(M // 128, 64, 128, 4, device="cuda")
+    h0 = torch.zeros(M // 128, 32, 128, 8, dtype=torch.bfloat16, device="cuda")
+    sdf = torch.zeros(M, device="cuda")
+    lib.call("mli_tc_sdf_trunk_fwd", Xs, 36, K, Ws, b0.cuda(), w_sdf.cuda(), b_sdf.cuda(), M, 0, M, s0, h0, sdf)
+    z = x0.double() @ W0.double().t() + b0.double()
+    h = _softplus100(z)
+    ref_sdf = h @ w_sdf.double() + b_sdf.double()
+    # split-bf16 (3 products) carries ~16 mantissa bits per operand: |z| ~ 1 -> errors of a few 1e-5
+    assert float((sdf.cpu().double() - ref_sdf).abs().max()) < 2e-4, float((sdf.cpu().double() - ref_sdf).abs().max())
+    got_s0 = tcl32_host_to_rows(s0.cpu(), M).double()
+    assert float((got_s0 - torch.sigmoid(100 * z)).abs().max()) < 5e-3   # sigmoid(100 z): slope 25 x |dz| ~ 1e-4
+    got_h = from_tcl_host(h0.cpu(), M).double()
+    assert torch.allclose(got_h, h, rtol=1e-2, atol=1e-3)
+    sdf2 = torch.zeros(M, device="cuda")
+    lib.call("mli_tc_sdf_trunk_fwd", Xs, 36, K, Ws, b0.cuda(), w_sdf.cuda(), b_sdf.cuda(), M, 2, 0, None, None, sdf2)
+    assert torch.equal(sdf2.cpu(), sdf.cpu())
+    # ragged row count (sampling queries): rows beyond M are not written
+    Mr = 300
+    sdf3 = torch.full((384,), 7.0, device="cuda")
+    lib.call("mli_tc_sdf_trunk_fwd", Xs, 36, K, Ws, b0.cuda(), w_sdf.cuda(), b_sdf.cuda(), Mr, 2, 0, None, None, sdf3)
+    assert torch.equal(sdf3.cpu()[:Mr], sdf.cpu()[:Mr]) and bool((sdf3.cpu()[Mr:] == 7.0).all())
+
+
+def test_sdf_trunk_fwd_taps_delta(lib):
+    """d_i = sdf(x0 + dx_i) - sdf(x0) from deltas: must match an fp64 evaluation of the ABSOLUTE formula to ~1e-5
+    relative -- the property the 4-tap stencil needs and bf16 *values* cannot give."""
+    M, taps = 256, 4
+    K, W0, b0, w_sdf, b_sdf, x0 = _trunk_case(M, seed=7)
+    dx = torch.randn(taps, M, K) * 3e-4
+    dx[:, :, 131:] = 0
+    Ws = split_tcl_host(W0, 256).cuda()
+    X = torch.cat([split_tcl_host(x0)] + [split_tcl_host(dx[i]) for i in range(taps)], dim=0).cuda()
+    s0 = torch.zeros(M // 128, 64, 128, 4, device="cuda")
+    h0 = torch.zeros(M // 128, 32, 128, 8, dtype=torch.bfloat16, device="cuda")
+    dz = torch.zeros(taps * M // 128, 32, 128, 8, dtype=torch.bfloat16, device="cuda")
+    sdf = torch.zeros((1 + taps) * M, device="cuda")
+    args = (36, K, Ws, b0.cuda(), w_sdf.cuda(), b_sdf.cuda())
+    lib.call("mli_tc_sdf_trunk_fwd", X, *args, M, 0, M, s0, h0, sdf)
+    lib.call("mli_tc_sdf_trunk_fwd", X[M // 128:], *args, taps * M, 1, M, s0, dz, sdf[M:])
+    # reference on the operands the kernel actually sees (hi + lo), in float64, absolute formulation
+    def rec(t):
+        return (bf(t) + bf(t - bf(t))).double()
+    Wd = rec(W0)
+    z0 = rec(x0) @ Wd.t() + b0.double()
+    f0 = _softplus100(z0) @ w_sdf.double()
+    got = sdf.cpu().double()[M:].view(taps, M)
+    for i in range(taps):
+        zi = z0 + rec(dx[i]) @ Wd.t()
+        ref = _softplus100(zi) @ w_sdf.double() - f0
+        err = float((got[i] - ref).abs().max() / ref.abs().max())
+        assert err < 2e-4, (i, err)
+        dzi = from_tcl_host(dz.cpu()[i * M // 128:(i + 1) * M // 128], M).double()
+        assert torch.allclose(dzi, zi - z0, rtol=1e-2, atol=1e-5)
+    # second-order quantity (what the Hessian uses): sum of the 4 deltas of a symmetric stencil
+    dxs = torch.randn(M, K) * 3e-4
+    dxs[:, 131:] = 0
+    sym = torch.stack([dxs, -dxs, dxs.flip(1) * 0 + dxs * 0.5, -dxs * 0.5])
+    X2 = torch.cat([split_tcl_host(x0)] + [split_tcl_host(sym[i]) for i in range(taps)], dim=0).cuda()
+    lib.call("mli_tc_sdf_trunk_fwd", X2[M // 128:], *args, taps * M, 1, M, s0, None, sdf[M:])
+    got2 = sdf.cpu().double()[M:].view(taps, M).sum(0)
+    ref2 = sum(_softplus100(z0 + rec(sym[i]) @ Wd.t()) @ w_sdf.double() - f0 for i in range(taps))
+    assert float((got2 - ref2).abs().max()) < 2e-2 * float(ref2.abs().max()) + 1e-9, (float((got2 - ref2).abs().max()), float(ref2.abs().max()))
+
+
+def test_sdf_trunk_bwd(lib):
+    torch.manual_seed(8)
+    M, taps = 256, 4
+    z0 = torch.randn(M, 256) * 0.02
+    z0[:, :16] += 0.3      # saturated units (softplus threshold)
+    z0[:, 16:32] -= 0.3    # dead units
+    s0 = torch.sigmoid(100 * z0)
+    dzs = torch.randn(taps, M, 256) * 2e-3
+    g = torch.randn(1 + taps, M)
+    g[1:] *= 900.0
+    dH0 = torch.randn(M, 256)
+    h0 = _softplus100(z0)
+    w = torch.randn(256) * 0.1
+    Ed = torch.zeros((1 + taps) * M // 128, 32, 128, 8, dtype=torch.bfloat16, device="cuda")
+    dw, db = torch.zeros(256, device="cuda"), torch.zeros(1, device="cuda")
+    ws = torch.empty(lib.load().mli_tc_sdf_trunk_bwd_ws_bytes(M), dtype=torch.uint8, device="cuda")
+    dz_t = torch.cat([to_tcl_host(dzs[i]) for i in range(taps)], dim=0).cuda()
+    lib.call("mli_tc_sdf_trunk_bwd", g.reshape(-1).cuda(), M, taps, rows_to_tcl32_host(s0).cuda(), dz_t,
+             to_tcl_host(dH0).cuda(), to_tcl_host(h0).cuda(), w.cuda(), Ed, dw, db, ws)
+    # reference on the rounded inputs the kernel sees
+    dzr, dHr, hr = bf(dzs).double(), bf(dH0).double(), bf(h0).double()
+    s0d, gd, wd = s0.double(), g.double(), w.double()
+    e0 = (gd[0][:, None] * wd + dHr) * s0d
+    a = torch.expm1(100 * dzr)
+    si = (1 + a) * s0d / (1 + a * s0d)
+    ei = gd[1:, :, None] * wd * si
+    E = e0 + ei.sum(0)
+    got = from_tcl_host(Ed.cpu(), (1 + taps) * M).double().view(1 + taps, M, 256)
+    assert float((got[0] - E).abs().max()) < 1e-2 * float(E.abs().max()), float((got[0] - E).abs().max())
+    for i in range(taps):
+        assert float((got[1 + i] - ei[i]).abs().max()) < 1e-2 * float(ei[i].abs().max())
+    dhi = torch.log1p(a * s0d) / 100
+    ref_dw = (gd.sum(0)[:, None] * hr).sum(0) + (gd[1:, :, None] * dhi).sum((0, 1))
+    assert float((dw.cpu().double() - ref_dw).abs().max()) < 1e-4 * float(ref_dw.abs().max()) + 1e-3
+    assert abs(float(db.cpu()) - float(gd.sum())) < 1e-3 * float(gd.abs().sum()) * 1e-3 + 1e-2
+    # heads-only variant (no dw): same Ed
+    Ed2 = torch.zeros_like(Ed)
+    lib.call("mli_tc_sdf_trunk_bwd", g.reshape(-1).cuda(), M, taps, rows_to_tcl32_host(s0).cuda(), dz_t,
+             to_tcl_host(dH0).cuda(), None, w.cuda(), Ed2, None, None, None)
+    # (different instantiation -> different FMA contraction: equal to within one bf16 ulp)
+    assert torch.allclose(Ed2.cpu().float(), Ed.cpu().float(), rtol=1e-2, atol=1e-2)
+
+
+def _grid(lib, T=14):
+    return lib.make_grid(16, 8, T, 32, math.exp((math.log(2048) - math.log(32)) / 15))
+
+
+def _rays(R, seed=9):
+    g = torch.Generator().manual_seed(seed)
+    center = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    ray = torch.nn.functional.normalize(0.3 * torch.randn(R, 3, generator=g) - center, dim=-1)
+    dists = 2.0 + 2.0 * torch.rand(R, 16, generator=g).sort(dim=1).values
+    return center, ray, dists
+
+
+@pytest.mark.parametrize("taps", [0, 4, 6])
+def test_encode_rays_tcl_matches_fp32_encode(lib, taps):
+    R, n = 64, 16
+    grid = _grid(lib)
+    torch.manual_seed(10)
+    table = ((torch.rand(int(grid.n_entries) * 8) * 2 - 1) * 0.05).cuda()
+    center, ray, dists = _rays(R)
+    eps = 1.0 / 2048 / (math.sqrt(3) if taps == 4 else 1.0)
+    M, P = R * n, 1 + taps
+    X32 = torch.zeros(P * M, 144, device="cuda")
+    lib.call("mli_encode_rays", grid, table, center.cuda(), ray.cuda(), dists.cuda(), 16, R, n, taps, eps, -2.0, 2.0, X32, 144)
+    Xt = torch.zeros(P * M // 128, 36, 128, 8, dtype=torch.bfloat16, device="cuda")
+    lib.call("mli_encode_rays_tcl", grid, table, center.cuda(), ray.cuda(), dists.cuda(), 16, R, n, taps, eps, -2.0, 2.0,
+             Xt, 36, 18)
+    rec = (from_tcl_host(Xt.cpu()[:, :18], P * M) + from_tcl_host(Xt.cpu()[:, 18:], P * M)).view(P, M, 144)
+    ref = X32.cpu().view(P, M, 144)
+    assert float((rec[0] - ref[0]).abs().max()) < 2e-5 * float(ref[0].abs().max())
+    assert bool((rec[:, :, 131:] == 0).all())
+    for p in range(1, P):
+        d = ref[p] - ref[0]   # fp32 difference of fp32 rows == what the kernel forms before splitting
+        assert float((rec[p] - d).abs().max()) < 2e-5 * float(d.abs().max()) + 1e-12, p
+
+
+def test_encode_rays_bwd_delta_basis_equals_absolute_basis(lib):
+    R, n, taps = 64, 16, 4
+    grid = _grid(lib)
+    center, ray, dists = _rays(R, seed=11)
+    eps = 1.0 / 2048 / math.sqrt(3)
+    M, P = R * n, 1 + taps
+    torch.manual_seed(12)
+    dX = torch.randn(P, M, 128)
+    dX[1:] *= 100.0
+    dX[0] -= dX[1:].sum(0) * 0.999   # large, nearly cancelling per-plane gradients like the real stencil's
+    n_par = int(grid.n_entries) * 8
+    tg_abs, tg_del = torch.zeros(n_par, device="cuda"), torch.zeros(n_par, device="cuda")
+    args = (grid, center.cuda(), ray.cuda(), dists.cuda(), 16, R, n, taps, eps, -2.0, 2.0)
+    lib.call("mli_encode_rays_bwd", *args, dX.reshape(P * M, 128).cuda(), 128, tg_abs, 0)
+    dXd = dX.clone()
+    dXd[0] = dX.sum(0)
+    lib.call("mli_encode_rays_bwd", *args, dXd.reshape(P * M, 128).cuda(), 128, tg_del, 1)
+    scale = float(tg_abs.abs().max())
+    assert scale > 0
+    assert float((tg_abs - tg_del).abs().max()) < 2e-4 * scale, (float((tg_abs - tg_del).abs().max()), scale)
