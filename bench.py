@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MLI_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("MLI_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--grad", default="full", choices=["full", "heads"], help="full-grad (primary) or stage-b as shipped")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dict-size", type=int, default=22)
@@ -259,7 +259,7 @@ def main():
     value = world * RAYS * args.steps / (ms * 1e-3)
     e2e = world * RAYS * args.steps / (ms_e2e * 1e-3)
     hbm_peak, tf_peak, peak_src = peaks()
-    dense = [k for k in prof if k.startswith("mli_linear") or k.startswith("mli_rowdot")]
+    dense = [k for k in prof if k.startswith(("mli_linear", "mli_rowdot", "mli_tc_linear", "mli_tc_wgrad", "mli_tc_sdf_trunk_fwd", "mli_tc_rowdot"))]
     dense_ms = sum(prof[k][1] for k in dense)
     frac_flops = 1.0 if args.grad == "full" else 631.3 / 806.0
     achieved_tf = MLP_FLOP_PER_RAY * frac_flops * RAYS * args.steps / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0

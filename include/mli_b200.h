@@ -181,12 +181,13 @@ int mli_tc_sdf_trunk_bwd(const float* g, int64_t M, int32_t taps, const float* s
 /* Weight-gradient GEMM: out[b][r, c] = sum_m L[m, 8*(l_chunk0 + b*l_batch_chunks) + r] * R[m, 8*(r_chunk0 +
  * b*r_batch_chunks) + c]; r < rows_out (multiple of 128), c < cols_out (multiple of 16; < 256 or a multiple of 256).
  * L, R: TCL-128 (the same bytes serve as MN-major operands).  Split over row tiles, deterministic reduction.
- * transpose_out: write out[c, r] instead. */
+ * transpose_out: write out[c, r] instead.  colsum_L (may be NULL): also colsum_L[b*colsum_batch_stride + r] =
+ * sum_m L[m, ... + r] (the bias gradient when L = dZ), computed from the shared-memory stages at no extra HBM traffic. */
 int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch);
 int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
                  int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
                  int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
-                 int32_t transpose_out, void* ws, void* stream);
+                 int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream);
 /* Column sums (bias gradients) of chunks [chunk0, chunk0+n_chunks) of a TCL-128 matrix -> out[8*n_chunks]. */
 int64_t mli_tc_colsum_ws_bytes(int64_t M, int32_t n_chunks);
 int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* out, void* ws,

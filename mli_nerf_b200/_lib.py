@@ -167,7 +167,9 @@ def profile_end():
 
 def _n_launches(name, args):
     """How many of our kernels one call launches (for bench.py's gpu_launches claim)."""
-    if name in ("mli_linear_wgrad", "mli_tc_wgrad", "mli_tc_colsum"):
+    if name == "mli_tc_wgrad":
+        return 3 if args[17] is not None else 2
+    if name in ("mli_linear_wgrad", "mli_tc_colsum"):
         return 2
     if name == "mli_tc_sdf_trunk_bwd":
         return 2 if args[9] is not None else 1

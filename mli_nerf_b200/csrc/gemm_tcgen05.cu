@@ -24,6 +24,7 @@
 // CTAs, fp32 partials + fixed-order reduction (deterministic).
 // Roofline: tensor pipe (2 * M * N * K flops per call); operands stream from L2/HBM at (128+BN)*2 B per 128*BN MACs.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -141,62 +142,82 @@ struct TcNT {
   const float* w2; const float* b2; float* vec_out; float* s0; int tiles_per_plane;
 };
 
+// a < b ? x : y as a predicated select: both sides are always evaluated.  Written as `cond ? cheap : MUFU-chain` the
+// compiler emitted a divergent branch per element, which serialised the 32 independent elements of a chunk and made
+// the softplus epilogues ~10x slower than the relu ones (profiles/r01_summary.md).
+__device__ __forceinline__ float sel_lt(float a, float b, float x, float y) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "f"(x), "f"(y));
+  return r;
+}
+// softplus(beta = 100) = max(x, 0) + log1p(exp(-|100 x|)) / 100: branch-free, and beyond torch's threshold (100 x > 20)
+// the second term is < 2.1e-11, below half an ulp of x, so the result equals torch's `x` exactly
+__device__ __forceinline__ float softplus100_fast(float x) {
+  return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(100.0f * x))) * 0.01f;
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float x) {
   if constexpr (ACT == MLI_ACT_RELU) return x > 0.0f ? x : 0.0f;
-  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return mli_softplus100(x);
-  else if constexpr (ACT == MLI_ACT_SIGMOID) return mli_sigmoid(x);
+  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return softplus100_fast(x);  // |error| < 1e-8 absolute
+  else if constexpr (ACT == MLI_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
   else return x;
 }
 template <int ACT>
 __device__ __forceinline__ float act_dfo(float y) {
   if constexpr (ACT == MLI_ACT_RELU) return y > 0.0f ? 1.0f : 0.0f;
-  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return y > 0.2f ? 1.0f : 1.0f - __expf(-100.0f * y);  // y is bf16 anyway
+  else if constexpr (ACT == MLI_ACT_SOFTPLUS100) return sel_lt(0.2f, y, 1.0f, 1.0f - __expf(-100.0f * y));  // y is bf16 anyway
   else if constexpr (ACT == MLI_ACT_SIGMOID) return y * (1.0f - y);
   else return 1.0f;
 }
 
-// one 32-column chunk of the generic epilogues: v[] = accumulator row slice -> global memory
-template <int EPI, int ACT, bool OUT_F32>
-__device__ __forceinline__ void epi_generic_chunk(const TcNT& p, float* v, int ncol, int c0, int n0, int batch, int tile_m,
-                                                  int r_local, int64_t row, const float* bias, const uint4* auxr) {
+// one 32-column chunk of the generic epilogues: v[] = accumulator row slice -> global memory.
+// NCOL is the compile-time column count of the chunk (32, or 16 for the tail of a BN % 32 == 16 tile): no guards inside,
+// so the 32 elements form one basic block and their MUFU / memory latencies overlap.
+template <int EPI, int ACT, bool OUT_F32, int NCOL>
+__device__ __forceinline__ void epi_generic_chunk_n(const TcNT& p, float* v, int c0, int n0, int batch, int tile_m,
+                                                    int r_local, int64_t row, const float* bias, const uint4* auxr) {
   if constexpr (EPI == EPI_BIAS_ACT) {
+    if (bias) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < ncol) {
-        float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[g * 4 + 0] = act_fwd<ACT>(v[g * 4 + 0] + b4.x);
-        v[g * 4 + 1] = act_fwd<ACT>(v[g * 4 + 1] + b4.y);
-        v[g * 4 + 2] = act_fwd<ACT>(v[g * 4 + 2] + b4.z);
-        v[g * 4 + 3] = act_fwd<ACT>(v[g * 4 + 3] + b4.w);
+      for (int g = 0; g < NCOL / 4; ++g) {
+        // `bias` points to shared memory in the persistent kernel (its ring leaves no L1 for repeated global loads)
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + g * 4);
+        v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
       }
     }
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) v[i] = act_fwd<ACT>(v[i]);
   } else if (auxr != nullptr) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < ncol) {
-        float y[8];
-        unpack8(auxr[g], y);
+    for (int g = 0; g < NCOL / 8; ++g) {
+      float y[8];
+      unpack8(auxr[g], y);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[g * 8 + i] *= act_dfo<ACT>(y[i]);
-      }
+      for (int i = 0; i < 8; ++i) v[g * 8 + i] *= act_dfo<ACT>(y[i]);
     }
   }
   if constexpr (OUT_F32) {
     if (row < p.M) {
       float* dst = reinterpret_cast<float*>(p.out) + row * p.ldo + p.out_col0 + batch * p.out_batch_cols + n0 + c0;
 #pragma unroll
-      for (int g = 0; g < 8; ++g)
-        if (g * 4 < ncol) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      for (int g = 0; g < NCOL / 4; ++g)
+        *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
     }
   } else {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
                          ((int64_t)tile_m * p.out_chunks + p.out_chunk0 + (int64_t)batch * p.out_batch_chunks + (n0 + c0) / 8) * (kTileM * 8) +
                          r_local * 8;
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      if (g * 8 < ncol) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+    for (int g = 0; g < NCOL / 8; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
   }
+}
+
+template <int EPI, int ACT, bool OUT_F32>
+__device__ __forceinline__ void epi_generic_chunk(const TcNT& p, float* v, int ncol, int c0, int n0, int batch, int tile_m,
+                                                  int r_local, int64_t row, const float* bias, const uint4* auxr) {
+  if (ncol == 32) epi_generic_chunk_n<EPI, ACT, OUT_F32, 32>(p, v, c0, n0, batch, tile_m, r_local, row, bias, auxr);
+  else epi_generic_chunk_n<EPI, ACT, OUT_F32, 16>(p, v, c0, n0, batch, tile_m, r_local, row, bias, auxr);
 }
 
 __device__ __forceinline__ void load_aux_chunk(const TcNT& p, int batch, int tile_m, int r_local, int col, int ncol, uint4* auxr) {
@@ -311,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_nt_kernel(TcNT p) {
 // The same main loop serves the SDF trunk (EPI_SDF_*): split-bf16 operands (3 MMA passes per k-step), epilogue =
 // softplus + the 256->1 SDF head as an in-register row dot (the hidden activations of the tap planes never reach HBM).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kP_Stages = 4;
+constexpr int kP_MaxStages = 8;
 constexpr int kP_EpiWarps = 8;
 constexpr int kP_Threads = 64 + 32 * kP_EpiWarps;
 
@@ -324,18 +345,18 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __device__ __forceinline__ float fast_expm1(float t) {
   const float big = __expf(t) - 1.0f;
   const float small = t * (1.0f + t * (0.5f + t * (0.16666667f + t * 0.041666668f)));
-  return fabsf(t) < 0.03f ? small : big;
+  return sel_lt(fabsf(t), 0.03f, small, big);
 }
 __device__ __forceinline__ float fast_log1p(float q) {
   const float big = __logf(1.0f + q);
   const float small = q * (1.0f + q * (-0.5f + q * (0.33333334f - q * 0.25f)));
-  return fabsf(q) < 0.03f ? small : big;
+  return sel_lt(fabsf(q), 0.03f, small, big);
 }
 
 template <int EPI, int ACT, bool OUT_F32>
-__global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT p, int n_row_tiles, int n_tiles_n) {
+__global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT p, int n_row_tiles, int n_tiles_n, int n_stages) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * kP_Stages + 4];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * kP_MaxStages + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_b0[256];
   __shared__ __align__(16) float s_w2[256];
@@ -350,20 +371,23 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
   const uint32_t a_stage_bytes = kStageChunks * kTileM * 16;
   const uint32_t sB = smem_u32(smem), sA = sB + b_bytes;
   const uint32_t b_full = smem_u32(&bars[0]);
-  const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kP_Stages]);
-  const uint32_t t_full0 = smem_u32(&bars[1 + 2 * kP_Stages]), t_empty0 = smem_u32(&bars[1 + 2 * kP_Stages + 2]);
+  const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kP_MaxStages]);
+  const uint32_t t_full0 = smem_u32(&bars[1 + 2 * kP_MaxStages]), t_empty0 = smem_u32(&bars[1 + 2 * kP_MaxStages + 2]);
+  const uint32_t kP_Stages = (uint32_t)n_stages;
   const int n_kt = (kc_total + stage_chunks - 1) / stage_chunks;
   const uint32_t acc_stride = (BN + 31) / 32 * 32;
   const uint32_t tmem_cols = 2 * acc_stride <= 32 ? 32 : 2 * acc_stride <= 64 ? 64 : 2 * acc_stride <= 128 ? 128 : 2 * acc_stride <= 256 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
-    for (int s = 0; s < kP_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
+    for (uint32_t s = 0; s < kP_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(t_full0 + 8 * a, 1); mbar_init(t_empty0 + 8 * a, kP_EpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (kSdf) {
     for (int i = threadIdx.x; i < 256; i += kP_Threads) { s_b0[i] = p.bias[i]; s_w2[i] = p.w2[i]; }
+  } else if (EPI == EPI_BIAS_ACT && p.bias) {
+    for (int i = threadIdx.x; i < BN; i += kP_Threads) s_b0[i] = p.bias[batch * p.bias_batch + tile_n * BN + i];
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
@@ -444,7 +468,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
     const int r_local = q * 32 + lane;
     const int n0 = tile_n * BN;
     const int n_cc = (BN + 31) / 32;
-    const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? p.bias + batch * p.bias_batch + n0 : nullptr;
+    const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? s_b0 : nullptr;
     const bool has_aux = (EPI == EPI_MUL_DACT) && p.aux != nullptr;
     uint32_t it = 0;
     for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x, ++it) {
@@ -518,9 +542,11 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
             for (int i = 0; i < 32; ++i) {
               const float z = v[i] + s_b0[c0 + i];
               const float bz = 100.0f * z;
-              float h, s;
-              if (bz > 20.0f) { h = z; s = 1.0f / (1.0f + __expf(-bz)); }
-              else { const float e = expf(bz); h = log1pf(e) * 0.01f; s = e / (1.0f + e); }
+              // one MUFU exp shared by softplus and its derivative (branch-free); absolute error of h < 1e-8
+              const float e = __expf(-fabsf(bz));
+              const float h = fmaxf(z, 0.0f) + __logf(1.0f + e) * 0.01f;
+              const float rcp = __fdividef(1.0f, 1.0f + e);
+              const float s = sel_lt(bz, 0.0f, e * rcp, rcp);
               dot = fmaf(s_w2[c0 + i], h, dot);
               v[i] = h;
               sg[i] = s;
@@ -570,10 +596,15 @@ struct TcTN {
   const __nv_bfloat16* R; int r_chunks, r_chunk0, r_batch_chunks;  // "X" side  -> output cols (BN per CTA)
   int BN, n_row_tiles, tiles_per_split, S;
   float* part; int rows_out, cols_out;                             // [batch*S][rows_out][cols_out] fp32
+  float* cs_part;                                                  // [batch*S][rows_out] column sums of L (bias grads)
 };
 
 constexpr int kTN_Stages = 2;
 
+// COLSUM: the four epilogue warps, idle during the main loop, also sum the columns of the L operand (= bias gradient of
+// the layer whose weight gradient this GEMM produces) straight from the shared-memory stages, so dZ is read from HBM
+// once for both.  Row-private partial sums in registers, one cross-row reduction through shared memory at the end.
+template <bool COLSUM>
 __global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(TcTN p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 * kTN_Stages + 1];
@@ -591,9 +622,10 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(TcTN p) {
   const int t_end = min(p.n_row_tiles, t_begin + p.tiles_per_split);
   const int n_t = max(0, t_end - t_begin);
   const uint32_t tmem_cols = tmem_cols_pow2(BN);
+  const bool do_cs = COLSUM && tile_c == 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTN_Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < kTN_Stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, do_cs ? 5 : 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -637,9 +669,42 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(TcTN p) {
   } else {
     const int q = warp & 3;
     const int r_out = tile_r * kTileM + q * 32 + lane;
+    float cs[COLSUM ? 128 : 1];
+    const int t = threadIdx.x - 64;  // 0..127: k-row of the stage this thread sums
+    if constexpr (COLSUM) {
+      if (do_cs) {
+#pragma unroll
+        for (int k = 0; k < 128; ++k) cs[k] = 0.0f;
+        for (int i = 0; i < n_t; ++i) {
+          const int s = i % kTN_Stages;
+          mbar_wait(full0 + 8 * s, (i / kTN_Stages) & 1);
+          const uint4* sl = reinterpret_cast<const uint4*>(smem + (size_t)s * stage_bytes) + t;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {  // chunk j of row t: 16 B, conflict-free (consecutive lanes, consecutive 16 B)
+            float x[8];
+            unpack8(sl[j * kTileM], x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cs[j * 8 + k] += x[k];
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+      }
+    }
     if (n_t > 0) {
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+    }
+    if constexpr (COLSUM) {
+      if (do_cs) {  // all loads and MMAs have completed: the stage buffers are free -> [128 rows][129] fp32 transpose
+        float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+        for (int k = 0; k < 128; ++k) red[t * 129 + k] = n_t > 0 ? cs[k] : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float v = 0.0f;
+        for (int r = 0; r < 128; ++r) v += red[r * 129 + t];
+        p.cs_part[(size_t)blockIdx.z * p.rows_out + tile_r * kTileM + t] = v;
+      }
     }
     float* dst_base = p.part + ((size_t)blockIdx.z * p.rows_out + r_out) * p.cols_out + tile_c * BN;
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -756,23 +821,35 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int S, int 
   out[e] = v;
 }
 
+// splits of the contraction dimension: the TN kernel's shared-memory stages allow one CTA per SM, so aim for exactly
+// one wave (300 CTAs on 148 SMs ran as 2.03 waves before)
 int tn_splits(int n_row_tiles, int out_tiles) {
-  int s = (2 * MLI_NUM_SMS + out_tiles - 1) / out_tiles;
+  int s = MLI_NUM_SMS / out_tiles;
   if (s > n_row_tiles) s = n_row_tiles;
-  if (s > 64) s = 64;
+  if (s > 74) s = 74;
   return s < 1 ? 1 : s;
+}
+
+__global__ void tn_colsum_reduce_kernel(const float* __restrict__ part, int S, int rows, float* __restrict__ out,
+                                        int64_t batch_stride) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows) return;
+  float v = 0.0f;
+  for (int s = 0; s < S; ++s) v += part[((size_t)(b * S + s)) * rows + e];  // fixed order: deterministic
+  out[b * batch_stride + e] = v;
 }
 
 // raise the dynamic-smem limit of a kernel only when it has to grow (keeps the call out of CUDA-graph captures
 // after the first eager step); keyed by the kernel's address (all NT instantiations share one function type)
 int set_smem(const void* kernel, size_t bytes) {
-  static const void* keys[16];
-  static size_t vals[16];
+  static const void* keys[64];
+  static size_t vals[64];
   static int n = 0;
   int i = 0;
   for (; i < n; ++i) if (keys[i] == kernel) break;
   if (i == n) {
-    if (n == 16) { mli_set_error("set_smem: table full"); return MLI_EINVAL; }
+    if (n == 64) { mli_set_error("set_smem: table full"); return MLI_EINVAL; }
     keys[n] = kernel; vals[n] = 0; ++n;
   }
   if (bytes > vals[i]) {
@@ -833,8 +910,21 @@ template <int EPI, int ACT, bool OUT_F32>
 int launch_nt(const TcNT& p, int N, int batch, cudaStream_t st) {
   const int BN = p.BN;
   const int kc_total = p.split ? 2 * p.k_chunks : p.k_chunks;
-  const size_t smem_p = (size_t)kc_total * BN * 16 + (size_t)kP_Stages * kStageChunks * kTileM * 16;
-  if (smem_p <= 220 * 1024) {  // persistent weight-stationary kernel
+  // activation ring: as many 16 KB stages as fit next to the resident weight tile (bytes in flight per SM are what
+  // bounds the achieved HBM bandwidth of these kernels), at least 3
+  constexpr size_t kStatic = EPI >= EPI_SDF_CENTER ? 3584 : (EPI == EPI_BIAS_ACT ? 1536 : 512);
+  const size_t b_bytes = (size_t)kc_total * BN * 16, a_stage = (size_t)kStageChunks * kTileM * 16;
+  int n_stages = b_bytes + kStatic < 232448 ? (int)((232448 - kStatic - b_bytes) / a_stage) : 0;
+  // measured (tools/bench_kernels.py, head layers): the forward epilogue runs best with 4 stages (6.2 vs 5.4 TB/s with
+  // 6 -- it needs the L1 the carve-out leaves for its stores), the data-gradient one with 6 (6.3 vs 6.0 TB/s)
+  const int cap = EPI == EPI_MUL_DACT ? 6 : 4;
+  if (n_stages > cap) n_stages = cap;
+  if (const char* ev = getenv("MLI_NT_STAGES")) {  // tuning knob for the micro-benchmarks (tools/bench_kernels.py)
+    const int v = atoi(ev);
+    if (v >= 3 && v < n_stages) n_stages = v;
+  }
+  const size_t smem_p = b_bytes + (size_t)n_stages * a_stage;
+  if (n_stages >= 3) {  // persistent weight-stationary kernel
     const int n_tiles_n = N / BN, groups = n_tiles_n * batch;
     const int n_row_tiles = (int)mli_cdiv(p.M, kTileM);
     int per_group = MLI_NUM_SMS / groups;
@@ -842,7 +932,7 @@ int launch_nt(const TcNT& p, int N, int batch, cudaStream_t st) {
     if (per_group > n_row_tiles) per_group = n_row_tiles;
     dim3 pgrid(per_group, groups);
     if (int e = set_smem((const void*)tc_gemm_nt_persist_kernel<EPI, ACT, OUT_F32>, smem_p)) return e;
-    tc_gemm_nt_persist_kernel<EPI, ACT, OUT_F32><<<pgrid, kP_Threads, smem_p, st>>>(p, n_row_tiles, n_tiles_n);
+    tc_gemm_nt_persist_kernel<EPI, ACT, OUT_F32><<<pgrid, kP_Threads, smem_p, st>>>(p, n_row_tiles, n_tiles_n, n_stages);
     MLI_LAUNCH_OK();
     return MLI_OK;
   }
@@ -942,14 +1032,14 @@ extern "C" int mli_tc_sdf_trunk_fwd(const void* X, int32_t x_chunks, int32_t K, 
 extern "C" int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch) {
   const int n_row_tiles = (int)((M + kTileM - 1) / kTileM);
   const int out_tiles = ((rows_out + 127) / 128) * ((cols_out + 255) / 256) * batch;
-  return (int64_t)batch * tn_splits(n_row_tiles, out_tiles) * rows_out * cols_out * sizeof(float);
+  return (int64_t)batch * tn_splits(n_row_tiles, out_tiles) * rows_out * (cols_out + 1) * sizeof(float);
 }
 
 // out[b][r, c] (or transposed) = sum_m L[m, l0 + r] * R[m, r0 + c],  r < rows_out (multiple of 128), c < cols_out
 extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
                             int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
                             int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
-                            int32_t transpose_out, void* ws, void* stream) {
+                            int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream) {
   MLI_ENTRY();
   MLI_REQUIRE(M >= 1 && batch >= 1 && rows_out >= 128 && rows_out % 128 == 0, "tc_wgrad: rows_out must be a multiple of 128");
   MLI_REQUIRE(cols_out >= 16 && cols_out % 16 == 0, "tc_wgrad: cols_out must be a multiple of 16");
@@ -965,10 +1055,19 @@ extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, i
   p.R = (const __nv_bfloat16*)R; p.r_chunks = r_chunks; p.r_chunk0 = r_chunk0; p.r_batch_chunks = r_batch_chunks;
   p.BN = BN; p.n_row_tiles = n_row_tiles; p.tiles_per_split = (n_row_tiles + S - 1) / S; p.S = S;
   p.part = (float*)ws; p.rows_out = rows_out; p.cols_out = cols_out;
+  p.cs_part = p.part + (size_t)batch * S * rows_out * cols_out;
   const size_t smem = (size_t)kTN_Stages * (16 * kTileM * 16 + (BN / 8) * kTileM * 16);
-  if (int e = set_smem((const void*)tc_gemm_tn_kernel, smem)) return e;
   dim3 grid(cols_out / BN, rows_out / 128, S * batch);
-  tc_gemm_tn_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  if (colsum_L) {
+    if (int e = set_smem((const void*)tc_gemm_tn_kernel<true>, smem)) return e;
+    tc_gemm_tn_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    MLI_LAUNCH_OK();
+    tn_colsum_reduce_kernel<<<dim3(mli_cdiv(rows_out, 256), batch), 256, 0, (cudaStream_t)stream>>>(p.cs_part, S, rows_out, colsum_L,
+                                                                                                 colsum_batch_stride);
+  } else {
+    if (int e = set_smem((const void*)tc_gemm_tn_kernel<false>, smem)) return e;
+    tc_gemm_tn_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  }
   MLI_LAUNCH_OK();
   dim3 g2(mli_cdiv((int64_t)rows_out * cols_out, 256), batch);
   tn_reduce_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(p.part, S, rows_out, cols_out, out, ldo, out_batch_stride, transpose_out);

@@ -39,15 +39,21 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
   return o;
 }
+// a < b ? x : y as a predicated select (both sides evaluated: keeps the 8 elements of a chunk in one basic block)
+__device__ __forceinline__ float sel_lt(float a, float b, float x, float y) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "f"(x), "f"(y));
+  return r;
+}
 __device__ __forceinline__ float fast_expm1(float t) {
   const float big = __expf(t) - 1.0f;
   const float small = t * (1.0f + t * (0.5f + t * (0.16666667f + t * 0.041666668f)));
-  return fabsf(t) < 0.03f ? small : big;
+  return sel_lt(fabsf(t), 0.03f, small, big);
 }
 __device__ __forceinline__ float fast_log1p(float q) {
   const float big = __logf(1.0f + q);
   const float small = q * (1.0f + q * (-0.5f + q * (0.33333334f - q * 0.25f)));
-  return fabsf(q) < 0.03f ? small : big;
+  return sel_lt(fabsf(q), 0.03f, small, big);
 }
 
 template <bool WITH_DW>

@@ -72,37 +72,50 @@ __global__ void __launch_bounds__(kTile) rowdot_tcl_fwd_kernel(const __nv_bfloat
 }
 
 // dZ[m, c] = (sum_{j covering c} dS[m,j] w[j, c - off_j]) * act'(A[m,c])   (bf16 TCL out, same chunk geometry as A)
-__global__ void __launch_bounds__(256) rowdot_tcl_bwd_kernel(const float* __restrict__ dS, int64_t lds,
-                                                             const __nv_bfloat16* __restrict__ A, int a_chunks, int64_t M,
-                                                             const float* __restrict__ w, RdArgs a, int act_prev,
-                                                             __nv_bfloat16* __restrict__ dZ, int n_chunks) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t m_padded = (M + kTile - 1) / kTile * kTile;
-  if (e >= m_padded * n_chunks) return;
-  const int64_t tile = e / ((int64_t)kTile * n_chunks);
-  const int rem = (int)(e % ((int64_t)kTile * n_chunks));
-  const int c = rem / kTile, r = rem % kTile;
-  const int64_t m = tile * kTile + r;
-  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const int64_t idx = ((tile * a_chunks + c) * kTile + r) * 8;
-  if (m < M) {
-    for (int j = 0; j < a.J; ++j) {
-      const int k = c * 8 - a.col_off[j];
-      if (k < 0 || k >= a.K) continue;
-      const float d = dS[m * lds + j];
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + j * a.K + k));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + j * a.K + k + 4));
-      v[0] = fmaf(d, w0.x, v[0]); v[1] = fmaf(d, w0.y, v[1]); v[2] = fmaf(d, w0.z, v[2]); v[3] = fmaf(d, w0.w, v[3]);
-      v[4] = fmaf(d, w1.x, v[4]); v[5] = fmaf(d, w1.y, v[5]); v[6] = fmaf(d, w1.z, v[6]); v[7] = fmaf(d, w1.w, v[7]);
+// One thread = one row of a 128-row tile; it keeps the row's J upstream gradients in registers and walks 32 chunks,
+// so every A load / dZ store is 16 B per thread, 2 KB contiguous per CTA, with 32 independent loads in flight.
+constexpr int kBwdChunksPerCta = 32;
+
+__global__ void __launch_bounds__(kTile) rowdot_tcl_bwd_kernel(const float* __restrict__ dS, int64_t lds,
+                                                               const __nv_bfloat16* __restrict__ A, int a_chunks, int64_t M,
+                                                               const float* __restrict__ w, RdArgs a, int act_prev,
+                                                               __nv_bfloat16* __restrict__ dZ) {
+  extern __shared__ float sw[];  // [J][K]
+  for (int i = threadIdx.x; i < a.J * a.K; i += kTile) sw[i] = w[i];
+  __syncthreads();
+  const int64_t tile = blockIdx.x;
+  const int64_t m = tile * kTile + threadIdx.x;
+  const int c_begin = blockIdx.y * kBwdChunksPerCta;
+  const int c_end = min(a_chunks, c_begin + kBwdChunksPerCta);
+  float d[kMaxJ];
+#pragma unroll
+  for (int j = 0; j < kMaxJ; ++j) d[j] = (j < a.J && m < M) ? dS[m * lds + j] : 0.0f;
+#pragma unroll 4
+  for (int c = c_begin; c < c_end; ++c) {
+    const int64_t idx = ((tile * a_chunks + c) * kTile + threadIdx.x) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) {
+      const int k = c * 8 - a.col_off[j];  // warp-uniform
+      if (j < a.J && k >= 0 && k < a.K) {
+        const float* ww = sw + j * a.K + k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(d[j], ww[i], v[i]);
+      }
     }
     if (act_prev != MLI_ACT_NONE) {
       float y[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(A + idx)), y);
+      if (act_prev == MLI_ACT_RELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= mli_dact_from_out(y[i], act_prev);
+        for (int i = 0; i < 8; ++i) v[i] = y[i] > 0.0f ? v[i] : 0.0f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= mli_dact_from_out(y[i], act_prev);
+      }
     }
+    *reinterpret_cast<uint4*>(dZ + idx) = pack8(v);  // padding rows are written as zeros (d = 0)
   }
-  *reinterpret_cast<uint4*>(dZ + idx) = pack8(v);  // padding rows are written as zeros
 }
 
 int make_args(RdArgs* a, const int32_t* col_off, int32_t J, int32_t K) {
@@ -141,9 +154,9 @@ extern "C" int mli_tc_rowdot_bwd_data(const float* dS, int64_t lds, const void* 
   if (int e = make_args(&a, host_col_off, J, K)) return e;
   MLI_REQUIRE(lds >= J, "rowdot_tcl: lds < J");
   if (M <= 0) return MLI_OK;
-  const int64_t m_padded = (M + kTile - 1) / kTile * kTile;
-  rowdot_tcl_bwd_kernel<<<mli_cdiv(m_padded * a_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
-      dS, lds, (const __nv_bfloat16*)A, a_chunks, M, w, a, act_prev, (__nv_bfloat16*)dZ, a_chunks);
+  dim3 grid(mli_cdiv(M, kTile), mli_cdiv(a_chunks, kBwdChunksPerCta));
+  rowdot_tcl_bwd_kernel<<<grid, kTile, (size_t)J * K * sizeof(float), (cudaStream_t)stream>>>(
+      dS, lds, (const __nv_bfloat16*)A, a_chunks, M, w, a, act_prev, (__nv_bfloat16*)dZ);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

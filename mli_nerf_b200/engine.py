@@ -207,10 +207,12 @@ class RenderEngine:
              aux.shape[1] if aux is not None else 0, aux_chunk0, aux_bchunks, act, out, int(out_f32),
              0 if out_f32 else out.shape[1], out_chunk0, out_bchunks, ldo, 0, 0, M, batch, epi)
 
-    def _tc_wgrad(self, L, l_chunk0, l_b, R, r_chunk0, r_b, M, rows, cols, batch, out, ldo, bstride, transpose=0):
+    def _tc_wgrad(self, L, l_chunk0, l_b, R, r_chunk0, r_b, M, rows, cols, batch, out, ldo, bstride, transpose=0,
+                  db=None):
+        """out[b] = L[b]^T R[b]; db (optional, [batch*rows]) = column sums of L from the same pass (bias gradient)."""
         ws = torch.empty(_lib.load().mli_tc_wgrad_ws_bytes(M, rows, cols, batch), dtype=torch.uint8, device=self.device)
         call("mli_tc_wgrad", L, L.shape[1], l_chunk0, l_b, R, R.shape[1], r_chunk0, r_b, M, rows, cols, batch, out, ldo,
-             bstride, transpose, ws)
+             bstride, transpose, db, rows, ws)
 
     def _tc_colsum(self, X, chunk0, n_chunks, M):
         out = self._f(n_chunks * 8)
@@ -424,17 +426,16 @@ class RenderEngine:
                 dbout = self._tc_colsum(dSt, 0, 1, M)[:self.J]
             for l in (2, 1, 0):
                 if need_heads:
-                    dWh[l] = self._f(nh, HID, HID)
-                    self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID, HID * HID)
-                    dbh[l + 1] = self._tc_colsum(dZ, 0, nh * 32, M)
+                    dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
+                    self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID, HID * HID, db=dbh[l + 1])
                 dZp = self._tcl(M, nh * 32)
                 self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0, A[l], 0, 32, ACT_RELU, dZp,
                                 False, 0, 32, 0, M, nh, 1)
                 dZ = dZp
             if need_heads:
-                self._tc_wgrad(dZ, 0, 0, XH, 0, 0, M, nh * HID, 256, 1, dWh0, KH_PAD, 0)
+                dbh[0] = self._f(nh * HID)
+                self._tc_wgrad(dZ, 0, 0, XH, 0, 0, M, nh * HID, 256, 1, dWh0, KH_PAD, 0, db=dbh[0])
                 self._tc_wgrad(dZ, 0, 0, XH, XH_OFF // 8, 0, M, nh * HID, KH_PAD - XH_OFF, 1, dWh0[:, XH_OFF:], KH_PAD, 0)
-                dbh[0] = self._tc_colsum(dZ, 0, nh * 32, M)
             if need_sdf:
                 dZ1 = self._tcl(M, 32)
                 self._tc_linear(dZ, 0, 0, T["Wh0t_feat"], 0, nh * HID, HID, 256, None, 0, XH, 0, 0, ACT_SOFTPLUS100, dZ1,
@@ -442,8 +443,8 @@ class RenderEngine:
                 self._tc_linear(dZ, 0, 0, T["Wh0t_x"], 0, nh * HID, KH_PAD - XH_OFF, KH_PAD - XH_OFF, None, 0, None, 0, 0,
                                 ACT_NONE, dXx, True, 0, 0, KH_PAD - XH_OFF, M, 1, 1)
                 if train_mlp:
-                    self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0)
-                    db1 = self._tc_colsum(dZ1, 0, 32, M)
+                    db1 = self._f(HID)
+                    self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0, db=db1)
                 self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dH0, False, 0, 0, 0,
                                 M, 1, 1)
         if need_heads:

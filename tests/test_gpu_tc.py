@@ -96,14 +96,18 @@ def test_tc_wgrad(lib, M, rows, cols, batch):
     out = torch.zeros(batch, rows, cols, device="cuda")
     ws = torch.empty(lib.load().mli_tc_wgrad_ws_bytes(M, rows, cols, batch), dtype=torch.uint8, device="cuda")
     lib.call("mli_tc_wgrad", to_tcl_host(dZ).cuda(), batch * rows // 8, 0, rows // 8, to_tcl_host(X).cuda(), batch * cols // 8,
-             0, cols // 8, M, rows, cols, batch, out, cols, rows * cols, 0, ws)
+             0, cols // 8, M, rows, cols, batch, out, cols, rows * cols, 0, None, 0, ws)
     ref = torch.einsum("mbr,mbc->brc", bf(dZ).view(M, batch, rows), bf(X).view(M, batch, cols))
     err = float((out.cpu() - ref).abs().max() / ref.abs().max())
     assert err < 1e-4, err
     outT = torch.zeros(batch, cols, rows, device="cuda")
+    db = torch.zeros(batch * rows, device="cuda")
     lib.call("mli_tc_wgrad", to_tcl_host(dZ).cuda(), batch * rows // 8, 0, rows // 8, to_tcl_host(X).cuda(), batch * cols // 8,
-             0, cols // 8, M, rows, cols, batch, outT, rows, rows * cols, 1, ws)
+             0, cols // 8, M, rows, cols, batch, outT, rows, rows * cols, 1, db, rows, ws)
     assert torch.equal(outT.cpu().transpose(1, 2), out.cpu())
+    # fused column sums of L (bias gradient) from the same pass
+    ref_db = bf(dZ).view(M, batch, rows).sum(0)
+    assert float((db.cpu().view(batch, rows) - ref_db).abs().max()) < 1e-4 * float(ref_db.abs().max()) + 1e-3
 
 
 def test_tc_colsum(lib):
