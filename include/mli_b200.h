@@ -136,6 +136,14 @@ int mli_linear_wgrad(const float* dZ, int64_t lddz, int64_t sdz, const float* X,
  * tile row and `tile_rows`-row tiles; rows >= M / columns >= cols are zero-filled. */
 int mli_tc_to_tcl(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
                   int32_t dst_chunks, int32_t chunk0, int32_t n_chunks, void* stream);
+/* backward of mli_encode_rays_tcl w.r.t. the table: dX = bf16 TCL-128 gradient of the delta-basis rows (x_chunks chunks
+ * per tile row, chunk l = level l; plane 0 = sum over the stencil planes, plane i = tap i), as the data-gradient GEMM
+ * of the SDF trunk writes it.  Only levels [level_begin, level_end) are processed, so a caller can launch level groups
+ * separately and start the gradient all-reduce of a finished level's slab while the next ones are still running. */
+int mli_encode_rays_bwd_tcl(const mli_grid_t* grid, const float* center, const float* ray_unit, const float* dists,
+                            int64_t ld_d, int64_t R, int32_t n, int32_t taps, float tap_eps, float vol_min,
+                            float vol_max, const void* dX, int32_t x_chunks, float* table_grad, int32_t level_begin,
+                            int32_t level_end, void* stream);
 /* split-bf16 variant: chunks [chunk0, +n_chunks) = bf16(x), chunks [lo_chunk0, +n_chunks) = bf16(x - bf16(x)). */
 int mli_tc_to_tcl_split(const float* src, int64_t ld, int64_t M, int32_t cols, void* dst, int32_t tile_rows,
                         int32_t dst_chunks, int32_t chunk0, int32_t lo_chunk0, int32_t n_chunks, void* stream);

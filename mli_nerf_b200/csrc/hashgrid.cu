@@ -20,9 +20,10 @@ constexpr int kThreads = 256;
 template <int F>
 __device__ __forceinline__ void load_entry(const float* __restrict__ table, uint32_t row, float* v) {
   if constexpr (F == 8) {
-    const float4* p = reinterpret_cast<const float4*>(table + (size_t)row * 8);
-    float4 a = __ldg(p), b = __ldg(p + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    // one 256-bit load per corner (LDG.E.256, sm_100+): the whole 32-byte sector in a single L1 request instead of two
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "l"(table + (size_t)row * 8));
   } else if constexpr (F == 4) {
     float4 a = __ldg(reinterpret_cast<const float4*>(table + (size_t)row * 4));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -301,33 +302,155 @@ __global__ void __launch_bounds__(kThreads) encode_rays_tcl_kernel(mli_grid_t gr
   const int planes = 1 + a.taps;
   const int L = grid.n_levels;
   const bool active = level < (int)grid.active_levels;
-  float p0[3] = {0.f, 0.f, 0.f}, acc0[F];
-  for (int pl = 0; pl < planes; ++pl) {
-    float p[3], x01[3], acc[F];
-    ray_point01(a, ray, i, pl, p, x01);
-    if (active) {
-      interp<F>(grid.level[level], table, x01[0], x01[1], x01[2], acc);
-    } else {
+  const mli_level_t& lv = grid.level[level];
+  // centre: fetch the 8 corner sectors once and KEEP them -- a tap point is < 0.15 finest cells away, so it nearly
+  // always lies in the same cell and its interpolation only needs new weights (same fma order as a fresh fetch, so
+  // the result is bit-identical); only taps that cross a cell face gather again.  This cuts the L1 requests of the
+  // 5-plane stencil by ~3.5x (the kernel was bound by L1 wavefronts, profiles/r01_summary.md).
+  float p0[3], x01[3], acc0[F], vals0[8][F];
+  ray_point01(a, ray, i, 0, p0, x01);
+  mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
 #pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+  for (int f = 0; f < F; ++f) acc0[f] = 0.0f;
+  if (active) {
+    uint32_t rows[8];
+    float wts[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mli_corner(lv, cell0, c, &rows[c], &wts[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) load_entry<F>(table, rows[c], vals0[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc0[f] = fmaf(wts[c], vals0[c][f], acc0[f]);
+  }
+  store_split8(X, x_chunks, kc, m, level, acc0);
+  if (level == 0) {  // xyz chunk + zero padding chunks, once per row
+    float v[8] = {p0[0], p0[1], p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    store_split8(X, x_chunks, kc, m, L, v);
+    v[0] = v[1] = v[2] = 0.0f;
+    for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, m, c, v);
+  }
+  for (int pl = 1; pl < planes; ++pl) {
+    float p[3], acc[F];
+    ray_point01(a, ray, i, pl, p, x01);
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+    if (active) {
+      const mli_cell_t cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+      if (cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2]) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float w = 1.0f;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) w *= ((c >> d) & 1) ? cell.w[d] : 1.0f - cell.w[d];
+#pragma unroll
+          for (int f = 0; f < F; ++f) acc[f] = fmaf(w, vals0[c][f], acc[f]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t row;
+          float w, v[F];
+          mli_corner(lv, cell, c, &row, &w);
+          load_entry<F>(table, row, v);
+#pragma unroll
+          for (int f = 0; f < F; ++f) acc[f] = fmaf(w, v[f], acc[f]);
+        }
+      }
     }
     const int64_t grow = (int64_t)pl * M + m;
-    if (pl == 0) {
 #pragma unroll
-      for (int f = 0; f < F; ++f) acc0[f] = acc[f];
-      p0[0] = p[0]; p0[1] = p[1]; p0[2] = p[2];
-    } else {
-#pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] -= acc0[f];
-      p[0] -= p0[0]; p[1] -= p0[1]; p[2] -= p0[2];
-    }
+    for (int f = 0; f < F; ++f) acc[f] -= acc0[f];
     store_split8(X, x_chunks, kc, grow, level, acc);
-    if (level == 0) {  // xyz chunk + zero padding chunks, once per row
-      float v[8] = {p[0], p[1], p[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (level == 0) {
+      float v[8] = {p[0] - p0[0], p[1] - p0[1], p[2] - p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
       store_split8(X, x_chunks, kc, grow, L, v);
       v[0] = v[1] = v[2] = 0.0f;
       for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, grow, c, v);
     }
+  }
+}
+
+// backward of encode_rays_tcl w.r.t. the table: dX is bf16 TCL-128 ([.., x_chunks, 128, 8], chunk l = level l) in the
+// delta basis (see encode_rays_bwd_kernel).  All planes' 16-byte gradient slices are loaded up front (independent,
+// fully coalesced: consecutive samples -> consecutive 16 B), then the same aggregation as the fp32 kernel.
+template <int PLANES>
+__global__ void __launch_bounds__(kThreads) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
+                                                                       const __nv_bfloat16* __restrict__ dX, int x_chunks,
+                                                                       float* __restrict__ table_grad, int level0) {
+  constexpr int F = 8;
+  const int level = level0 + blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= M || level >= (int)grid.active_levels) return;
+  const mli_level_t& lv = grid.level[level];
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  uint4 draw[PLANES];
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    const int64_t grow = (int64_t)pl * M + m;
+    draw[pl] = __ldg(reinterpret_cast<const uint4*>(dX + (((grow >> 7) * x_chunks + level) * 128 + (grow & 127)) * 8));
+  }
+  float p[3], x01[3];
+  ray_point01(a, ray, i, 0, p, x01);
+  const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+  float w0[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell0.w[k] : 1.0f - cell0.w[k];
+    w0[c] = w;
+  }
+  float agg[8][F];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int f = 0; f < F; ++f) agg[c][f] = 0.0f;
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    mli_cell_t cell = cell0;
+    if (pl) {
+      ray_point01(a, ray, i, pl, p, x01);
+      cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+    }
+    float d[F];
+    {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&draw[pl]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h[k]); d[2 * k] = f2.x; d[2 * k + 1] = f2.y; }
+    }
+    const bool same = cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2];
+    if (same) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float w = 1.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell.w[k] : 1.0f - cell.w[k];
+        if (pl) w -= w0[c];
+#pragma unroll
+        for (int f = 0; f < F; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t row;
+        float w;
+        mli_corner(lv, cell, c, &row, &w);
+        scatter_entry<F>(table_grad, row, w, d);
+#pragma unroll
+        for (int f = 0; f < F; ++f) agg[c][f] = fmaf(-w0[c], d[f], agg[c][f]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t row;
+    float w;
+    mli_corner(lv, cell0, c, &row, &w);
+    scatter_entry<F>(table_grad, row, 1.0f, agg[c]);
   }
 }
 
@@ -444,6 +567,28 @@ extern "C" int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, c
   if (R == 0) return MLI_OK;
   dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
   encode_rays_tcl_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_encode_rays_bwd_tcl(const mli_grid_t* grid, const float* center, const float* ray_unit,
+                                       const float* dists, int64_t ld_d, int64_t R, int32_t n, int32_t taps,
+                                       float tap_eps, float vol_min, float vol_max, const void* dX, int32_t x_chunks,
+                                       float* table_grad, int32_t level_begin, int32_t level_end, void* stream) {
+  MLI_ENTRY();
+  if (int e = check_grid(grid)) return e;
+  RayArgs a;
+  if (int e = make_ray_args(&a, center, ray_unit, dists, ld_d, R, n, taps, tap_eps, vol_min, vol_max)) return e;
+  MLI_REQUIRE(grid->feat == 8 && x_chunks >= (int32_t)grid->n_levels, "encode_rays_bwd_tcl: needs F = 8 and one chunk per level");
+  MLI_REQUIRE(taps == 0 || (R * n) % 128 == 0, "encode_rays_bwd_tcl: with taps, R*n must be a multiple of 128");
+  MLI_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= (int32_t)grid->n_levels, "encode_rays_bwd_tcl: bad level range");
+  if (R == 0 || level_begin == level_end) return MLI_OK;
+  dim3 g(mli_cdiv(R * n, kThreads), level_end - level_begin);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* d = (const __nv_bfloat16*)dX;
+  if (taps == 4) encode_rays_bwd_tcl_kernel<5><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else if (taps == 6) encode_rays_bwd_tcl_kernel<7><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else encode_rays_bwd_tcl_kernel<1><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

@@ -19,6 +19,33 @@ class GradReducer:
         self.stream = None
         if side_stream and torch.cuda.is_available():
             self.stream = torch.cuda.Stream()
+        self._early = {}  # data_ptr of gradients whose slabs were already reduced through the engine hook
+
+    # -- overlap of the hash-table gradient exchange with the rest of the backward pass ------------------------------
+    def attach(self, engine):
+        """Have `engine` hand over each level group's slab of the hash-table gradient as soon as its scatter kernel has
+        been launched: the all-reduce of that slab then runs on the side stream (NCCL over NVLink) while the compute
+        stream continues with the next level group and the deferred weight-gradient GEMMs."""
+        engine.table_grad_hook = self._on_table_slab if self.world > 1 else None
+
+    def _avg(self, t):
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)  # averaged inside NCCL: no extra pass over the 1.46 GB
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.mul_(1.0 / self.world)
+
+    def _on_table_slab(self, flat, a, b):
+        if self.stream is None:
+            self._avg(flat[a:b])
+        else:
+            ev = torch.cuda.Event()
+            ev.record()  # the slab is final once everything enqueued so far on the compute stream has run
+            self.stream.wait_event(ev)
+            flat.record_stream(self.stream)
+            with torch.cuda.stream(self.stream):
+                self._avg(flat[a:b])
+        self._early[flat.data_ptr()] = self._early.get(flat.data_ptr(), 0) + (b - a)
 
     def _buckets(self):
         """(big tensors reduced in place, list of small grads flattened into one bucket)."""
@@ -26,7 +53,10 @@ class GradReducer:
         for n, p in self.model.named_parameters():
             if p.grad is None:
                 continue
+            if self._early.get(p.grad.data_ptr(), 0) == p.grad.numel():
+                continue  # every slab of this gradient already went through the hook during backward
             (big if p.grad.numel() >= (1 << 22) else small).append(p.grad)
+        self._early = {}
         return big, small
 
     def allreduce_grads(self):
@@ -34,7 +64,6 @@ class GradReducer:
         if self.world <= 1:
             return
         big, small = self._buckets()
-        scale = 1.0 / self.world
         cur = torch.cuda.current_stream() if self.stream is not None else None
         if self.stream is not None:
             self.stream.wait_stream(cur)
@@ -44,12 +73,10 @@ class GradReducer:
                 flat = g.view(-1)
                 slices = self.level_slices or [(0, flat.numel())]
                 for a, b in slices:
-                    dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM)
-                flat.mul_(scale)
+                    self._avg(flat[a:b])
             if small:
                 bucket = torch.cat([g.reshape(-1) for g in small])
-                dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
-                bucket.mul_(scale)
+                self._avg(bucket)
                 off = 0
                 for g in small:
                     g.copy_(bucket[off:off + g.numel()].view_as(g))

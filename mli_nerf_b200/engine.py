@@ -119,10 +119,28 @@ class RenderEngine:
         self.normal_eps = 1.0 / cfg.resolutions()[-1]
         self.active_levels = cfg.n_levels
         self.W = None
+        # multi-GPU overlap: called as hook(table_grad_flat, start_elem, end_elem) right after the scatter kernel of a
+        # level group has been launched (that slab of the hash-table gradient is final once the kernel completes)
+        self.table_grad_hook = None
 
     # ------------------------------------------------------------------------------------------------------
     def n_table_params(self):
         return int(self.grid.n_entries) * self.cfg.feat_per_level
+
+    def level_groups(self):
+        """Level ranges launched separately by the table-gradient scatter: the small dense levels together, then one
+        (128 MB at T = 2^22) hashed level at a time.  -> [(level_begin, level_end, elem_begin, elem_end)]"""
+        F, lv = self.cfg.feat_per_level, self.grid.level
+        n = self.cfg.n_levels
+        first = 0
+        while first < n and not lv[first].hashed:
+            first += 1
+        bounds = ([0, first] if first > 0 else [0]) + list(range(first + 1, n + 1))
+        out = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            end = (lv[b].offset if b < n else int(self.grid.n_entries)) * F
+            out.append((a, b, int(lv[a].offset) * F, int(end)))
+        return out
 
     def set_active_levels(self, active):
         self.active_levels = int(active)
@@ -214,8 +232,8 @@ class RenderEngine:
         call("mli_tc_wgrad", L, L.shape[1], l_chunk0, l_b, R, R.shape[1], r_chunk0, r_b, M, rows, cols, batch, out, ldo,
              bstride, transpose, db, rows, ws)
 
-    def _tc_colsum(self, X, chunk0, n_chunks, M):
-        out = self._f(n_chunks * 8)
+    def _tc_colsum(self, X, chunk0, n_chunks, M, out=None):
+        out = self._f(n_chunks * 8) if out is None else out
         ws = torch.empty(_lib.load().mli_tc_colsum_ws_bytes(M, n_chunks), dtype=torch.uint8, device=self.device)
         call("mli_tc_colsum", X, X.shape[1], chunk0, n_chunks, M, out, ws)
         return out
@@ -378,6 +396,7 @@ class RenderEngine:
         dH0 = self._tcl(M, 32) if (need_sdf and self.tc) else None            # same quantity, bf16 TCL
         dXx = self._f(M, KH_PAD - XH_OFF) if need_sdf else None
         dW1, db1 = (self._f(HID, HID), None) if (need_sdf and train_mlp) else (None, None)
+        later = []  # deferred weight-gradient launches (tensor-core mode)
         if not self.tc:
             # ---- heads, fp32 CUDA-core path -------------------------------------------------------------------------
             dZ = self._f(M, nh * HID)
@@ -415,27 +434,34 @@ class RenderEngine:
                      1, prec)
         else:
             # ---- heads + SDF layer 1 on the tensor cores (bf16 TCL operands, fp32 accumulation in TMEM) ---------------
+            # Data-gradient chain first, weight gradients deferred (`later`): the hash-table gradient -- the 1.46 GB that
+            # a multi-GPU step has to all-reduce -- only depends on the former, so it is launched as early as possible
+            # and its exchange overlaps the weight-gradient GEMMs.
             T, XH = W["T"], ctx["XH"]
             dZ = self._tcl(M, nh * 32)
             call("mli_tc_rowdot_bwd_data", dS, 8, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ)
             if need_heads:
-                dSt = self._to_tcl(dS, 8, M, 8, self._tcl(M, 2), 128, 0, 2)
-                outT = self._f(nh, 16, HID)  # [head][j][k] = sum_m dS[m, j] A4[m, head*256 + k]
-                self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1)
-                dWout = torch.stack([outT[self.col_off[j] // HID, j] for j in range(self.J)])
-                dbout = self._tc_colsum(dSt, 0, 1, M)[:self.J]
+                def _out_layer():
+                    dSt = self._to_tcl(dS, 8, M, 8, self._tcl(M, 2), 128, 0, 2)
+                    outT = self._f(nh, 16, HID)  # [head][j][k] = sum_m dS[m, j] A4[m, head*256 + k]
+                    self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1)
+                    dWout.copy_(torch.stack([outT[self.col_off[j] // HID, j] for j in range(self.J)]))
+                    dbout.copy_(self._tc_colsum(dSt, 0, 1, M)[:self.J])
+                later.append(_out_layer)
             for l in (2, 1, 0):
                 if need_heads:
                     dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
-                    self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID, HID * HID, db=dbh[l + 1])
+                    later.append(lambda dZ=dZ, l=l: self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID,
+                                                                   HID * HID, db=dbh[l + 1]))
                 dZp = self._tcl(M, nh * 32)
                 self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0, A[l], 0, 32, ACT_RELU, dZp,
                                 False, 0, 32, 0, M, nh, 1)
                 dZ = dZp
             if need_heads:
                 dbh[0] = self._f(nh * HID)
-                self._tc_wgrad(dZ, 0, 0, XH, 0, 0, M, nh * HID, 256, 1, dWh0, KH_PAD, 0, db=dbh[0])
-                self._tc_wgrad(dZ, 0, 0, XH, XH_OFF // 8, 0, M, nh * HID, KH_PAD - XH_OFF, 1, dWh0[:, XH_OFF:], KH_PAD, 0)
+                later.append(lambda dZ=dZ: self._tc_wgrad(dZ, 0, 0, XH, 0, 0, M, nh * HID, 256, 1, dWh0, KH_PAD, 0, db=dbh[0]))
+                later.append(lambda dZ=dZ: self._tc_wgrad(dZ, 0, 0, XH, XH_OFF // 8, 0, M, nh * HID, KH_PAD - XH_OFF, 1,
+                                                          dWh0[:, XH_OFF:], KH_PAD, 0))
             if need_sdf:
                 dZ1 = self._tcl(M, 32)
                 self._tc_linear(dZ, 0, 0, T["Wh0t_feat"], 0, nh * HID, HID, 256, None, 0, XH, 0, 0, ACT_SOFTPLUS100, dZ1,
@@ -444,9 +470,15 @@ class RenderEngine:
                                 ACT_NONE, dXx, True, 0, 0, KH_PAD - XH_OFF, M, 1, 1)
                 if train_mlp:
                     db1 = self._f(HID)
-                    self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0, db=db1)
+                    later.append(lambda: self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0, db=db1))
                 self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dH0, False, 0, 0, 0,
                                 M, 1, 1)
+        if need_sdf:
+            grads.update(self._backward_sdf(p, ctx, need, train_mlp, d_grad, d_hessians, dXx, d_sdf_c, dZ0, dH0, dW1, db1,
+                                            later))
+        for fn in later:
+            fn()
+        later.clear()
         if need_heads:
             j0 = 0
             for hi, (name, kind, odim, _) in enumerate(self.heads):
@@ -469,8 +501,16 @@ class RenderEngine:
                 grads[pre + "4.weight_v"], grads[pre + "4.weight_g"] = dv, dg
                 grads[pre + "4.bias"] = dbout[j0:j0 + odim]
                 j0 += odim
-        if not need_sdf:
-            return grads
+        return grads
+
+    def _backward_sdf(self, p, ctx, need, train_mlp, d_grad, d_hessians, dXx, d_sdf_c, dZ0, dH0, dW1, db1, later):
+        """SDF stencil -> SDF trunk -> hash table part of backward().  The table gradient is launched here, level group
+        by level group; the trunk's weight gradients are appended to `later`."""
+        cfg, W = self.cfg, self.W
+        R, M, P, N = ctx["R"], ctx["M"], ctx["P"], cfg.n_samples
+        prec = _lib.PREC_FP32
+        H0 = ctx["H0"]
+        grads = {}
         d_sdf = self._f(P * M)
         call("mli_geometry_bwd", ctx["gradients"], M, N, cfg.taps, self.tap_eps, ctx["outside"], d_grad, d_hessians, dXx,
              KH_PAD - XH_OFF, 0, d_sdf_c, d_sdf)
@@ -486,12 +526,13 @@ class RenderEngine:
             call("mli_tc_sdf_trunk_bwd", d_sdf, M, cfg.taps, ctx["S0"], ctx["DZ"], dH0, ctx["H0c"], W["w_sdf"], Ed, dw_sdf,
                  db_sdf, ws)
             if train_mlp:
-                self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0)
-                db0 = self._tc_colsum(Ed, 0, 32, M)  # plane 0 = E = sum of the per-plane gradients
+                db0 = self._f(HID)
+                later.append(lambda: self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0))
+                later.append(lambda: self._tc_colsum(Ed, 0, 32, M, out=db0))  # plane 0 = E = sum of the per-plane grads
             if "table" in need:
-                dX0 = self._f(P * M, 128)
-                self._tc_linear(Ed, 0, 0, T["W0t_enc"], 0, HID, 128, 128, None, 0, None, 0, 0, ACT_NONE, dX0, True, 0, 0,
-                                128, P * M, 1, 1)
+                dX0 = self._tcl(P * M, 16)  # bf16 TCL: chunk l = level l, read back coalesced by the scatter kernel
+                self._tc_linear(Ed, 0, 0, T["W0t_enc"], 0, HID, 128, 128, None, 0, None, 0, 0, ACT_NONE, dX0, False, 0, 0,
+                                0, P * M, 1, 1)
         else:
             # ---- SDF network layer 0 + SDF head in fp32 on the CUDA cores (the rtol-1e-3 parity mode) -------------------
             ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(P * M, 1, HID), dtype=torch.uint8, device=self.device)
@@ -511,23 +552,34 @@ class RenderEngine:
                 dX0 = self._f(P * M, 128)
                 call("mli_linear_dgrad", dZ0, HID, 0, W["W0t"], HID, 0, None, 0, 0, dX0, 128, 0, P * M, HID, 128, ACT_NONE,
                      0, 1, prec)
-        if train_mlp:
-            dv, dg = self._f(HID, 131), self._f(HID, 1)
-            call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.0.weight_v"],
-                 p["neural_sdf.mlp.linears.0.weight_g"], dW0, K0_PAD, HID, 131, self.map_sdf0, 0, dv, dg)
-            grads["neural_sdf.mlp.linears.0.weight_v"], grads["neural_sdf.mlp.linears.0.weight_g"] = dv, dg
-            grads["neural_sdf.mlp.linears.0.bias"] = db0
-            dv, dg = self._f(HID, HID), self._f(HID, 1)
-            call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.1.weight_v"],
-                 p["neural_sdf.mlp.linears.1.weight_g"], dW1, HID, HID, HID, None, 0, dv, dg)
-            grads["neural_sdf.mlp.linears.1.weight_v"], grads["neural_sdf.mlp.linears.1.weight_g"] = dv, dg
-            grads["neural_sdf.mlp.linears.1.bias"] = db1
-            grads["neural_sdf.mlp.linear_sdf.weight"], grads["neural_sdf.mlp.linear_sdf.bias"] = dw_sdf, db_sdf
         if "table" in need:
             tg = self._z(self.n_table_params())
-            call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
-                 self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg, int(self.tc))
+            if self.tc:
+                groups = self.level_groups() if self.table_grad_hook is not None else \
+                    [(0, cfg.n_levels, 0, self.n_table_params())]  # one launch when nobody waits for single slabs
+                for lv0, lv1, e0, e1 in groups:
+                    call("mli_encode_rays_bwd_tcl", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N,
+                         cfg.taps, self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 16, tg, lv0, lv1)
+                    if self.table_grad_hook is not None:
+                        self.table_grad_hook(tg, e0, e1)
+            else:
+                call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
+                     self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg, 0)
             grads["neural_sdf.tcnn_encoding.params"] = tg
+        if train_mlp:
+            dv0, dg0, dv1, dg1 = self._f(HID, 131), self._f(HID, 1), self._f(HID, HID), self._f(HID, 1)
+
+            def _unpack():
+                call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.0.weight_v"],
+                     p["neural_sdf.mlp.linears.0.weight_g"], dW0, K0_PAD, HID, 131, self.map_sdf0, 0, dv0, dg0)
+                call("mli_weightnorm_unpack_grad", p["neural_sdf.mlp.linears.1.weight_v"],
+                     p["neural_sdf.mlp.linears.1.weight_g"], dW1, HID, HID, HID, None, 0, dv1, dg1)
+            later.append(_unpack)  # after the (possibly deferred) weight-gradient GEMMs
+            grads["neural_sdf.mlp.linears.0.weight_v"], grads["neural_sdf.mlp.linears.0.weight_g"] = dv0, dg0
+            grads["neural_sdf.mlp.linears.0.bias"] = db0
+            grads["neural_sdf.mlp.linears.1.weight_v"], grads["neural_sdf.mlp.linears.1.weight_g"] = dv1, dg1
+            grads["neural_sdf.mlp.linears.1.bias"] = db1
+            grads["neural_sdf.mlp.linear_sdf.weight"], grads["neural_sdf.mlp.linear_sdf.bias"] = dw_sdf, db_sdf
         return grads
 
     # ------------------------------------------------------------------------------------------------------

@@ -40,6 +40,42 @@ def test_grad_allreduce_mean_world2(tmp_path):
         assert torch.equal(res[r]["head.bias"], res[0]["head.bias"])
 
 
+def _worker_hook(rank, world, port_no, out):
+    """Overlap path: slabs of the big gradient go through the engine hook during 'backward'; the final call must only
+    reduce what is left (and must not average the table a second time)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = torch.nn.ModuleDict(dict(table=torch.nn.Embedding(1 << 19, 8), head=torch.nn.Linear(7, 3)))
+    g = torch.Generator().manual_seed(200 + rank)
+    tg = torch.randn(model["table"].weight.numel(), generator=g)
+    red = GradReducer(model, world, side_stream=False)
+
+    class Eng:
+        table_grad_hook = None
+    eng = Eng()
+    red.attach(eng)
+    n = tg.numel()
+    for a, b in ((0, n // 4), (n // 4, n // 2), (n // 2, n)):
+        eng.table_grad_hook(tg, a, b)
+    model["table"].weight.grad = tg.view_as(model["table"].weight)
+    model["head"].weight.grad = torch.randn(3, 7, generator=g)
+    red.allreduce_grads()
+    torch.save({k: p.grad for k, p in model.named_parameters() if p.grad is not None}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_grad_allreduce_overlap_hook_world2(tmp_path):
+    world, out = 2, str(tmp_path / "h")
+    mp.spawn(_worker_hook, args=(world, 29741, out), nprocs=world, join=True)
+    res = [torch.load(out + f".{r}") for r in range(world)]
+    gens = [torch.Generator().manual_seed(200 + r) for r in range(world)]
+    tabs = [torch.randn((1 << 19) * 8, generator=g) for g in gens]
+    heads = [torch.randn(3, 7, generator=g) for g in gens]
+    for r in range(world):
+        assert torch.allclose(res[r]["table.weight"].reshape(-1), sum(tabs) / world, atol=1e-6)
+        assert torch.allclose(res[r]["head.weight"], sum(heads) / world, atol=1e-6)
+
+
 def test_shard_rays_partition():
     for n, w in ((640000, 8), (97200, 4), (10, 3), (5, 8)):
         spans = [shard_rays(n, r, w) for r in range(w)]

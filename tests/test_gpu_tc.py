@@ -333,3 +333,10 @@ def test_encode_rays_bwd_delta_basis_equals_absolute_basis(lib):
     scale = float(tg_abs.abs().max())
     assert scale > 0
     assert float((tg_abs - tg_del).abs().max()) < 2e-4 * scale, (float((tg_abs - tg_del).abs().max()), scale)
+    # bf16 TCL input variant (what the tensor-core path uses): equals the fp32 delta-basis kernel on bf16-rounded input
+    tg_ref, tg_tcl = torch.zeros(n_par, device="cuda"), torch.zeros(n_par, device="cuda")
+    lib.call("mli_encode_rays_bwd", *args, bf(dXd).reshape(P * M, 128).cuda(), 128, tg_ref, 1)
+    dXt = to_tcl_host(dXd.reshape(P * M, 128)).cuda()
+    for lv0, lv1 in ((0, 6), (6, 7), (7, 16)):  # level groups, as the overlapped multi-GPU backward launches them
+        lib.call("mli_encode_rays_bwd_tcl", *args, dXt, 16, tg_tcl, lv0, lv1)
+    assert float((tg_ref - tg_tcl).abs().max()) < 1e-5 * float(tg_ref.abs().max())
