@@ -262,24 +262,42 @@ def main():
     value = world * RAYS * args.steps / (ms * 1e-3)
     e2e = world * RAYS * args.steps / (ms_e2e * 1e-3)
     hbm_peak, tf_peak, peak_src = peaks()
-    dense = [k for k in prof if k.startswith(("mli_linear", "mli_rowdot", "mli_tc_linear", "mli_tc_wgrad", "mli_tc_sdf_trunk_fwd", "mli_tc_rowdot"))]
+    # Dominant kernel class = the dense layers (the fused-MLP work, 806.0 MFLOP per ray fwd+bwd at 4 taps,
+    # full-grad; 631.3 heads-only), i.e. every tcgen05 GEMM entry point (+ the CUDA-core ones in fp32 mode).  Their
+    # summed CUDA-event time over the timed steps is the denominator of `achieved`.
+    dense_keys = ("mli_linear", "mli_rowdot", "mli_tc_linear", "mli_tc_wgrad", "mli_tc_sdf_trunk_fwd", "mli_tc_rowdot")
+    dense = [k for k in prof if k.startswith(dense_keys)]
     dense_ms = sum(prof[k][1] for k in dense)
+    prof_ms = sum(v[1] for v in prof.values())
     frac_flops = 1.0 if args.grad == "full" else 631.3 / 806.0
     achieved_tf = MLP_FLOP_PER_RAY * frac_flops * RAYS * args.steps / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else 0.0
+    # DRAM traffic of the same kernels for one step, from the committed ncu capture of this command (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("precision") == args.precision and t.get("grad") == args.grad:
+            traffic = t.get("dense_layers_dram_bytes_per_step")
+    # per-kernel HBM view (algorithmic bytes are in DESIGN.md section 4): time share of every entry point
+    shares = {k: round(v[1] / prof_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]} if prof_ms else {}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "grad": args.grad, "precision": args.precision, "rays_per_gpu": RAYS,
-                   "samples_per_ray": N_SAMPLES, "cuda_graph": (not args.no_graph) and world == 1, "l2": "inputs larger than L2: 1.46 GB hash table + 1.46 GB gradient "
+                   "samples_per_ray": N_SAMPLES, "cuda_graph": (not args.no_graph) and world == 1,
+                   "l2": "inputs larger than L2: 1.46 GB hash table + 1.46 GB gradient "
                    "buffer streamed every step (L2 = 126 MB), 8 rotating ray batches"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,  # our kernels per `steps` steps (counted on the eager pass; the graph replays the same)
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "dense layers (mli_linear_fwd/dgrad/wgrad + rowdot)",
+        "roofline": {"bound": "tensor", "kernel": "dense layers: " + ", ".join(sorted(dense)),
                      "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "share_of_step": dense_ms / ms if ms > 0 else None},
+                     "traffic": traffic, "peak_source": peak_src,
+                     "share_of_step": dense_ms / prof_ms if prof_ms > 0 else None,
+                     "hbm_view": {"peak_gbs": hbm_peak,
+                                  "note": "unfused layer-by-layer GEMMs are HBM-bound: see profiles/ for GB/s per kernel"},
+                     "time_shares": shares},
         "profile_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
     if not args.no_cpu_baseline:

@@ -103,12 +103,15 @@ __global__ void __launch_bounds__(kTile) sdf_trunk_bwd_kernel(const float* __res
         unpack8(dzr[p], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float a = fast_expm1(fminf(fmaxf(100.0f * d[i], -80.0f), 80.0f));
-          const float q = a * s0[i];
-          const float sp = __fdividef((1.0f + a) * s0[i], 1.0f + q);  // sigmoid(100 (z0 + dz)) from sigma0 and dz
+          // sigmoid(100 (z0 + dz)) = et s0 / (1 + (et - 1) s0), et = exp(100 dz).  Plain MUFU exp / log suffice in the
+          // backward: the absolute error of dh (~4e-9) times |g_i| (~1e3) stays ~1e-5 below the O(0.1..1) sums.
+          const float t = fminf(fmaxf(100.0f * d[i], -80.0f), 80.0f);
+          const float et = __expf(t);
+          const float num = et * s0[i];
+          const float sp = __fdividef(num, 1.0f - s0[i] + num);
           e[i] = gp * w[i] * sp;
           E[i] += e[i];
-          if (WITH_DW) hw[i] = fmaf(gp, fast_log1p(q) * 0.01f, hw[i]);
+          if (WITH_DW) hw[i] = fmaf(gp, __logf(1.0f - s0[i] + num) * 0.01f, hw[i]);
         }
         *reinterpret_cast<uint4*>(Ed + (int64_t)(p + 1) * M * 256 + e_idx) = pack8(e);
       }
