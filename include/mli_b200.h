@@ -175,6 +175,13 @@ int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_b
 int mli_tc_sdf_trunk_fwd(const void* X, int32_t x_chunks, int32_t K, const void* W0s, const float* b0,
                          const float* w_sdf, const float* b_sdf, int64_t rows, int32_t mode, int64_t rows_per_plane,
                          float* sigma0, void* h_or_dz, float* vec_out, void* stream);
+/* The same in ONE launch for a training/eval forward: per 128-sample tile the centre rows and every tap plane run in
+ * the same persistent CTA, sigma0 stays in TMEM between them (never re-read from HBM).  X holds the 1+taps planes
+ * (plane-major, M rows each); sdf [(1+taps)*M] receives plane 0 = sdf, plane i = sdf_tap_i - sdf_centre; sigma0 and dz
+ * may be NULL when no backward pass follows.  M % 128 == 0. */
+int mli_tc_sdf_trunk_fused(const void* X, int32_t x_chunks, int32_t K, const void* W0s, const float* b0,
+                           const float* w_sdf, const float* b_sdf, int64_t M, int32_t taps, float* sigma0, void* h0,
+                           void* dz, float* sdf, void* stream);
 /* Backward of the trunk's activation / SDF head in the delta basis.  g [(1+taps)*M] = dL/d sdf of every stencil plane
  * (mli_geometry_bwd), dH0 = dL/d h0 arriving through layer 1 (bf16 TCL, 32 chunks, may be NULL).  Writes Ed (bf16 TCL,
  * (1+taps)*M rows x 32 chunks): plane 0 = E = sum over planes of e_p, plane i = e_i, with

@@ -341,16 +341,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kP_EpiWarps) : "memory"); }
 
-// expm1 / log1p for the tap epilogue: MUFU-based away from 0, 4-term Taylor near 0 (relative error < 3e-6 either way)
-__device__ __forceinline__ float fast_expm1(float t) {
-  const float big = __expf(t) - 1.0f;
-  const float small = t * (1.0f + t * (0.5f + t * (0.16666667f + t * 0.041666668f)));
-  return sel_lt(fabsf(t), 0.03f, small, big);
-}
-__device__ __forceinline__ float fast_log1p(float q) {
-  const float big = __logf(1.0f + q);
-  const float small = q * (1.0f + q * (-0.5f + q * (0.33333334f - q * 0.25f)));
-  return sel_lt(fabsf(q), 0.03f, small, big);
+// dh = softplus(z0 + dz) - softplus(z0) = log(1 + (exp(100 dz) - 1) sigma0) / 100 with plain MUFU exp / log.
+// Error budget: both MUFU ops contribute an ABSOLUTE error of ~5e-9 to dh (5e-7 on exp, 4e-7 on log, x 1/100); dh is
+// ~2.5e-4 per unit, so d_i = w_sdf . dh keeps ~2e-5 relative accuracy (gradient) and the 4-tap Hessian
+// sum_i d_i / (2 e^2) sees ~0.1 of pseudo-random error, below the fp32 reference's own 0.35.
+// (A Taylor-patched expm1/log1p pair bought nothing measurable and doubled the instruction count of an epilogue that is
+// ALU-bound: 2 epilogue warps per scheduler.)
+__device__ __forceinline__ float tap_dh(float dz, float sigma0) {
+  const float t = fminf(fmaxf(100.0f * dz, -80.0f), 80.0f);
+  return __logf(fmaf(__expf(t) - 1.0f, sigma0, 1.0f)) * 0.01f;
 }
 
 template <int EPI, int ACT, bool OUT_F32>
@@ -525,11 +524,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
             }
             const float* sg = reinterpret_cast<const float*>(cur);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float t = fminf(fmaxf(100.0f * v[i], -80.0f), 80.0f);
-              const float dh = fast_log1p(fast_expm1(t) * sg[i]) * 0.01f;
-              dot = fmaf(s_w2[c0 + i], dh, dot);
-            }
+            for (int i = 0; i < 32; ++i) dot = fmaf(s_w2[c0 + i], tap_dh(v[i], sg[i]), dot);
             if (p.out) {  // dz (bf16 TCL) for the backward pass
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)tile_m * p.out_chunks + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
@@ -584,6 +579,234 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused SDF trunk: centre rows AND all tap rows of a 128-sample tile in one persistent CTA.
+//   TMEM (512 columns): [0,256) centre accumulator z0, overwritten IN PLACE by the centre epilogue with
+//   sigma0 = sigmoid(100 z0) (tcgen05.st), which the tap epilogues then read back with tcgen05.ld -- the tap rows never
+//   fetch sigma0 from HBM (that re-read was half of the unfused tap kernel's traffic); [256,384) / [384,512): the two
+//   128-column halves of a tap plane's accumulator, used ping-pong so the epilogue of one half overlaps the MMAs of the
+//   next (the tap's A tile is streamed once per half; the second pass hits L2).
+// Work order per sample tile: centre (N = 256), then (tap 1, half 0), (tap 1, half 1), (tap 2, half 0), ...
+// Outputs: sdf[plane 0] = w_sdf . softplus(z0) + b_sdf, sdf[plane i] = w_sdf . (softplus(z0 + dz_i) - softplus(z0)),
+// h0 (bf16 TCL), and -- for the backward pass only -- sigma0 (fp32 TCL32) and dz (bf16 TCL).
+// ---------------------------------------------------------------------------------------------------------------
+struct TcSdfFused {
+  const __nv_bfloat16* X; int x_chunks, k_chunks, stage_chunks;
+  const __nv_bfloat16* W0s; const float* b0; const float* w2; const float* b2;
+  int64_t M; int taps;
+  float* s0; __nv_bfloat16* h0; __nv_bfloat16* dz; float* sdf;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+constexpr int kF_Stages = 4;
+
+__global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdfFused p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * kF_Stages + 2 + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_b0[256];
+  __shared__ __align__(16) float s_w2[256];
+  __shared__ float s_part[2][kTileM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kc = p.k_chunks, kc_total = 2 * p.k_chunks, stage_chunks = p.stage_chunks;
+  const uint32_t b_bytes = (uint32_t)kc_total * 256 * 16;
+  const uint32_t a_stage_bytes = kStageChunks * kTileM * 16;
+  const uint32_t sB = smem_u32(smem), sA = sB + b_bytes;
+  const uint32_t b_full = smem_u32(&bars[0]);
+  const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kF_Stages]);
+  const uint32_t c_full = smem_u32(&bars[1 + 2 * kF_Stages]), c_empty = smem_u32(&bars[2 + 2 * kF_Stages]);
+  const uint32_t t_full0 = smem_u32(&bars[3 + 2 * kF_Stages]), t_empty0 = smem_u32(&bars[5 + 2 * kF_Stages]);
+  const int n_kt = kc_total / stage_chunks;
+  const int n_st = (int)(p.M / kTileM);  // sample tiles (= tiles per plane)
+  const int taps = p.taps;
+
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    for (int s = 0; s < kF_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
+    mbar_init(c_full, 1); mbar_init(c_empty, kP_EpiWarps);
+    for (int h = 0; h < 2; ++h) { mbar_init(t_full0 + 8 * h, 1); mbar_init(t_empty0 + 8 * h, kP_EpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += kP_Threads) { s_b0[i] = p.b0[i]; s_w2[i] = p.w2[i]; }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_full, b_bytes);
+      for (int c = 0; c < kc_total; c += kStageChunks) {
+        const int nch = min(kStageChunks, kc_total - c);
+        bulk_g2s(sB + c * 256 * 16, p.W0s + (int64_t)c * 256 * 8, nch * 256 * 16, b_full);
+      }
+      uint32_t cnt = 0;
+      for (int st = blockIdx.x; st < n_st; st += gridDim.x) {
+        for (int u = 0; u < 1 + 2 * taps; ++u) {  // unit 0 = centre, then (tap, half) pairs: each streams one A tile
+          const int plane = u == 0 ? 0 : 1 + (u - 1) / 2;
+          const __nv_bfloat16* a_src = p.X + ((int64_t)plane * n_st + st) * p.x_chunks * (kTileM * 8);
+          for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
+            const uint32_t s = cnt % kF_Stages;
+            if (cnt >= kF_Stages) mbar_wait(a_empty0 + 8 * s, ((cnt / kF_Stages) - 1) & 1);
+            mbar_expect_tx(a_full0 + 8 * s, stage_chunks * kTileM * 16);
+            bulk_g2s(sA + s * a_stage_bytes, a_src + (int64_t)kt * stage_chunks * kTileM * 8, stage_chunks * kTileM * 16, a_full0 + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_c = make_idesc(256, 0, 0), idesc_t = make_idesc(128, 0, 0);
+      const uint32_t lbo_a = kTileM * 16, lbo_b = 256 * 16;
+      mbar_wait(b_full, 0);
+      uint32_t cnt = 0, it = 0;
+      for (int st = blockIdx.x; st < n_st; st += gridDim.x, ++it) {
+        for (int u = 0; u < 1 + 2 * taps; ++u) {
+          uint32_t d_tmem, idesc, b_row_off;
+          if (u == 0) {
+            if (it >= 1) mbar_wait(c_empty, (it - 1) & 1);  // every tap epilogue of the previous tile has read sigma0
+            d_tmem = tmem_base; idesc = idesc_c; b_row_off = 0;
+          } else {
+            const uint32_t h = (u - 1) & 1, n_use = it * taps + (u - 1) / 2;  // uses of this half-buffer so far
+            if (n_use >= 1) mbar_wait(t_empty0 + 8 * h, (n_use - 1) & 1);
+            d_tmem = tmem_base + 256 + h * 128; idesc = idesc_t; b_row_off = h * 128 * 16;
+          }
+          tc_fence_after();
+          uint32_t first = 1;
+          for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
+            const uint32_t s = cnt % kF_Stages;
+            mbar_wait(a_full0 + 8 * s, (cnt / kF_Stages) & 1);
+            tc_fence_after();
+            const int c_begin = kt * stage_chunks;
+            const uint32_t sa = sA + s * a_stage_bytes;
+            if (c_begin < kc) {  // A hi stage: x B hi and x B lo
+              const uint32_t sb_hi = sB + c_begin * lbo_b + b_row_off, sb_lo = sB + (kc + c_begin) * lbo_b + b_row_off;
+              for (int kk = 0; kk < stage_chunks / 2; ++kk) {
+                const uint64_t da = make_desc(sa + kk * 2 * lbo_a, lbo_a, 128);
+                umma(d_tmem, da, make_desc(sb_hi + kk * 2 * lbo_b, lbo_b, 128), idesc, first ^ 1u);
+                first = 0;
+                umma(d_tmem, da, make_desc(sb_lo + kk * 2 * lbo_b, lbo_b, 128), idesc, 1u);
+              }
+            } else {             // A lo stage: x B hi
+              const uint32_t sb_hi = sB + (c_begin - kc) * lbo_b + b_row_off;
+              for (int kk = 0; kk < stage_chunks / 2; ++kk)
+                umma(d_tmem, make_desc(sa + kk * 2 * lbo_a, lbo_a, 128), make_desc(sb_hi + kk * 2 * lbo_b, lbo_b, 128), idesc, 1u);
+            }
+            umma_commit(a_empty0 + 8 * s);
+          }
+          umma_commit(u == 0 ? c_full : t_full0 + 8 * ((u - 1) & 1));
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;            // TMEM lane quarter
+    const int sub = (warp - 2) >> 2;   // which of the two warps of the quarter: takes the 32-column chunks of its parity
+    const int r_local = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t it = 0, sync_cnt = 0;
+    for (int st = blockIdx.x; st < n_st; st += gridDim.x, ++it) {
+      const int64_t row = (int64_t)st * kTileM + r_local;
+      // ---- centre: z0 -> h0, sigma0 (kept in TMEM), sdf0 ----------------------------------------------------------
+      float dot = 0.0f;
+      mbar_wait(c_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const int c0 = (sub + 2 * k) * 32;
+        float v[32], sg[32];
+        tmem_ld32(tmem_base + lane_addr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float z = v[i] + s_b0[c0 + i];
+          const float bz = 100.0f * z;
+          const float e = __expf(-fabsf(bz));
+          const float h = fmaxf(z, 0.0f) + __logf(1.0f + e) * 0.01f;
+          const float rcp = __fdividef(1.0f, 1.0f + e);
+          sg[i] = sel_lt(bz, 0.0f, e * rcp, rcp);
+          dot = fmaf(s_w2[c0 + i], h, dot);
+          v[i] = h;
+        }
+        tmem_st32(tmem_base + lane_addr + c0, sg);
+        if (p.s0) {
+          float* sdst = p.s0 + ((int64_t)st * 64 * kTileM + (int64_t)(c0 / 4) * kTileM + r_local) * 4;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(sdst + (int64_t)g * kTileM * 4) = make_float4(sg[g * 4], sg[g * 4 + 1], sg[g * 4 + 2], sg[g * 4 + 3]);
+        }
+        __nv_bfloat16* dst = p.h0 + ((int64_t)st * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (sub == 1) s_part[sync_cnt & 1][r_local] = dot;
+      epi_bar_sync();
+      if (sub == 0 && row < p.M) p.sdf[row] = dot + s_part[sync_cnt & 1][r_local] + p.b2[0];
+      ++sync_cnt;
+      // ---- taps: dz -> dh = log1p(expm1(100 dz) sigma0) / 100 -> d_i ---------------------------------------------
+      for (int tp = 0; tp < taps; ++tp) {
+        float dt = 0.0f;
+        const uint32_t n_use = it * taps + tp;
+        const int64_t trow_tile = (int64_t)tp * n_st + st;  // tile index inside the [taps*M, 256] dz matrix
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(t_full0 + 8 * h, n_use & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int k = 0; k < 2; ++k) {
+            const int cl = (sub + 2 * k) * 32;   // column inside the half
+            const int c0 = h * 128 + cl;         // hidden unit
+            float v[32], sg[32];
+            tmem_ld32(tmem_base + lane_addr + 256 + h * 128 + cl, v);
+            tmem_ld32(tmem_base + lane_addr + c0, sg);
+            if (k == 1) {  // last read of this half-accumulator by this warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(t_empty0 + 8 * h);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dt = fmaf(s_w2[c0 + i], tap_dh(v[i], sg[i]), dt);
+            if (p.dz) {
+              __nv_bfloat16* dst = p.dz + (trow_tile * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+            }
+          }
+        }
+        if (tp == taps - 1) {  // sigma0 of this tile is not needed any more: the centre accumulator may be reused
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(c_empty);
+        }
+        if (sub == 1) s_part[sync_cnt & 1][r_local] = dt;
+        epi_bar_sync();
+        if (sub == 0 && row < p.M) p.sdf[(int64_t)(1 + tp) * p.M + row] = dt + s_part[sync_cnt & 1][r_local];
+        ++sync_cnt;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -1027,6 +1250,34 @@ extern "C" int mli_tc_sdf_trunk_fwd(const void* X, int32_t x_chunks, int32_t K, 
   if (mode == 0) return launch_nt<EPI_SDF_CENTER, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
   if (mode == 1) return launch_nt<EPI_SDF_TAP, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
   return launch_nt<EPI_SDF_ONLY, MLI_ACT_SOFTPLUS100, false>(p, 256, 1, st);
+}
+
+// Fused centre + taps variant of mli_tc_sdf_trunk_fwd (one launch, sigma0 resident in TMEM)
+extern "C" int mli_tc_sdf_trunk_fused(const void* X, int32_t x_chunks, int32_t K, const void* W0s, const float* b0,
+                                      const float* w_sdf, const float* b_sdf, int64_t M, int32_t taps, float* sigma0,
+                                      void* h0, void* dz, float* sdf, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= kTileM && M % kTileM == 0, "tc_sdf_trunk_fused: M must be a positive multiple of 128");
+  MLI_REQUIRE(taps == 4 || taps == 6, "Only support 4 or 6 taps.");
+  MLI_REQUIRE(K >= 16 && K % 16 == 0 && x_chunks >= K / 4, "tc_sdf_trunk_fused: X must hold [hi | lo] halves of K/8 chunks each");
+  MLI_REQUIRE(X && W0s && b0 && w_sdf && b_sdf && h0 && sdf, "tc_sdf_trunk_fused: NULL argument");
+  TcSdfFused p;
+  memset(&p, 0, sizeof(p));
+  p.X = (const __nv_bfloat16*)X; p.x_chunks = x_chunks; p.k_chunks = K / 8;
+  int sc = kStageChunks;
+  while (sc > 2 && (p.k_chunks % sc) != 0) sc -= 2;
+  MLI_REQUIRE(p.k_chunks % sc == 0, "tc_sdf_trunk_fused: K/8 must be even");
+  p.stage_chunks = sc;
+  p.W0s = (const __nv_bfloat16*)W0s; p.b0 = b0; p.w2 = w_sdf; p.b2 = b_sdf; p.M = M; p.taps = taps;
+  p.s0 = sigma0; p.h0 = (__nv_bfloat16*)h0; p.dz = (__nv_bfloat16*)dz; p.sdf = sdf;
+  const size_t smem = (size_t)2 * p.k_chunks * 256 * 16 + (size_t)kF_Stages * kStageChunks * kTileM * 16;
+  MLI_REQUIRE(smem + 3584 <= 232448, "tc_sdf_trunk_fused: weight tile does not fit in shared memory");
+  if (int e = set_smem((const void*)tc_sdf_trunk_fused_kernel, smem)) return e;
+  int grid = (int)(M / kTileM);
+  if (grid > MLI_NUM_SMS) grid = MLI_NUM_SMS;
+  tc_sdf_trunk_fused_kernel<<<grid, kP_Threads, smem, (cudaStream_t)stream>>>(p);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
 }
 
 extern "C" int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t cols_out, int32_t batch) {

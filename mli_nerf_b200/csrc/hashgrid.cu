@@ -144,6 +144,7 @@ struct RayArgs {
   int64_t ld_d, R;
   int32_t n, taps;
   float tap_eps, vol_min, vol_range;
+  float inv_range;  // 1/vol_range when that is exact (power-of-two range, e.g. [-2, 2]): x/range == x*inv_range bit for bit
 };
 
 __device__ __forceinline__ void ray_point01(const RayArgs& a, int64_t ray, int i, int plane, float* p, float* x01) {
@@ -151,7 +152,8 @@ __device__ __forceinline__ void ray_point01(const RayArgs& a, int64_t ray, int i
   float r[3] = {a.ray_unit[ray * 3], a.ray_unit[ray * 3 + 1], a.ray_unit[ray * 3 + 2]};
   mli_sample_point(c, r, a.dists[ray * a.ld_d + i], a.taps, plane, a.tap_eps, p);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) x01[k] = mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+  for (int k = 0; k < 3; ++k)
+    x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
 }
 
 template <int F>
@@ -289,100 +291,69 @@ __device__ __forceinline__ void store_split8(__nv_bfloat16* __restrict__ X, int 
   *reinterpret_cast<uint4*>(X + ((tile * x_chunks + kc + chunk) * 128 + r) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-__global__ void __launch_bounds__(kThreads) encode_rays_tcl_kernel(mli_grid_t grid, const float* __restrict__ table,
-                                                                   RayArgs a, __nv_bfloat16* __restrict__ X,
-                                                                   int x_chunks, int kc) {
+// Thread = (sample, level, plane): blockDim = (kS samples, planes).  A warp is 32 consecutive samples of ONE plane, so
+// its stores are 512 contiguous bytes; the 1+taps warps that share a sample range run side by side, their corner
+// fetches hit the same sectors (the tap points are < 0.15 finest cells from the centre) and merge in L1.  The centre
+// row reaches the tap threads through shared memory (fp32) for the delta.  ~60 registers -> 40+ warps per SM: the
+// previous thread-per-(sample, level) version looped over the planes at 16 warps per SM and was latency bound.
+template <int KS>
+__global__ void __launch_bounds__(KS * 7) encode_rays_tcl_kernel(mli_grid_t grid, const float* __restrict__ table,
+                                                                 RayArgs a, __nv_bfloat16* __restrict__ X,
+                                                                 int x_chunks, int kc) {
   constexpr int F = 8;
+  __shared__ __align__(16) float s_acc[KS][F];
+  __shared__ float s_p[KS][3];
   const int level = blockIdx.y;
   const int64_t M = a.R * a.n;
-  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (m >= M) return;
-  const int64_t ray = m / a.n;
-  const int i = (int)(m - ray * a.n);
-  const int planes = 1 + a.taps;
+  const int sl = threadIdx.x, pl = threadIdx.y;
+  const int64_t m = (int64_t)blockIdx.x * KS + sl;
+  const bool valid = m < M;
   const int L = grid.n_levels;
-  const bool active = level < (int)grid.active_levels;
-  const mli_level_t& lv = grid.level[level];
-  // centre: fetch the 8 corner sectors once and KEEP them -- a tap point is < 0.15 finest cells away, so it nearly
-  // always lies in the same cell and its interpolation only needs new weights (same fma order as a fresh fetch, so
-  // the result is bit-identical); only taps that cross a cell face gather again.  This cuts the L1 requests of the
-  // 5-plane stencil by ~3.5x (the kernel was bound by L1 wavefronts, profiles/r01_summary.md).
-  float p0[3], x01[3], acc0[F], vals0[8][F];
-  ray_point01(a, ray, i, 0, p0, x01);
-  mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+  float p[3] = {0.f, 0.f, 0.f}, acc[F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) acc0[f] = 0.0f;
-  if (active) {
-    uint32_t rows[8];
-    float wts[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) mli_corner(lv, cell0, c, &rows[c], &wts[c]);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) load_entry<F>(table, rows[c], vals0[c]);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int f = 0; f < F; ++f) acc0[f] = fmaf(wts[c], vals0[c][f], acc0[f]);
-  }
-  store_split8(X, x_chunks, kc, m, level, acc0);
-  if (level == 0) {  // xyz chunk + zero padding chunks, once per row
-    float v[8] = {p0[0], p0[1], p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-    store_split8(X, x_chunks, kc, m, L, v);
-    v[0] = v[1] = v[2] = 0.0f;
-    for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, m, c, v);
-  }
-  for (int pl = 1; pl < planes; ++pl) {
-    float p[3], acc[F];
+  for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+  if (valid) {
+    const int64_t ray = m / a.n;
+    const int i = (int)(m - ray * a.n);
+    float x01[3];
     ray_point01(a, ray, i, pl, p, x01);
+    if (level < (int)grid.active_levels) interp<F>(grid.level[level], table, x01[0], x01[1], x01[2], acc);
+  }
+  if (pl == 0) {
 #pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
-    if (active) {
-      const mli_cell_t cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
-      if (cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2]) {
+    for (int f = 0; f < F; ++f) s_acc[sl][f] = acc[f];
+    s_p[sl][0] = p[0]; s_p[sl][1] = p[1]; s_p[sl][2] = p[2];
+  }
+  __syncthreads();
+  if (!valid) return;
+  if (pl != 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float w = 1.0f;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) w *= ((c >> d) & 1) ? cell.w[d] : 1.0f - cell.w[d];
-#pragma unroll
-          for (int f = 0; f < F; ++f) acc[f] = fmaf(w, vals0[c][f], acc[f]);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint32_t row;
-          float w, v[F];
-          mli_corner(lv, cell, c, &row, &w);
-          load_entry<F>(table, row, v);
-#pragma unroll
-          for (int f = 0; f < F; ++f) acc[f] = fmaf(w, v[f], acc[f]);
-        }
-      }
-    }
-    const int64_t grow = (int64_t)pl * M + m;
-#pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] -= acc0[f];
-    store_split8(X, x_chunks, kc, grow, level, acc);
-    if (level == 0) {
-      float v[8] = {p[0] - p0[0], p[1] - p0[1], p[2] - p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
-      store_split8(X, x_chunks, kc, grow, L, v);
-      v[0] = v[1] = v[2] = 0.0f;
-      for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, grow, c, v);
-    }
+    for (int f = 0; f < F; ++f) acc[f] -= s_acc[sl][f];
+    p[0] -= s_p[sl][0]; p[1] -= s_p[sl][1]; p[2] -= s_p[sl][2];
+  }
+  const int64_t grow = (int64_t)pl * M + m;
+  store_split8(X, x_chunks, kc, grow, level, acc);
+  if (level == 0) {  // xyz chunk + zero padding chunks, once per row
+    float v[8] = {p[0], p[1], p[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    store_split8(X, x_chunks, kc, grow, L, v);
+    v[0] = v[1] = v[2] = 0.0f;
+    for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, grow, c, v);
   }
 }
 
 // backward of encode_rays_tcl w.r.t. the table: dX is bf16 TCL-128 ([.., x_chunks, 128, 8], chunk l = level l) in the
 // delta basis (see encode_rays_bwd_kernel).  All planes' 16-byte gradient slices are loaded up front (independent,
 // fully coalesced: consecutive samples -> consecutive 16 B), then the same aggregation as the fp32 kernel.
+constexpr int kBwdThreads = 128;  // 4 CTAs of 128 threads at <= 128 registers: 16 warps per SM instead of 8
+
 template <int PLANES>
-__global__ void __launch_bounds__(kThreads) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
+__global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
                                                                        const __nv_bfloat16* __restrict__ dX, int x_chunks,
                                                                        float* __restrict__ table_grad, int level0) {
   constexpr int F = 8;
   const int level = level0 + blockIdx.y;
   const int64_t M = a.R * a.n;
-  const int64_t m = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t m = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
   if (m >= M || level >= (int)grid.active_levels) return;
   const mli_level_t& lv = grid.level[level];
   const int64_t ray = m / a.n;
@@ -409,7 +380,9 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_tcl_kernel(mli_grid_
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int f = 0; f < F; ++f) agg[c][f] = 0.0f;
-#pragma unroll
+  // Rolled plane loop (the unrolled one was 3.8k instructions and stalled on instruction fetch); the preloaded gradient
+  // slices stay in registers and rotate down one slot per iteration so that draw[0] is always the current plane.
+#pragma unroll 1
   for (int pl = 0; pl < PLANES; ++pl) {
     mli_cell_t cell = cell0;
     if (pl) {
@@ -418,7 +391,10 @@ __global__ void __launch_bounds__(kThreads) encode_rays_bwd_tcl_kernel(mli_grid_
     }
     float d[F];
     {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&draw[pl]);
+      const uint4 cur = draw[0];
+#pragma unroll
+      for (int k = 0; k + 1 < PLANES; ++k) draw[k] = draw[k + 1];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur);
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h[k]); d[2 * k] = f2.x; d[2 * k + 1] = f2.y; }
     }
@@ -516,6 +492,8 @@ static int make_ray_args(RayArgs* a, const float* center, const float* ray_unit,
   MLI_REQUIRE(vol_max > vol_min, "empty volume range");
   a->center = center; a->ray_unit = ray_unit; a->dists = dists; a->ld_d = ld_d; a->R = R; a->n = n;
   a->taps = taps; a->tap_eps = tap_eps; a->vol_min = vol_min; a->vol_range = vol_max - vol_min;
+  int ex = 0;
+  a->inv_range = frexpf(a->vol_range, &ex) == 0.5f ? 1.0f / a->vol_range : 0.0f;  // power of two -> exact reciprocal
   return MLI_OK;
 }
 
@@ -565,8 +543,15 @@ extern "C" int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, c
               "encode_rays_tcl: need k_chunks >= levels+1 (even) and x_chunks >= 2*k_chunks");
   MLI_REQUIRE(taps == 0 || (R * n) % 128 == 0, "encode_rays_tcl: with taps, R*n must be a multiple of 128 (plane-major tiles)");
   if (R == 0) return MLI_OK;
-  dim3 g(mli_cdiv(R * n, kThreads), grid->n_levels);
-  encode_rays_tcl_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+  if (taps == 0) {
+    constexpr int KS = 128;
+    dim3 g(mli_cdiv(R * n, KS), grid->n_levels);
+    encode_rays_tcl_kernel<KS><<<g, dim3(KS, 1), 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+  } else {
+    constexpr int KS = 64;
+    dim3 g(mli_cdiv(R * n, KS), grid->n_levels);
+    encode_rays_tcl_kernel<KS><<<g, dim3(KS, 1 + taps), 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+  }
   MLI_LAUNCH_OK();
   return MLI_OK;
 }
@@ -583,12 +568,12 @@ extern "C" int mli_encode_rays_bwd_tcl(const mli_grid_t* grid, const float* cent
   MLI_REQUIRE(taps == 0 || (R * n) % 128 == 0, "encode_rays_bwd_tcl: with taps, R*n must be a multiple of 128");
   MLI_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= (int32_t)grid->n_levels, "encode_rays_bwd_tcl: bad level range");
   if (R == 0 || level_begin == level_end) return MLI_OK;
-  dim3 g(mli_cdiv(R * n, kThreads), level_end - level_begin);
+  dim3 g(mli_cdiv(R * n, kBwdThreads), level_end - level_begin);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* d = (const __nv_bfloat16*)dX;
-  if (taps == 4) encode_rays_bwd_tcl_kernel<5><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
-  else if (taps == 6) encode_rays_bwd_tcl_kernel<7><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
-  else encode_rays_bwd_tcl_kernel<1><<<g, kThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  if (taps == 4) encode_rays_bwd_tcl_kernel<5><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else if (taps == 6) encode_rays_bwd_tcl_kernel<7><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else encode_rays_bwd_tcl_kernel<1><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

@@ -79,7 +79,10 @@ MLI_HD uint32_t mli_grid_index(const mli_level_t& lv, uint32_t gx, uint32_t gy, 
     if (stride <= lv.size) { index += gy * stride; stride *= lv.res; }
     if (stride <= lv.size) { index += gz * stride; stride *= lv.res; }
   }
-  return index % lv.size;
+  // index % size without the ~20-instruction runtime-divisor modulo in the common cases (level-uniform branches):
+  // hashed levels have a power-of-two size (mask), dense indices of in-range points are already < size
+  if ((lv.size & (lv.size - 1u)) == 0u) return index & (lv.size - 1u);
+  return index < lv.size ? index : index % lv.size;
 }
 
 struct mli_cell_t {

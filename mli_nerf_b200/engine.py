@@ -313,13 +313,12 @@ class RenderEngine:
             Xd = self._tcl(P * M, 2 * K0_CH)
             call("mli_encode_rays_tcl", self.grid, table, center, ray_unit, dists, N, R, N, cfg.taps, self.tap_eps,
                  cfg.vol_range[0], cfg.vol_range[1], Xd, 2 * K0_CH, K0_CH)
-            S0 = torch.empty(M // 128, 64, 128, 4, dtype=torch.float32, device=self.device)
+            # sigma0 / dz are only written for the backward pass; inside the kernel sigma0 lives in TMEM
+            S0 = torch.empty(M // 128, 64, 128, 4, dtype=torch.float32, device=self.device) if keep_dz else None
             H0c = self._tcl(M, 32)
             DZ = self._tcl(cfg.taps * M, 32) if keep_dz else None
-            call("mli_tc_sdf_trunk_fwd", Xd, 2 * K0_CH, K0_PAD, T["W0s"], W["b0"], W["w_sdf"], W["b_sdf"], M, 0, M, S0,
-                 H0c, sdf)
-            call("mli_tc_sdf_trunk_fwd", Xd[M // 128:], 2 * K0_CH, K0_PAD, T["W0s"], W["b0"], W["w_sdf"], W["b_sdf"],
-                 cfg.taps * M, 1, M, S0, DZ, sdf[M:])
+            call("mli_tc_sdf_trunk_fused", Xd, 2 * K0_CH, K0_PAD, T["W0s"], W["b0"], W["w_sdf"], W["b_sdf"], M, cfg.taps,
+                 S0, H0c, DZ, sdf)
         gradients = self._f(M, 3)
         hessians = self._f(M, 3) if training else None
         S = self._f(M, 8)

@@ -418,8 +418,18 @@ def test_render_bf16_tensor_core_mode(lib):
     for k, (a, b) in dict(rgb=(0, 3), o_r=(3, 6), o_s=(6, 7), o_re=(7, 10)).items():
         err = (out[:, a:b] - out_ref[k][0].detach()).abs()
         assert float(err.max()) < 2e-2 and float(err.mean()) < 3e-3, (k, float(err.max()), float(err.mean()))
-    # SDF trunk layer 0 stays fp32, so geometry is unchanged
+    # SDF trunk: split-bf16 operands (3 tcgen05 products, ~16 mantissa bits) + fp32-formed tap deltas.  Stated bounds:
+    # sdf |err| <= 1e-3*|sdf| + 1e-5; numerical gradients: relative L2 error <= 2e-3 over the rays that hit the
+    # bounds; Hessians: mean |err| <= 1.0 (the fp32 reference's own cancellation noise is ~0.35)
     assert torch.allclose(res["sdf"].cpu()[:256 * 128].view(256, 128), out_ref["sdfs"][0, :, :, 0], rtol=1e-3, atol=1e-5)
+    inside = ~out_ref["outside"][0, :, 0]
+    g_got, g_ref = res["gradients"].cpu().view(256, 128, 3)[inside], out_ref["gradients"][0].detach()[inside]
+    g_err = float((g_got - g_ref).norm() / g_ref.norm())
+    h_got, h_ref = res["hessians"].cpu().view(256, 128, 3)[inside], out_ref["hessians"][0].detach()[inside]
+    h_err = float((h_got - h_ref).abs().mean())
+    print(f"bf16 mode: gradient rel L2 err {g_err:.2e}, hessian mean abs err {h_err:.3f} (|hess| mean {float(h_ref.abs().mean()):.1f})")
+    assert g_err < 2e-3, g_err
+    assert h_err < 1.0, h_err
     tg = {k: cu(v[0]) for k, v in case["targets"].items()}
     _, d_out, d_grad, d_hess = eng.losses(loss_cfg(ocfg0), res["out"], res["gradients"], res["hessians"], outside, tg)
     grads = eng.backward(p, ctx, d_out, d_grad, d_hess, None)

@@ -224,6 +224,15 @@ def test_sdf_trunk_fwd_taps_delta(lib):
         assert err < 2e-4, (i, err)
         dzi = from_tcl_host(dz.cpu()[i * M // 128:(i + 1) * M // 128], M).double()
         assert torch.allclose(dzi, zi - z0, rtol=1e-2, atol=1e-5)
+    # fused single-launch variant (sigma0 resident in TMEM, tap accumulators in two 128-column halves): same numbers
+    s0f, h0f, dzf = torch.zeros_like(s0), torch.zeros_like(h0), torch.zeros_like(dz)
+    sdff = torch.zeros_like(sdf)
+    lib.call("mli_tc_sdf_trunk_fused", X, *args, M, taps, s0f, h0f, dzf, sdff)
+    assert torch.equal(s0f.cpu(), s0.cpu()) and torch.equal(h0f.cpu(), h0.cpu()) and torch.equal(dzf.cpu(), dz.cpu())
+    assert torch.allclose(sdff.cpu(), sdf.cpu(), rtol=1e-6, atol=1e-9)
+    sdfe = torch.zeros_like(sdf)   # eval flavour: no sigma0 / dz stores
+    lib.call("mli_tc_sdf_trunk_fused", X, *args, M, taps, None, h0f, None, sdfe)
+    assert torch.equal(sdfe.cpu(), sdff.cpu())
     # second-order quantity (what the Hessian uses): sum of the 4 deltas of a symmetric stencil
     dxs = torch.randn(M, K) * 3e-4
     dxs[:, 131:] = 0

@@ -69,9 +69,34 @@ def bench_wgrad(rows, cols, batch, with_db, nbuf=3, label=""):
           f"{2.0 * M * batch * rows * cols / us / 1e6:7.1f} TFLOP/s")
 
 
+def bench_encode(log2_T, taps=4, R=2048, n=128):
+    import math
+    grid = _lib.make_grid(16, 8, log2_T, 32, math.exp((math.log(2048) - math.log(32)) / 15))
+    n_par = int(grid.n_entries) * 8
+    table = (torch.rand(n_par, device=dev) * 2 - 1) * 1e-2
+    g = torch.Generator(device="cpu").manual_seed(0)
+    center = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    ray = torch.nn.functional.normalize(0.3 * torch.randn(R, 3, generator=g) - center, dim=-1)
+    dists = (2.0 + 2.0 * torch.rand(R, n, generator=g).sort(dim=1).values).to(dev)
+    center, ray = center.to(dev), ray.to(dev)
+    P, Mq = 1 + taps, R * n
+    X = torch.empty(P * Mq // 128, 36, 128, 8, dtype=torch.bfloat16, device=dev)
+    eps = 1.0 / 2048 / math.sqrt(3)
+    us_f = timeit(lambda i: _lib.call("mli_encode_rays_tcl", grid, table, center, ray, dists, n, R, n, taps, eps, -2.0, 2.0,
+                                      X, 36, 18))
+    dX = tcl(P * Mq, 16)
+    tg = torch.zeros(n_par, device=dev)
+    us_b = timeit(lambda i: _lib.call("mli_encode_rays_bwd_tcl", grid, center, ray, dists, n, R, n, taps, eps, -2.0, 2.0,
+                                      dX, 16, tg, 0, 16))
+    print(f"encode T=2^{log2_T} ({n_par * 4 / 1e6:.0f} MB table): fwd {us_f:8.1f} us   bwd {us_b:8.1f} us")
+
+
 def main():
     _lib.load()
     which = set(sys.argv[1:])
+    if not which or "encode" in which:
+        for t in (14, 17, 19, 22):
+            bench_encode(t)
     if not which or "linear" in which:
         for st in ("4", "6", None):
             if st is None:
