@@ -127,12 +127,15 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # bounded sample: size the per-step ray count so that warmup+steps finish in ~2.5 minutes
-    n = 64
-    t = cpu_reference_step(n, threads, seed=100)  # also builds the 1.46 GB table
-    t = cpu_reference_step(n, threads, seed=101)
+    # bounded sample: size the per-step ray count so that warmup+steps finish in ~2.5 minutes.  A step costs
+    # t(n) = a + b*n (a = the dense 1.46 GB table gradient, independent of the ray count): fit a, b on two probes.
+    cpu_reference_step(32, threads, seed=100)  # also builds the 1.46 GB table
+    t32 = cpu_reference_step(32, threads, seed=101)
+    t128 = cpu_reference_step(128, threads, seed=102)
+    b = max((t128 - t32) / 96.0, 1e-4)
+    a = max(t32 - 32 * b, 0.0)
     budget = 150.0 / max(1, args.steps + args.warmup)
-    n_rays = int(max(32, min(RAYS, n * budget / max(t, 1e-3))))
+    n_rays = int(max(32, min(RAYS, (budget - a) / b)))
     n_rays = 1 << (n_rays.bit_length() - 1)
     for i in range(args.warmup):
         cpu_reference_step(n_rays, threads, seed=200 + i)
@@ -302,8 +305,8 @@ def main():
     }
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n = 256
-        cpu_reference_step(64, threads, seed=1)  # warm-up (allocates the table)
+        n = 512  # bounded sample: ~10-20 s of host time
+        cpu_reference_step(16, threads, seed=1)  # warm-up (allocates the 1.46 GB table)
         t = cpu_reference_step(n, threads, seed=2)
         line["cpu_baseline"] = {"value": n / t, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n} of the {RAYS} rays of one step (x{N_SAMPLES} samples), fwd+bwd, all 5 "

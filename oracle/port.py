@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle.torch_hashgrid import corner_indices, level_table
+from oracle.torch_hashgrid import hash_encode as _hash_encode
 
 
 @dataclass
@@ -93,15 +94,7 @@ def wn_weight(p, prefix):
 
 def hash_encode(p, cfg, x01):
     """tcnn HashGrid stand-in, see torch_hashgrid.py; table = p['neural_sdf.tcnn_encoding.params']."""
-    table = p["neural_sdf.tcnn_encoding.params"].view(-1, cfg.feat_per_level)
-    outs = []
-    for lv in cfg.levels():
-        idx, wt = corner_indices(x01.detach(), lv)
-        acc = torch.zeros(x01.shape[0], cfg.feat_per_level, dtype=torch.float32)
-        for c in range(8):
-            acc = acc + wt[:, c:c + 1] * table[lv["offset"] + idx[:, c]]
-        outs.append(acc)
-    return torch.cat(outs, dim=-1)
+    return _hash_encode(p["neural_sdf.tcnn_encoding.params"], x01, cfg.levels(), cfg.feat_per_level)
 
 
 def sdf_encode(p, cfg, pts):
