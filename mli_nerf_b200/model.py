@@ -130,7 +130,9 @@ class _RenderFunction(torch.autograd.Function):
             eng.pack_weights(p)
             near, far, outside = eng.bounds(center, ray_unit)
             dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], center, ray_unit, near, far, rands)
-            res, saved = eng.forward(p, center, ray_unit, pts_light, dists, near, far, outside, training, model.progress)
+            need_bwd = any(ctx.needs_input_grad[7:])  # no parameter needs a gradient (eval / no_grad): skip the saves
+            res, saved = eng.forward(p, center, ray_unit, pts_light, dists, near, far, outside, training, model.progress,
+                                     keep_dz=need_bwd)
         ctx.model, ctx.names, ctx.saved, ctx.params = model, names, saved, params
         ctx.W = eng.W
         out = res["out"]
@@ -292,6 +294,24 @@ class Model(torch.nn.Module):
             res["_dist"] = extras[:, 4:5].view(B, R, 1)
         return res
 
+    @torch.no_grad()
+    def sdf(self, points, chunk=1 << 20):
+        """``neural_sdf.sdf(points)`` of the reference (projects/neuralangelo/utils/modules.py:73-74), the query the mesh
+        extraction sweeps over its 512^3 lattice (projects/neuralangelo/utils/mesh.py:25-49): points [...,3] -> [...,1].
+        Runs the encode + SDF-trunk kernels of the sampling path (no head layers)."""
+        eng = self.engine
+        names, params = self._named()
+        p = dict(zip(names, params))
+        eng.pack_weights(p)
+        pts = points.reshape(-1, 3).contiguous().float()
+        out = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
+        for s in range(0, pts.shape[0], chunk):
+            c = pts[s:s + chunk]
+            zeros3, zeros1 = torch.zeros_like(c), torch.zeros(c.shape[0], 1, device=c.device)
+            # a "ray" of one sample at distance 0 along a zero direction is the point itself
+            out[s:s + chunk] = eng.sdf_query(p["neural_sdf.tcnn_encoding.params"], c, zeros3, zeros1, 1, 1)
+        return out.view(*points.shape[:-1], 1)
+
     def forward(self, data):
         """NeuralLumen/model.py:113-131."""
         pose = data["pose"]
@@ -375,8 +395,10 @@ class Model(torch.nn.Module):
         return losses
 
     @torch.no_grad()
-    def inference(self, data):
-        """NeuralLumen/model.py:60-111: full-image render in chunks of rand_rays_val rays, eval outputs + *_map."""
+    def inference(self, data, per_sample=True):
+        """NeuralLumen/model.py:60-111: full-image render in chunks of rand_rays_val rays, eval outputs + *_map.
+        ``per_sample=False`` drops the [B,HW,128,.] debug tensors (dists / weights / gradients) that the reference
+        concatenates but nothing downstream reads."""
         self.eval()
         pose = data["pose"]
         B = pose.shape[0]
@@ -388,6 +410,9 @@ class Model(torch.nn.Module):
             e = min(H * W, s + self.rand_rays_val)
             o = self.render_rays_lumen(c[:, s:e], r[:, s:e], l[:, s:e], stratified=False)
             o["depth"] = o.pop("_dist") / norm[:, s:e]
+            if not per_sample:
+                for k in ("dists", "weights", "gradients"):
+                    o.pop(k, None)
             chunks.append(o)
         output = {k: torch.cat([ch[k] for ch in chunks], dim=1) for k, v in chunks[0].items() if v is not None}
         rot = pose[..., :3, :3]
