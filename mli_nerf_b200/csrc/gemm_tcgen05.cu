@@ -612,7 +612,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       : "memory");
 }
 
-constexpr int kF_Stages = 4;
+constexpr int kF_Stages = 6;   // x 12 KB (6-chunk K slices): 72 KB of activations in flight next to the 147 KB weight tile
 
 __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdfFused p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kc = p.k_chunks, kc_total = 2 * p.k_chunks, stage_chunks = p.stage_chunks;
   const uint32_t b_bytes = (uint32_t)kc_total * 256 * 16;
-  const uint32_t a_stage_bytes = kStageChunks * kTileM * 16;
+  const uint32_t a_stage_bytes = (uint32_t)stage_chunks * kTileM * 16;
   const uint32_t sB = smem_u32(smem), sA = sB + b_bytes;
   const uint32_t b_full = smem_u32(&bars[0]);
   const uint32_t a_full0 = smem_u32(&bars[1]), a_empty0 = smem_u32(&bars[1 + kF_Stages]);
@@ -1270,7 +1270,7 @@ extern "C" int mli_tc_sdf_trunk_fused(const void* X, int32_t x_chunks, int32_t K
   p.stage_chunks = sc;
   p.W0s = (const __nv_bfloat16*)W0s; p.b0 = b0; p.w2 = w_sdf; p.b2 = b_sdf; p.M = M; p.taps = taps;
   p.s0 = sigma0; p.h0 = (__nv_bfloat16*)h0; p.dz = (__nv_bfloat16*)dz; p.sdf = sdf;
-  const size_t smem = (size_t)2 * p.k_chunks * 256 * 16 + (size_t)kF_Stages * kStageChunks * kTileM * 16;
+  const size_t smem = (size_t)2 * p.k_chunks * 256 * 16 + (size_t)kF_Stages * p.stage_chunks * kTileM * 16;
   MLI_REQUIRE(smem + 3584 <= 232448, "tc_sdf_trunk_fused: weight tile does not fit in shared memory");
   if (int e = set_smem((const void*)tc_sdf_trunk_fused_kernel, smem)) return e;
   int grid = (int)(M / kTileM);

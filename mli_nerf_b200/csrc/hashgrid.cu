@@ -344,28 +344,40 @@ __global__ void __launch_bounds__(KS * 7) encode_rays_tcl_kernel(mli_grid_t grid
 // backward of encode_rays_tcl w.r.t. the table: dX is bf16 TCL-128 ([.., x_chunks, 128, 8], chunk l = level l) in the
 // delta basis (see encode_rays_bwd_kernel).  All planes' 16-byte gradient slices are loaded up front (independent,
 // fully coalesced: consecutive samples -> consecutive 16 B), then the same aggregation as the fp32 kernel.
-constexpr int kBwdThreads = 128;  // 4 CTAs of 128 threads at <= 128 registers: 16 warps per SM instead of 8
+constexpr int kBwdThreads = 128;
 
+// Two threads per (sample, level), four features each: the per-thread state (corner accumulators 8x4, gradient slices
+// PLANES x 8 B) halves, which lifts the kernel from 16 to 24+ resident warps per SM; every corner update is still one
+// 16-byte RED per thread.  The cell / weight arithmetic is done by both threads of a pair (the kernel is latency bound,
+// not issue bound).  Ray origin / direction / distance are loaded once, not once per plane.
 template <int PLANES>
-__global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
-                                                                       const __nv_bfloat16* __restrict__ dX, int x_chunks,
-                                                                       float* __restrict__ table_grad, int level0) {
-  constexpr int F = 8;
+__global__ void __launch_bounds__(kBwdThreads, 6) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
+                                                                             const __nv_bfloat16* __restrict__ dX, int x_chunks,
+                                                                             float* __restrict__ table_grad, int level0) {
+  constexpr int FH = 4;
   const int level = level0 + blockIdx.y;
   const int64_t M = a.R * a.n;
-  const int64_t m = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
+  const int64_t m = t >> 1;
+  const int half = (int)(t & 1);
   if (m >= M || level >= (int)grid.active_levels) return;
   const mli_level_t& lv = grid.level[level];
   const int64_t ray = m / a.n;
   const int i = (int)(m - ray * a.n);
-  uint4 draw[PLANES];
+  uint2 draw[PLANES];
 #pragma unroll
   for (int pl = 0; pl < PLANES; ++pl) {
     const int64_t grow = (int64_t)pl * M + m;
-    draw[pl] = __ldg(reinterpret_cast<const uint4*>(dX + (((grow >> 7) * x_chunks + level) * 128 + (grow & 127)) * 8));
+    draw[pl] = __ldg(reinterpret_cast<const uint2*>(dX + (((grow >> 7) * x_chunks + level) * 128 + (grow & 127)) * 8 + half * 4));
   }
+  const float rc[3] = {__ldg(a.center + ray * 3), __ldg(a.center + ray * 3 + 1), __ldg(a.center + ray * 3 + 2)};
+  const float rr[3] = {__ldg(a.ray_unit + ray * 3), __ldg(a.ray_unit + ray * 3 + 1), __ldg(a.ray_unit + ray * 3 + 2)};
+  const float rd = __ldg(a.dists + ray * a.ld_d + i);
   float p[3], x01[3];
-  ray_point01(a, ray, i, 0, p, x01);
+  mli_sample_point(rc, rr, rd, a.taps, 0, a.tap_eps, p);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
   const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
   float w0[8];
 #pragma unroll
@@ -375,28 +387,32 @@ __global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli
     for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell0.w[k] : 1.0f - cell0.w[k];
     w0[c] = w;
   }
-  float agg[8][F];
+  float agg[8][FH];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
-    for (int f = 0; f < F; ++f) agg[c][f] = 0.0f;
+    for (int f = 0; f < FH; ++f) agg[c][f] = 0.0f;
+  float* const tg = table_grad + half * FH;
   // Rolled plane loop (the unrolled one was 3.8k instructions and stalled on instruction fetch); the preloaded gradient
   // slices stay in registers and rotate down one slot per iteration so that draw[0] is always the current plane.
 #pragma unroll 1
   for (int pl = 0; pl < PLANES; ++pl) {
     mli_cell_t cell = cell0;
     if (pl) {
-      ray_point01(a, ray, i, pl, p, x01);
+      mli_sample_point(rc, rr, rd, a.taps, pl, a.tap_eps, p);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
       cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
     }
-    float d[F];
+    float d[FH];
     {
-      const uint4 cur = draw[0];
+      const uint2 cur = draw[0];
 #pragma unroll
       for (int k = 0; k + 1 < PLANES; ++k) draw[k] = draw[k + 1];
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const float2 f2 = __bfloat1622float2(h[k]); d[2 * k] = f2.x; d[2 * k + 1] = f2.y; }
+      for (int k = 0; k < 2; ++k) { const float2 f2 = __bfloat1622float2(h[k]); d[2 * k] = f2.x; d[2 * k + 1] = f2.y; }
     }
     const bool same = cell.g[0] == cell0.g[0] && cell.g[1] == cell0.g[1] && cell.g[2] == cell0.g[2];
     if (same) {
@@ -407,7 +423,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli
         for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell.w[k] : 1.0f - cell.w[k];
         if (pl) w -= w0[c];
 #pragma unroll
-        for (int f = 0; f < F; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
+        for (int f = 0; f < FH; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
       }
     } else {
 #pragma unroll
@@ -415,9 +431,9 @@ __global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli
         uint32_t row;
         float w;
         mli_corner(lv, cell, c, &row, &w);
-        scatter_entry<F>(table_grad, row, w, d);
+        atomicAdd(reinterpret_cast<float4*>(tg + (size_t)row * 8), make_float4(w * d[0], w * d[1], w * d[2], w * d[3]));
 #pragma unroll
-        for (int f = 0; f < F; ++f) agg[c][f] = fmaf(-w0[c], d[f], agg[c][f]);
+        for (int f = 0; f < FH; ++f) agg[c][f] = fmaf(-w0[c], d[f], agg[c][f]);
       }
     }
   }
@@ -426,7 +442,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) encode_rays_bwd_tcl_kernel(mli
     uint32_t row;
     float w;
     mli_corner(lv, cell0, c, &row, &w);
-    scatter_entry<F>(table_grad, row, 1.0f, agg[c]);
+    atomicAdd(reinterpret_cast<float4*>(tg + (size_t)row * 8), make_float4(agg[c][0], agg[c][1], agg[c][2], agg[c][3]));
   }
 }
 
@@ -568,7 +584,7 @@ extern "C" int mli_encode_rays_bwd_tcl(const mli_grid_t* grid, const float* cent
   MLI_REQUIRE(taps == 0 || (R * n) % 128 == 0, "encode_rays_bwd_tcl: with taps, R*n must be a multiple of 128");
   MLI_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= (int32_t)grid->n_levels, "encode_rays_bwd_tcl: bad level range");
   if (R == 0 || level_begin == level_end) return MLI_OK;
-  dim3 g(mli_cdiv(R * n, kBwdThreads), level_end - level_begin);
+  dim3 g(mli_cdiv(2 * R * n, kBwdThreads), level_end - level_begin);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* d = (const __nv_bfloat16*)dX;
   if (taps == 4) encode_rays_bwd_tcl_kernel<5><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
