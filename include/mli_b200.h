@@ -240,6 +240,30 @@ int mli_weightnorm_pack(const float* v, const float* g, int32_t N, int32_t K, co
 int mli_weightnorm_unpack_grad(const float* v, const float* g, const float* dWp, int64_t ldw, int32_t N, int32_t K,
                                const int32_t* col_map, int32_t row_off, float* dv, float* dg, void* stream);
 
+/* All weight_norm reparameterisations of a step in ONE launch, written straight into the layouts the tensor-core
+ * kernels read.  Per matrix (descriptor): W = g v/||v|| [N,K] is scattered (col_map, row_off as above) into any of
+ *   Wp    fp32 row-major (ldw)                                                       (may be NULL)
+ *   tcl   bf16 TCL with tcl_tile-row tiles and tcl_chunks chunks per tile row; tcl_lo >= 0 also writes the split-bf16
+ *         remainder bf16(w - bf16(w)) tcl_lo chunks further                           (may be NULL)
+ *   tclt  up to two bf16 TCL copies of column ranges [c0, c1) of the TRANSPOSE: element
+ *         (tclt_row_off + c - c0, tclt_col_off + n)                                   (may be NULL)
+ * Target buffers must be zero where no element is scattered (K padding).  The same descriptors drive the backward:
+ * dWp (fp32, layout of Wp) -> dv [N,K], dg [N] (mli_weightnorm_unpack_grad_batch).  Descriptors live in HOST memory
+ * (at most MLI_WN_MAX_DESCS; they travel as kernel parameters). */
+#define MLI_WN_MAX_DESCS 24
+typedef struct {
+  const float* v; const float* g; const int32_t* col_map;
+  float* Wp; void* tcl; void* tclt[2];
+  const float* dWp; float* dv; float* dg;
+  int64_t ldw;
+  int32_t N, K, row_off;
+  int32_t tcl_tile, tcl_chunks, tcl_lo;
+  int32_t tclt_c0[2], tclt_c1[2], tclt_tile[2], tclt_chunks[2], tclt_row_off[2], tclt_col_off[2];
+  int32_t row_begin;  /* filled by the library */
+} mli_wn_desc_t;
+int mli_weightnorm_pack_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream);
+int mli_weightnorm_unpack_grad_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Rays, bounds, sampling (projects/neuralangelo/model.py:420-484; nerf_util.py:20-68,199-205;
  * NeuralLumen/utils/utils.py:86-123)

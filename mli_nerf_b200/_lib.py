@@ -44,6 +44,19 @@ class LossCfg(C.Structure):
                 ("has_intrinsic", C.c_int32)]
 
 
+class WnDesc(C.Structure):
+    """mli_wn_desc_t (batched weight_norm pack / unpack)."""
+    _fields_ = [("v", C.c_void_p), ("g", C.c_void_p), ("col_map", C.c_void_p),
+                ("Wp", C.c_void_p), ("tcl", C.c_void_p), ("tclt", C.c_void_p * 2),
+                ("dWp", C.c_void_p), ("dv", C.c_void_p), ("dg", C.c_void_p),
+                ("ldw", C.c_int64),
+                ("N", C.c_int32), ("K", C.c_int32), ("row_off", C.c_int32),
+                ("tcl_tile", C.c_int32), ("tcl_chunks", C.c_int32), ("tcl_lo", C.c_int32),
+                ("tclt_c0", C.c_int32 * 2), ("tclt_c1", C.c_int32 * 2), ("tclt_tile", C.c_int32 * 2),
+                ("tclt_chunks", C.c_int32 * 2), ("tclt_row_off", C.c_int32 * 2), ("tclt_col_off", C.c_int32 * 2),
+                ("row_begin", C.c_int32)]
+
+
 # Signature table derived from include/mli_b200.h itself (single source of truth for the ABI):
 #   p = device pointer (tensor / None / int), i = int32, l = int64, f = float, d = double, u = uint32,
 #   s = stream, h / H = HOST int32 / float array (parameter names starting with host_).
@@ -177,6 +190,8 @@ def _n_launches(name, args):
         return (1 if args[10] is not None else 0) + (2 if args[14] is not None else 0)
     if name == "mli_composite_bwd":
         return 1 + (1 if args[18] is not None else 0)
+    if name in ("mli_weightnorm_pack_batch", "mli_weightnorm_unpack_grad_batch"):
+        return 1
     if name == "mli_losses_fwd_bwd":
         return 3 + (1 if args[0].has_intrinsic else 0)
     return 1

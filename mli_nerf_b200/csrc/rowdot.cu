@@ -5,6 +5,8 @@
 // /root/reference/projects/nerf/utils/nerf_util.py:177-178,191 (head output layer),
 // /root/reference/imaginaire/trainers/utils/get_trainer.py:106-150 (AdamW).
 // All of these are HBM-bandwidth bound (one pass over the [M,K] activations).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -179,6 +181,95 @@ __global__ void __launch_bounds__(128) weightnorm_grad_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// batched weight_norm: every matrix of the step in one launch (descriptors travel as kernel parameters)
+// ---------------------------------------------------------------------------------------------------------
+struct WnBatch {
+  mli_wn_desc_t d[MLI_WN_MAX_DESCS];
+  int n;
+};
+
+__device__ __forceinline__ int64_t tcl_index(int64_t R, int C, int tile, int chunks) {
+  return (((R / tile) * chunks + (C >> 3)) * tile + (R % tile)) * 8 + (C & 7);
+}
+
+__global__ void __launch_bounds__(128) weightnorm_pack_batch_kernel(const __grid_constant__ WnBatch b) {
+  __shared__ float red[32];
+  __shared__ float s_scale;
+  int di = 0;
+  while (di + 1 < b.n && (int)blockIdx.x >= b.d[di + 1].row_begin) ++di;
+  const mli_wn_desc_t& d = b.d[di];
+  const int n = blockIdx.x - d.row_begin;
+  const float* vr = d.v + (int64_t)n * d.K;
+  float ss = 0.0f;
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x) { const float x = vr[k]; ss = fmaf(x, x, ss); }
+  ss = mli_block_sum(ss, red);
+  if (threadIdx.x == 0) s_scale = d.g[n] / sqrtf(ss);
+  __syncthreads();
+  const float scale = s_scale;
+  const int64_t R = d.row_off + n;
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
+    const float wv = vr[k] * scale;
+    const int c = d.col_map ? d.col_map[k] : k;
+    if (d.Wp) d.Wp[R * d.ldw + c] = wv;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+    if (d.tcl) {
+      __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(d.tcl);
+      t[tcl_index(R, c, d.tcl_tile, d.tcl_chunks)] = hi;
+      if (d.tcl_lo >= 0) t[tcl_index(R, c + 8 * d.tcl_lo, d.tcl_tile, d.tcl_chunks)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (d.tclt[q] && c >= d.tclt_c0[q] && c < d.tclt_c1[q])
+        reinterpret_cast<__nv_bfloat16*>(d.tclt[q])[tcl_index(d.tclt_row_off[q] + c - d.tclt_c0[q], d.tclt_col_off[q] + n,
+                                                              d.tclt_tile[q], d.tclt_chunks[q])] = hi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) weightnorm_grad_batch_kernel(const __grid_constant__ WnBatch b) {
+  __shared__ float red[32];
+  __shared__ float s_ss, s_dot;
+  int di = 0;
+  while (di + 1 < b.n && (int)blockIdx.x >= b.d[di + 1].row_begin) ++di;
+  const mli_wn_desc_t& d = b.d[di];
+  const int n = blockIdx.x - d.row_begin;
+  const float* vr = d.v + (int64_t)n * d.K;
+  const float* dr = d.dWp + (int64_t)(d.row_off + n) * d.ldw;
+  float ss = 0.0f, dot = 0.0f;
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
+    const float x = vr[k];
+    const float g = dr[d.col_map ? d.col_map[k] : k];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(x, g, dot);
+  }
+  ss = mli_block_sum(ss, red);
+  if (threadIdx.x == 0) s_ss = ss;
+  dot = mli_block_sum(dot, red);
+  if (threadIdx.x == 0) s_dot = dot;
+  __syncthreads();
+  const float norm = sqrtf(s_ss), gn = d.g[n];
+  if (threadIdx.x == 0) d.dg[n] = s_dot / norm;
+  const float c1 = gn / norm, c2 = gn * s_dot / (norm * norm * norm);
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x)
+    d.dv[(int64_t)n * d.K + k] = c1 * dr[d.col_map ? d.col_map[k] : k] - c2 * vr[k];
+}
+
+static int make_wn_batch(WnBatch* b, const mli_wn_desc_t* descs, int32_t n, int* total_rows, bool backward) {
+  MLI_REQUIRE(descs != nullptr && n >= 1 && n <= MLI_WN_MAX_DESCS, "weightnorm batch: 1..%d descriptors", MLI_WN_MAX_DESCS);
+  int rows = 0;
+  for (int i = 0; i < n; ++i) {
+    b->d[i] = descs[i];
+    MLI_REQUIRE(descs[i].v && descs[i].g && descs[i].N >= 1 && descs[i].K >= 1, "weightnorm batch: bad descriptor %d", i);
+    if (backward) MLI_REQUIRE(descs[i].dWp && descs[i].dv && descs[i].dg, "weightnorm batch: descriptor %d has no gradient buffers", i);
+    b->d[i].row_begin = rows;
+    rows += descs[i].N;
+  }
+  b->n = n;
+  *total_rows = rows;
+  return MLI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW single-tensor semantics), gradient pre-scaled by grad_scale (1/world_size)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -317,6 +408,26 @@ extern "C" int mli_adamw_step(float* param, const float* grad, float* exp_avg, f
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4, n, lr, beta1,
                                                                   beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_weightnorm_pack_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream) {
+  MLI_ENTRY();
+  WnBatch b;
+  int rows = 0;
+  if (int e = make_wn_batch(&b, descs_on_host, n_descs, &rows, false)) return e;
+  weightnorm_pack_batch_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(b);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_weightnorm_unpack_grad_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream) {
+  MLI_ENTRY();
+  WnBatch b;
+  int rows = 0;
+  if (int e = make_wn_batch(&b, descs_on_host, n_descs, &rows, true)) return e;
+  weightnorm_grad_batch_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(b);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

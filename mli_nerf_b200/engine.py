@@ -172,6 +172,8 @@ class RenderEngine:
     # ------------------------------------------------------------------------------------------------------
     def pack_weights(self, p):
         """weight_norm reparameterisation into the padded / fused layouts the layer kernels read (per step)."""
+        if self.tc:
+            return self._pack_weights_tc(p)
         nh, W = self.nh, {}
         W["W0"], W["W0t"] = self._z(HID, K0_PAD), self._z(K0_PAD, HID)
         call("mli_weightnorm_pack", p["neural_sdf.mlp.linears.0.weight_v"], p["neural_sdf.mlp.linears.0.weight_g"], HID,
@@ -218,6 +220,116 @@ class RenderEngine:
         self.W = W
         return W
 
+
+    def _wn_specs(self):
+        """(v name, N, K, col_map tensor, row_off) of every weight-normalised matrix, in a fixed order."""
+        specs = [("neural_sdf.mlp.linears.0", HID, 131, self.map_sdf0, 0, "sdf0"),
+                 ("neural_sdf.mlp.linears.1", HID, HID, None, 0, "sdf1")]
+        j0 = 0
+        for hi, (name, kind, odim, _) in enumerate(self.heads):
+            pre = f"neural_rgb.{name}.linears."
+            specs.append((pre + "0", HID, len(_col_map(kind)), self.map_head[hi], hi * HID, ("h0", hi)))
+            for l in range(3):
+                specs.append((pre + f"{l + 1}", HID, HID, None, hi * HID, ("hl", l, hi)))
+            specs.append((pre + "4", odim, HID, None, j0, ("out", hi)))
+            j0 += odim
+        return specs
+
+    def _pack_weights_tc(self, p):
+        """Tensor-core mode: ONE launch writes every W = g v/||v|| straight into the bf16 TCL layouts (and fp32 W_out);
+        one zero-fill provides the K padding.  Replaces 17 pack + 15 layout-conversion launches."""
+        nh, W, T = self.nh, {}, {}
+        bf = torch.bfloat16
+        sizes = dict(W0s=HID * 2 * K0_PAD, W0t_enc=128 * HID, W1=HID * HID, W1t=HID * HID, Wh0=nh * HID * KH_PAD,
+                     Wh0t_feat=HID * nh * HID, Wh0t_x=(KH_PAD - XH_OFF) * nh * HID)
+        for l in range(3):
+            sizes[f"Whl{l}"] = nh * HID * HID
+            sizes[f"Whlt{l}"] = nh * HID * HID
+        flat = torch.zeros(sum(sizes.values()), dtype=bf, device=self.device)
+        off, buf = 0, {}
+        for k, n in sizes.items():
+            buf[k] = flat[off:off + n]
+            off += n
+        T["W0s"] = buf["W0s"].view(1, 2 * K0_CH, 256, 8)
+        T["W0t_enc"] = buf["W0t_enc"].view(1, 32, 128, 8)
+        T["W1"], T["W1t"] = buf["W1"].view(1, 32, 256, 8), buf["W1t"].view(1, 32, 256, 8)
+        T["Wh0"] = buf["Wh0"].view(nh, KH_PAD // 8, 256, 8)
+        T["Wh0t_feat"] = buf["Wh0t_feat"].view(1, nh * 32, 256, 8)
+        T["Wh0t_x"] = buf["Wh0t_x"].view(1, nh * 32, KH_PAD - XH_OFF, 8)
+        T["Whl"] = [buf[f"Whl{l}"].view(nh, 32, 256, 8) for l in range(3)]
+        T["Whlt"] = [buf[f"Whlt{l}"].view(nh, 32, 256, 8) for l in range(3)]
+        W["Wout"] = self._f(self.J, HID)
+        descs = (_lib.WnDesc * 24)()
+        specs = self._wn_specs()
+        for i, (name, N, K, cmap, row_off, tag) in enumerate(specs):
+            d = descs[i]
+            d.v, d.g = p[name + ".weight_v"].data_ptr(), p[name + ".weight_g"].data_ptr()
+            d.col_map = cmap.data_ptr() if cmap is not None else None
+            d.N, d.K, d.row_off, d.tcl_lo = N, K, row_off, -1
+            if tag == "sdf0":
+                d.tcl, d.tcl_tile, d.tcl_chunks, d.tcl_lo = T["W0s"].data_ptr(), 256, 2 * K0_CH, K0_CH
+                d.tclt[0] = T["W0t_enc"].data_ptr()
+                d.tclt_c0[0], d.tclt_c1[0], d.tclt_tile[0], d.tclt_chunks[0] = 0, 128, 128, 32
+            elif tag == "sdf1":
+                d.tcl, d.tcl_tile, d.tcl_chunks = T["W1"].data_ptr(), 256, 32
+                d.tclt[0] = T["W1t"].data_ptr()
+                d.tclt_c0[0], d.tclt_c1[0], d.tclt_tile[0], d.tclt_chunks[0] = 0, HID, 256, 32
+            elif tag[0] == "h0":
+                hi = tag[1]
+                d.tcl, d.tcl_tile, d.tcl_chunks = T["Wh0"].data_ptr(), 256, KH_PAD // 8
+                d.tclt[0] = T["Wh0t_feat"].data_ptr()
+                d.tclt_c0[0], d.tclt_c1[0], d.tclt_tile[0], d.tclt_chunks[0] = 0, HID, 256, nh * 32
+                d.tclt_col_off[0] = hi * HID
+                d.tclt[1] = T["Wh0t_x"].data_ptr()
+                d.tclt_c0[1], d.tclt_c1[1], d.tclt_tile[1], d.tclt_chunks[1] = XH_OFF, KH_PAD, KH_PAD - XH_OFF, nh * 32
+                d.tclt_col_off[1] = hi * HID
+            elif tag[0] == "hl":
+                _, l, hi = tag
+                d.tcl, d.tcl_tile, d.tcl_chunks = T["Whl"][l].data_ptr(), 256, 32
+                d.tclt[0] = T["Whlt"][l].data_ptr()
+                d.tclt_c0[0], d.tclt_c1[0], d.tclt_tile[0], d.tclt_chunks[0] = 0, HID, 256, 32
+                d.tclt_row_off[0] = hi * HID
+            else:  # output layer: fp32 rows of W_out
+                d.Wp, d.ldw = W["Wout"].data_ptr(), HID
+        call("mli_weightnorm_pack_batch", _lib.C.addressof(descs), len(specs))
+        W["b0"], W["b1"] = p["neural_sdf.mlp.linears.0.bias"], p["neural_sdf.mlp.linears.1.bias"]
+        W["w_sdf"], W["b_sdf"] = p["neural_sdf.mlp.linear_sdf.weight"], p["neural_sdf.mlp.linear_sdf.bias"]
+        W["bh"] = [torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for h in self.heads]) for l in range(4)]
+        W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
+        W["T"], W["_keep"] = T, flat
+        self.W = W
+        return W
+
+    def _unpack_grads_tc(self, p, dW0, dW1, dWh0, dWh, dWout, need_heads, train_mlp):
+        """One launch for the weight_norm backward of every matrix: dW (packed fp32) -> dv, dg."""
+        specs = [s for s in self._wn_specs() if (s[5] in ("sdf0", "sdf1") and train_mlp) or
+                 (s[5] not in ("sdf0", "sdf1") and need_heads)]
+        total = sum(N * K + N for _, N, K, _, _, _ in specs)
+        flat = self._f(total)
+        descs = (_lib.WnDesc * 24)()
+        out, off = {}, 0
+        for i, (name, N, K, cmap, row_off, tag) in enumerate(specs):
+            d = descs[i]
+            dv, dg = flat[off:off + N * K].view(N, K), flat[off + N * K:off + N * K + N].view(N, 1)
+            off += N * K + N
+            d.v, d.g = p[name + ".weight_v"].data_ptr(), p[name + ".weight_g"].data_ptr()
+            d.col_map = cmap.data_ptr() if cmap is not None else None
+            d.N, d.K, d.tcl_lo = N, K, -1
+            d.dv, d.dg = dv.data_ptr(), dg.data_ptr()
+            if tag == "sdf0":
+                src, d.ldw, d.row_off = dW0, K0_PAD, 0
+            elif tag == "sdf1":
+                src, d.ldw, d.row_off = dW1, HID, 0
+            elif tag[0] == "h0":
+                src, d.ldw, d.row_off = dWh0, KH_PAD, row_off
+            elif tag[0] == "hl":
+                src, d.ldw, d.row_off = dWh[tag[1]][tag[2]], HID, 0
+            else:
+                src, d.ldw, d.row_off = dWout, HID, row_off
+            d.dWp = src.data_ptr()
+            out[name + ".weight_v"], out[name + ".weight_g"] = dv, dg
+        call("mli_weightnorm_unpack_grad_batch", _lib.C.addressof(descs), len(specs))
+        return out
     # ---- tensor-core (bf16 TCL) building blocks -------------------------------------------------------------------
     def _tc_linear(self, A, a_chunk0, a_bchunks, B, b_belems, K, N, BN, bias, bias_b, aux, aux_chunk0, aux_bchunks, act,
                    out, out_f32, out_chunk0, out_bchunks, ldo, M, batch, epi):
@@ -478,7 +590,20 @@ class RenderEngine:
         for fn in later:
             fn()
         later.clear()
-        if need_heads:
+        if self.tc:
+            # weight_norm backward of every matrix in one launch; biases are plain column sums (already computed)
+            dW0 = grads.pop("_dW0", None)
+            if need_heads or dW0 is not None:
+                grads.update(self._unpack_grads_tc(p, dW0, dW1, dWh0, dWh, dWout, need_heads, dW0 is not None))
+            if need_heads:
+                j0 = 0
+                for hi, (name, kind, odim, _) in enumerate(self.heads):
+                    pre = f"neural_rgb.{name}.linears."
+                    for l in range(4):
+                        grads[pre + f"{l}.bias"] = dbh[l][hi * HID:(hi + 1) * HID]
+                    grads[pre + "4.bias"] = dbout[j0:j0 + odim]
+                    j0 += odim
+        elif need_heads:
             j0 = 0
             for hi, (name, kind, odim, _) in enumerate(self.heads):
                 pre = f"neural_rgb.{name}.linears."
@@ -565,7 +690,12 @@ class RenderEngine:
                 call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
                      self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg, 0)
             grads["neural_sdf.tcnn_encoding.params"] = tg
-        if train_mlp:
+        if train_mlp and self.tc:  # weight_v / weight_g come from the batched unpack in backward()
+            grads["_dW0"] = dW0
+            grads["neural_sdf.mlp.linears.0.bias"] = db0
+            grads["neural_sdf.mlp.linears.1.bias"] = db1
+            grads["neural_sdf.mlp.linear_sdf.weight"], grads["neural_sdf.mlp.linear_sdf.bias"] = dw_sdf, db_sdf
+        elif train_mlp:
             dv0, dg0, dv1, dg1 = self._f(HID, 131), self._f(HID, 1), self._f(HID, HID), self._f(HID, 1)
 
             def _unpack():
