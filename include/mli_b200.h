@@ -161,6 +161,16 @@ int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_b
                   void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
                   int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
                   void* stream);
+/* relu hidden layer (N = 256 per batch member, as mli_tc_linear epi 0) with the narrow output layer that follows it
+ * (nerf_util.py:191, 256 -> 3/3/1) fused into the epilogue: S[m, j] = act_j(w_out[j] . out[m, batch(j) block] + b_out[j])
+ * for j in [host_j0[b], host_j0[b] + host_nj[b]) of batch member b (nj <= 4, batch <= 4); the dot uses the fp32 layer
+ * output before its bf16 rounding.  Saves one HBM pass over the [M, 256*batch] activations. */
+int mli_tc_linear_dot(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
+                      int64_t b_batch_elems, int32_t K, const float* bias, int32_t bias_batch, void* out,
+                      int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks, int64_t M, int32_t batch,
+                      const float* w_out, const float* b_out, const int32_t* host_j0, const int32_t* host_nj,
+                      int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* stream);
+
 /* SDF trunk on the tensor cores (replaces MLPforNeuralSDF layer 0 + softplus + linear_sdf, mlp.py:55-69, for every
  * stencil plane; the numerical-gradient taps of modules.py:131-177 go through as fp32-formed deltas).
  *   X      split-bf16 TCL rows from mli_encode_rays_tcl (x_chunks chunks per tile row, K = 8*k_chunks padded inputs)
@@ -301,11 +311,13 @@ int mli_sample_merge(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n
  * tap_eps is the per-axis offset as a double (eps/sqrt(3) for 4 taps); the float32 divisors 4e, e^2 are derived
  * from it exactly as torch derives them from the Python float. */
 /* sdf_is_delta != 0: planes >= 1 of `sdf` hold sdf_tap - sdf_centre (mli_tc_sdf_trunk_fwd mode 1) instead of
- * absolute values; they are left as deltas. */
+ * absolute values; they are left as deltas.  xh_tcl (may be NULL): the same 38 (+10 zero) columns also / instead as bf16
+ * TCL chunks [xh_chunk0, xh_chunk0+6) of a matrix with xh_chunks chunks per tile row (the tensor-core head input). */
 int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, double tap_eps, const uint8_t* outside,
                      float outside_val, const float* center, const float* ray_unit, const float* pts_light,
                      const float* dists, int64_t ld_d, float* gradients, float* hessians, float* XH, int64_t ldxh,
-                     int32_t xh_off, int32_t sdf_is_delta, void* stream);
+                     int32_t xh_off, int32_t sdf_is_delta, void* xh_tcl, int32_t xh_chunks, int32_t xh_chunk0,
+                     void* stream);
 /* d_sdf [planes*M] = backward of gradients/hessians/normals (+ d_sdf_center_in from the alpha path).
  * d_grad_in / d_hess_in [M,3] may be NULL; dXH supplies d normal at columns xh_off+19..21 (may be NULL). */
 int mli_geometry_bwd(const float* gradients, int64_t M, int32_t N, int32_t taps, double tap_eps,

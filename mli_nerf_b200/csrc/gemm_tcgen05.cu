@@ -124,7 +124,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
 // Epilogues are compile-time (EPI, ACT, OUT_F32): a runtime activation switch inlined into the unrolled column loop
 // made the first version 23k instructions long and instruction-cache bound (profiles/r01_summary.md).
 // ---------------------------------------------------------------------------------------------------------------
-enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_SDF_CENTER = 2, EPI_SDF_TAP = 3, EPI_SDF_ONLY = 4 };
+enum { EPI_BIAS_ACT = 0, EPI_MUL_DACT = 1, EPI_SDF_CENTER = 2, EPI_SDF_TAP = 3, EPI_SDF_ONLY = 4, EPI_BIAS_ACT_DOT = 5 };
 
 struct TcNT {
   const __nv_bfloat16* A; int a_chunks, a_chunk0, a_batch_chunks;   // TCL-128, chunks per tile row, first chunk
@@ -140,6 +140,9 @@ struct TcNT {
   int split, stage_chunks;
   // SDF trunk epilogues (EPI_SDF_*): SDF head weights, per-row output, sigma(100 z0) in fp32 TCL32
   const float* w2; const float* b2; float* vec_out; float* s0; int tiles_per_plane;
+  // EPI_BIAS_ACT_DOT: the narrow output layer that follows this layer, fused into its epilogue.  Batch member b owns
+  // outputs [dot_j0[b], dot_j0[b] + dot_nj[b]) (<= 4 each): S[row, j] = act_j(w_out[j] . out_row + b_out[j])
+  const float* wdot; const float* bdot; float* S; int64_t lds; int dot_j0[4], dot_nj[4]; int dot_act; uint32_t dot_act_mask;
 };
 
 // a < b ? x : y as a predicated select: both sides are always evaluated.  Written as `cond ? cheap : MUFU-chain` the
@@ -177,7 +180,7 @@ __device__ __forceinline__ float act_dfo(float y) {
 template <int EPI, int ACT, bool OUT_F32, int NCOL>
 __device__ __forceinline__ void epi_generic_chunk_n(const TcNT& p, float* v, int c0, int n0, int batch, int tile_m,
                                                     int r_local, int64_t row, const float* bias, const uint4* auxr) {
-  if constexpr (EPI == EPI_BIAS_ACT) {
+  if constexpr (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_DOT) {
     if (bias) {
 #pragma unroll
       for (int g = 0; g < NCOL / 4; ++g) {
@@ -341,15 +344,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kP_EpiWarps) : "memory"); }
 
-// dh = softplus(z0 + dz) - softplus(z0) = log(1 + (exp(100 dz) - 1) sigma0) / 100 with plain MUFU exp / log.
+// dh = softplus(z0 + dz) - softplus(z0) = log(1 + (exp(100 dz) - 1) sigma0) / 100 with the two raw MUFU ops.
 // Error budget: both MUFU ops contribute an ABSOLUTE error of ~5e-9 to dh (5e-7 on exp, 4e-7 on log, x 1/100); dh is
 // ~2.5e-4 per unit, so d_i = w_sdf . dh keeps ~2e-5 relative accuracy (gradient) and the 4-tap Hessian
 // sum_i d_i / (2 e^2) sees ~0.1 of pseudo-random error, below the fp32 reference's own 0.35.
-// (A Taylor-patched expm1/log1p pair bought nothing measurable and doubled the instruction count of an epilogue that is
-// ALU-bound: 2 epilogue warps per scheduler.)
-__device__ __forceinline__ float tap_dh(float dz, float sigma0) {
-  const float t = fminf(fmaxf(100.0f * dz, -80.0f), 80.0f);
-  return __logf(fmaf(__expf(t) - 1.0f, sigma0, 1.0f)) * 0.01f;
+// The tap epilogue is ALU bound (two epilogue warps per scheduler), so the row dot accumulates w * log2(.) and the
+// constant ln2/100 is applied once per row: 7 instructions per element (min, mul, ex2, add, fma, lg2, fma).
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kTapDotScale = 0.0069314718f;  // ln(2) / 100
+__device__ __forceinline__ float tap_dot(float acc, float w, float dz, float sigma0) {
+  const float e = mufu_ex2(fminf(dz, 0.55f) * 144.26950409f);  // exp(100 dz); 100 dz <= 55 keeps e * sigma0 finite
+  return fmaf(w, mufu_lg2(fmaf(e - 1.0f, sigma0, 1.0f)), acc);
 }
 
 template <int EPI, int ACT, bool OUT_F32>
@@ -360,7 +366,10 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
   __shared__ __align__(16) float s_b0[256];
   __shared__ __align__(16) float s_w2[256];
   __shared__ float s_part[2][kTileM];
-  constexpr bool kSdf = EPI >= EPI_SDF_CENTER;
+  __shared__ __align__(16) float s_wd[EPI == EPI_BIAS_ACT_DOT ? 4 * 256 : 4];
+  __shared__ float s_dotp[EPI == EPI_BIAS_ACT_DOT ? 2 * 4 * kTileM : 4];
+  constexpr bool kSdf = EPI >= EPI_SDF_CENTER && EPI <= EPI_SDF_ONLY;
+  constexpr bool kDot = EPI == EPI_BIAS_ACT_DOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.y % n_tiles_n, batch = blockIdx.y / n_tiles_n;
   const int BN = p.BN;
@@ -385,8 +394,11 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
   }
   if (kSdf) {
     for (int i = threadIdx.x; i < 256; i += kP_Threads) { s_b0[i] = p.bias[i]; s_w2[i] = p.w2[i]; }
-  } else if (EPI == EPI_BIAS_ACT && p.bias) {
+  } else if ((EPI == EPI_BIAS_ACT || kDot) && p.bias) {
     for (int i = threadIdx.x; i < BN; i += kP_Threads) s_b0[i] = p.bias[batch * p.bias_batch + tile_n * BN + i];
+  }
+  if (kDot) {
+    for (int i = threadIdx.x; i < p.dot_nj[batch] * 256; i += kP_Threads) s_wd[i] = p.wdot[(int64_t)p.dot_j0[batch] * 256 + i];
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols));
@@ -467,8 +479,9 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
     const int r_local = q * 32 + lane;
     const int n0 = tile_n * BN;
     const int n_cc = (BN + 31) / 32;
-    const float* bias = (EPI == EPI_BIAS_ACT && p.bias) ? s_b0 : nullptr;
+    const float* bias = ((EPI == EPI_BIAS_ACT || kDot) && p.bias) ? s_b0 : nullptr;
     const bool has_aux = (EPI == EPI_MUL_DACT) && p.aux != nullptr;
+    const int nj = kDot ? p.dot_nj[batch] : 0;
     uint32_t it = 0;
     for (int tile_m = blockIdx.x; tile_m < n_row_tiles; tile_m += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
@@ -492,6 +505,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
         for (int g = 0; g < 8; ++g) s0r[g] = __ldg(reinterpret_cast<const float4*>(s0_src + (int64_t)(half * 8 + g) * kTileM * 4));
       }
       float dot = 0.0f;
+      float dj[4] = {0.f, 0.f, 0.f, 0.f};
       mbar_wait(t_full0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       bool released = false;
@@ -513,6 +527,15 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
           const int ncol = min(32, BN - c0);
           if constexpr (!kSdf) {
             epi_generic_chunk<EPI, ACT, OUT_F32>(p, v, ncol, c0, n0, batch, tile_m, r_local, row, bias, has_aux ? auxr[k] : nullptr);
+            if constexpr (kDot) {  // v[] now holds the activated layer output: feed the fused output layer
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (j < nj) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], s_wd[j * 256 + c0 + i], dj[j]);
+                }
+              }
+            }
           } else if constexpr (EPI == EPI_SDF_TAP) {
             // v = dz = W0 (x_tap - x_centre).  dh = softplus(z0 + dz) - softplus(z0) = log1p(expm1(100 dz) * sigma0) / 100
             float4 cur[8];
@@ -524,7 +547,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
             }
             const float* sg = reinterpret_cast<const float*>(cur);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dot = fmaf(s_w2[c0 + i], tap_dh(v[i], sg[i]), dot);
+            for (int i = 0; i < 32; ++i) dot = tap_dot(dot, s_w2[c0 + i], v[i], sg[i]);
             if (p.out) {  // dz (bf16 TCL) for the backward pass
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + ((int64_t)tile_m * p.out_chunks + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
@@ -563,12 +586,30 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty0 + 8 * acc);
       }
+      if constexpr (kDot) {  // output layer: combine the two column halves, bias + activation, store S
+        if (half == 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s_dotp[((it & 1) * 4 + j) * kTileM + r_local] = dj[j];
+        }
+        epi_bar_sync();
+        if (half == 0 && row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nj) {
+              const int jo = p.dot_j0[batch] + j;
+              const float r = dj[j] + s_dotp[((it & 1) * 4 + j) * kTileM + r_local] + (p.bdot ? p.bdot[jo] : 0.0f);
+              p.S[row * p.lds + jo] = ((p.dot_act_mask >> jo) & 1u) ? mli_act(r, p.dot_act) : r;
+            }
+          }
+        }
+      }
       if constexpr (kSdf) {  // combine the two column halves of each row (fixed order: deterministic)
         if (half == 1) s_part[it & 1][r_local] = dot;
         epi_bar_sync();
         if (half == 0 && row < p.M) {
           float r = dot + s_part[it & 1][r_local];
           if constexpr (EPI != EPI_SDF_TAP) r += p.b2[0];
+          else r *= kTapDotScale;
           p.vec_out[row] = r;
         }
       }
@@ -782,7 +823,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
               if (lane == 0) mbar_arrive(t_empty0 + 8 * h);
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dt = fmaf(s_w2[c0 + i], tap_dh(v[i], sg[i]), dt);
+            for (int i = 0; i < 32; ++i) dt = tap_dot(dt, s_w2[c0 + i], v[i], sg[i]);
             if (p.dz) {
               __nv_bfloat16* dst = p.dz + (trow_tile * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
@@ -797,7 +838,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
         }
         if (sub == 1) s_part[sync_cnt & 1][r_local] = dt;
         epi_bar_sync();
-        if (sub == 0 && row < p.M) p.sdf[(int64_t)(1 + tp) * p.M + row] = dt + s_part[sync_cnt & 1][r_local];
+        if (sub == 0 && row < p.M) p.sdf[(int64_t)(1 + tp) * p.M + row] = (dt + s_part[sync_cnt & 1][r_local]) * kTapDotScale;
         ++sync_cnt;
       }
     }
@@ -1135,7 +1176,7 @@ int launch_nt(const TcNT& p, int N, int batch, cudaStream_t st) {
   const int kc_total = p.split ? 2 * p.k_chunks : p.k_chunks;
   // activation ring: as many 16 KB stages as fit next to the resident weight tile (bytes in flight per SM are what
   // bounds the achieved HBM bandwidth of these kernels), at least 3
-  constexpr size_t kStatic = EPI >= EPI_SDF_CENTER ? 3584 : (EPI == EPI_BIAS_ACT ? 1536 : 512);
+  constexpr size_t kStatic = EPI == EPI_BIAS_ACT_DOT ? 10240 : EPI >= EPI_SDF_CENTER ? 3584 : (EPI == EPI_BIAS_ACT ? 1536 : 512);
   const size_t b_bytes = (size_t)kc_total * BN * 16, a_stage = (size_t)kStageChunks * kTileM * 16;
   int n_stages = b_bytes + kStatic < 232448 ? (int)((232448 - kStatic - b_bytes) / a_stage) : 0;
   // measured (tools/bench_kernels.py, head layers): the forward epilogue runs best with 4 stages (6.2 vs 5.4 TB/s with
@@ -1221,6 +1262,34 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
     case MLI_ACT_SOFTPLUS100: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_SOFTPLUS100>(p, N, batch, f32, st);
     default: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_NONE>(p, N, batch, f32, st);
   }
+}
+
+// Hidden layer (relu) with the narrow output layer that follows it fused into the epilogue (N = 256 per batch member).
+extern "C" int mli_tc_linear_dot(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
+                                 int64_t b_batch_elems, int32_t K, const float* bias, int32_t bias_batch, void* out,
+                                 int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks, int64_t M, int32_t batch,
+                                 const float* w_out, const float* b_out, const int32_t* host_j0, const int32_t* host_nj,
+                                 int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(M >= 1 && batch >= 1 && batch <= 4 && K >= 16 && K % 16 == 0, "tc_linear_dot: bad M/batch/K");
+  MLI_REQUIRE(a_chunk0 >= 0 && a_chunk0 + (batch - 1) * a_batch_chunks + K / 8 <= a_chunks, "tc_linear_dot: A chunk range");
+  MLI_REQUIRE(out_chunk0 >= 0 && out_chunk0 + (batch - 1) * out_batch_chunks + 32 <= out_chunks, "tc_linear_dot: out chunk range");
+  MLI_REQUIRE(w_out && S && host_j0 && host_nj, "tc_linear_dot: NULL argument");
+  MLI_REQUIRE(bias == nullptr || (((uintptr_t)bias & 15) == 0 && bias_batch % 4 == 0), "tc_linear_dot: bias must be 16-byte aligned");
+  TcNT p;
+  memset(&p, 0, sizeof(p));
+  p.A = (const __nv_bfloat16*)A; p.a_chunks = a_chunks; p.a_chunk0 = a_chunk0; p.a_batch_chunks = a_batch_chunks;
+  p.B = (const __nv_bfloat16*)B; p.b_batch_elems = b_batch_elems; p.k_chunks = K / 8; p.BN = 256;
+  p.bias = bias; p.bias_batch = bias_batch;
+  p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks; p.M = M;
+  p.split = 0; p.stage_chunks = kStageChunks;
+  p.wdot = w_out; p.bdot = b_out; p.S = S; p.lds = lds; p.dot_act = act_out; p.dot_act_mask = act_mask;
+  for (int b = 0; b < 4; ++b) {
+    p.dot_j0[b] = b < batch ? host_j0[b] : 0;
+    p.dot_nj[b] = b < batch ? host_nj[b] : 0;
+    MLI_REQUIRE(p.dot_nj[b] >= 0 && p.dot_nj[b] <= 4 && p.dot_j0[b] >= 0 && p.dot_j0[b] + p.dot_nj[b] <= lds, "tc_linear_dot: bad output range");
+  }
+  return launch_nt<EPI_BIAS_ACT_DOT, MLI_ACT_RELU, false>(p, 256, batch, (cudaStream_t)stream);
 }
 
 // SDF trunk layer 0 + SDF head on split-bf16 operands (see the persistent kernel).  N = 256 hidden units.

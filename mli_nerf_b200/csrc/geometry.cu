@@ -5,6 +5,8 @@
 // projects/NeuralLumen/model.py:343-349 (outside overwrite before the stencil, normalize, expand),
 // projects/neuralangelo/utils/spherical_harmonics.py:47-70, projects/NeuralLumen/utils/modules.py:106-109.
 // Elementwise, one thread per sample; HBM-bandwidth bound (~(1+taps)*4 B in, ~220 B out per sample).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -24,7 +26,8 @@ __global__ void __launch_bounds__(256) geometry_fwd_kernel(float* __restrict__ s
                                                            const float* __restrict__ dists, int64_t ld_d,
                                                            float* __restrict__ gradients, float* __restrict__ hessians,
                                                            float* __restrict__ XH, int64_t ldxh, int xh_off,
-                                                           int sdf_is_delta) {
+                                                           int sdf_is_delta, __nv_bfloat16* __restrict__ xh_tcl,
+                                                           int xh_chunks, int xh_chunk0) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const int64_t ray = m / g.N;
@@ -65,24 +68,40 @@ __global__ void __launch_bounds__(256) geometry_fwd_kernel(float* __restrict__ s
 #pragma unroll
     for (int a = 0; a < 3; ++a) hessians[m * 3 + a] = hess[a];
   }
-  if (XH) {
+  if (XH || xh_tcl) {
     const float c[3] = {center[ray * 3], center[ray * 3 + 1], center[ray * 3 + 2]};
     const float r[3] = {ray_unit[ray * 3], ray_unit[ray * 3 + 1], ray_unit[ray * 3 + 2]};
     float p[3];
     mli_sample_point(c, r, dists[ray * ld_d + i], 0, 0, 0.0f, p);
     const float nrm = sqrtf(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
     const float den = fmaxf(nrm, 1e-12f);  // F.normalize eps
-    float* row = XH + m * ldxh + xh_off;
-    float sh[16];
+    float row[48];
     row[0] = p[0]; row[1] = p[1]; row[2] = p[2];
-    mli_sh16(r[0], r[1], r[2], sh);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) row[3 + k] = sh[k];
+    mli_sh16(r[0], r[1], r[2], row + 3);
     row[19] = grad[0] / den; row[20] = grad[1] / den; row[21] = grad[2] / den;
-    mli_sh16(pts_light[ray * 3], pts_light[ray * 3 + 1], pts_light[ray * 3 + 2], sh);
+    mli_sh16(pts_light[ray * 3], pts_light[ray * 3 + 1], pts_light[ray * 3 + 2], row + 22);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) row[22 + k] = sh[k];
-    for (int k = xh_off + 38; k < ldxh; ++k) XH[m * ldxh + k] = 0.0f;
+    for (int k = 38; k < 48; ++k) row[k] = 0.0f;
+    if (XH) {
+      float* dst = XH + m * ldxh + xh_off;
+#pragma unroll
+      for (int k = 0; k < 38; ++k) dst[k] = row[k];
+      for (int k = xh_off + 38; k < ldxh; ++k) XH[m * ldxh + k] = 0.0f;
+    }
+    if (xh_tcl) {  // bf16 TCL chunks [xh_chunk0, xh_chunk0 + 6) of the head-input matrix: 16 B per thread and chunk
+      const int64_t tile = m >> 7;
+      const int rl = (int)(m & 127);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(row[j * 8 + 2 * q], row[j * 8 + 2 * q + 1]);
+          w[q] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(xh_tcl + ((tile * xh_chunks + xh_chunk0 + j) * 128 + rl) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
   }
 }
 
@@ -153,15 +172,18 @@ int make_const(GeoConst* g, int32_t N, int32_t taps, double tap_eps, float outsi
 extern "C" int mli_geometry_fwd(float* sdf, int64_t M, int32_t N, int32_t taps, double tap_eps, const uint8_t* outside,
                                 float outside_val, const float* center, const float* ray_unit, const float* pts_light,
                                 const float* dists, int64_t ld_d, float* gradients, float* hessians, float* XH,
-                                int64_t ldxh, int32_t xh_off, int32_t sdf_is_delta, void* stream) {
+                                int64_t ldxh, int32_t xh_off, int32_t sdf_is_delta, void* xh_tcl, int32_t xh_chunks,
+                                int32_t xh_chunk0, void* stream) {
   MLI_ENTRY();
   GeoConst g;
   if (int e = make_const(&g, N, taps, tap_eps, outside_val)) return e;
   MLI_REQUIRE(M >= 0 && M % N == 0, "geometry: M must be a multiple of N");
   MLI_REQUIRE(XH == nullptr || ldxh >= xh_off + 38, "geometry: XH row too short");
+  MLI_REQUIRE(xh_tcl == nullptr || (xh_chunk0 >= 0 && xh_chunk0 + 6 <= xh_chunks && M % 128 == 0), "geometry: bad TCL chunk range");
   if (M == 0) return MLI_OK;
   geometry_fwd_kernel<<<mli_cdiv(M, 256), 256, 0, (cudaStream_t)stream>>>(sdf, M, g, outside, center, ray_unit, pts_light,
-                                                                         dists, ld_d, gradients, hessians, XH, ldxh, xh_off, sdf_is_delta);
+                                                                         dists, ld_d, gradients, hessians, XH, ldxh, xh_off, sdf_is_delta,
+                                                                         (__nv_bfloat16*)xh_tcl, xh_chunks, xh_chunk0);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

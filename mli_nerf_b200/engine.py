@@ -122,10 +122,30 @@ class RenderEngine:
         # multi-GPU overlap: called as hook(table_grad_flat, start_elem, end_elem) right after the scatter kernel of a
         # level group has been launched (that slab of the hash-table gradient is final once the kernel completes)
         self.table_grad_hook = None
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._tg_early = None
 
     # ------------------------------------------------------------------------------------------------------
     def n_table_params(self):
         return int(self.grid.n_entries) * self.cfg.feat_per_level
+
+    def start_table_grad_zero(self):
+        """Zero-fill of the 1.46 GB hash-table gradient buffer, issued on a side stream so that it overlaps the
+        latency-bound sampling rounds of the forward pass instead of sitting in front of the scatter kernel.  The fused
+        train step calls this before sampling; backward() picks the buffer up (and falls back to a plain zero-fill)."""
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            tg = torch.zeros(self.n_table_params(), dtype=torch.float32, device=self.device)
+        tg.record_stream(cur)
+        self._tg_early = tg
+
+    def _take_table_grad(self):
+        if self._tg_early is not None:
+            tg, self._tg_early = self._tg_early, None
+            torch.cuda.current_stream().wait_stream(self._side)
+            return tg
+        return self._z(self.n_table_params())
 
     def level_groups(self):
         """Level ranges launched separately by the table-gradient scatter: the small dense levels together, then one
@@ -439,7 +459,7 @@ class RenderEngine:
             call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
                  prec)
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
-                 pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF, 0)
+                 pts_light, dists, N, gradients, hessians, XH, KH_PAD, XH_OFF, 0, None, 0, 0)
             A = [self._f(M, nh * HID) for _ in range(4)]
             call("mli_linear_fwd", XH, KH_PAD, 0, W["Wh0"], KH_PAD, 0, W["bh"][0], 0, A[0], nh * HID, 0, M, nh * HID,
                  KH_PAD, ACT_RELU, 1, prec)
@@ -454,18 +474,23 @@ class RenderEngine:
             XH = self._tcl(M, KH_PAD // 8)
             self._tc_linear(H0c, 0, 0, T["W1"], 0, HID, HID, 256, W["b1"], 0, None, 0, 0, ACT_SOFTPLUS100, XH, False, 0, 0,
                             0, M, 1, 0)
-            XHx = self._f(M, KH_PAD - XH_OFF)
+            # gradients / Hessians + the non-feature head inputs, written straight into XH's last 6 TCL chunks
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
-                 pts_light, dists, N, gradients, hessians, XHx, KH_PAD - XH_OFF, 0, 1)
-            self._to_tcl(XHx, KH_PAD - XH_OFF, M, KH_PAD - XH_OFF, XH, 128, XH_OFF // 8)
+                 pts_light, dists, N, gradients, hessians, None, 0, 0, 1, XH, KH_PAD // 8, XH_OFF // 8)
             A = [self._tcl(M, nh * 32) for _ in range(4)]
             self._tc_linear(XH, 0, 0, T["Wh0"], 0, KH_PAD, nh * HID, 256, W["bh"][0], 0, None, 0, 0, ACT_RELU, A[0], False,
                             0, 0, 0, M, 1, 0)
-            for l in range(3):
+            for l in range(2):
                 self._tc_linear(A[l], 0, 32, T["Whl"][l], HID * HID, HID, HID, 256, W["bh"][l + 1], HID, None, 0, 0,
                                 ACT_RELU, A[l + 1], False, 0, 32, 0, M, nh, 0)
-            call("mli_tc_rowdot_fwd", A[3], nh * 32, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
-                 self.act_mask, S, 8)
+            # last hidden layer with the 256 -> 3/3/1 output layers + sigmoid fused into its epilogue
+            j0s, njs, j = [], [], 0
+            for h in self.heads:
+                j0s.append(j)
+                njs.append(h[2])
+                j += h[2]
+            call("mli_tc_linear_dot", A[2], nh * 32, 0, 32, T["Whl"][2], HID * HID, HID, W["bh"][3], HID, A[3], nh * 32, 0,
+                 32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, 8)
         ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
                                  min(progress / cfg.anneal_end, 1.0))
         weights, out = self._f(R, N), self._f(R, self.n_out)
@@ -677,7 +702,7 @@ class RenderEngine:
                 call("mli_linear_dgrad", dZ0, HID, 0, W["W0t"], HID, 0, None, 0, 0, dX0, 128, 0, P * M, HID, 128, ACT_NONE,
                      0, 1, prec)
         if "table" in need:
-            tg = self._z(self.n_table_params())
+            tg = self._take_table_grad()
             if self.tc:
                 groups = self.level_groups() if self.table_grad_hook is not None else \
                     [(0, cfg.n_levels, 0, self.n_table_params())]  # one launch when nobody waits for single slabs

@@ -340,6 +340,8 @@ class Model(torch.nn.Module):
         if self.cfg_render.stratified:
             rands = torch.rand(B, R, self.path_cfg.coarse, 1, device=c.device).view(B * R, self.path_cfg.coarse)
         eng.pack_weights(p)
+        if p["neural_sdf.tcnn_encoding.params"].requires_grad:
+            eng.start_table_grad_zero()  # side stream: hidden behind the sampling rounds
         near, far, outside = eng.bounds(c, r)
         dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], c, r, near, far, rands)
         res, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, self.progress)
