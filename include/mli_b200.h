@@ -40,6 +40,10 @@ const char* mli_last_error(void);
 int mli_abi_version(void);
 /* 1 if the current device is compute capability 10.x, else 0 (never errors) */
 int mli_device_ok(void);
+/* Number of SMs the persistent tensor-core kernels (one CTA per SM, all of its shared memory) may occupy, default 148.
+ * A multi-GPU step lowers it so that the NCCL kernels of the overlapped gradient all-reduce find free SMs instead of
+ * queueing behind every persistent CTA.  The workspace size helpers follow the current limit. */
+int mli_set_sm_limit(int32_t n_sms);
 
 /* ------------------------------------------------------------------------------------------------------
  * Hash grid (replaces tcnn.Encoding HashGrid; modules.py:42-50, 84-86)

@@ -90,7 +90,8 @@ def _parse_header(path=HEADER_PATH):
     return sigs
 
 
-_SIGS = {k: v for k, v in _parse_header().items() if k not in ("mli_abi_version", "mli_device_ok", "mli_grid_init")}
+_SIGS = {k: v for k, v in _parse_header().items() if k not in ("mli_abi_version", "mli_device_ok", "mli_grid_init",
+                                                                "mli_set_sm_limit")}
 _CTYPE = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "d": C.c_double, "u": C.c_uint32,
           "s": C.c_void_p, "h": C.c_void_p, "H": C.c_void_p}
 
@@ -112,6 +113,8 @@ def load():
     lib.mli_last_error.restype = C.c_char_p
     lib.mli_abi_version.restype = C.c_int
     lib.mli_device_ok.restype = C.c_int
+    lib.mli_set_sm_limit.argtypes = [C.c_int32]
+    lib.mli_set_sm_limit.restype = C.c_int
     lib.mli_grid_init.argtypes = [C.POINTER(Grid), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
     lib.mli_grid_init.restype = C.c_int
     for name, sig in _SIGS.items():
@@ -255,3 +258,9 @@ def make_grid(n_levels, feat, log2_hashmap_size, base_resolution, per_level_scal
 
 def device_ok():
     return bool(load().mli_device_ok())
+
+
+def set_sm_limit(n_sms):
+    code = load().mli_set_sm_limit(int(n_sms))
+    if code != 0:
+        _raise(code, "mli_set_sm_limit")

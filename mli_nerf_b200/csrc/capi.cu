@@ -14,6 +14,14 @@ void mli_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mli_last_error(void) { return g_err; }
+
+static int g_sm_limit = MLI_NUM_SMS;
+int mli_sm_limit() { return g_sm_limit; }
+extern "C" int mli_set_sm_limit(int32_t n_sms) {
+  MLI_REQUIRE(n_sms >= 8 && n_sms <= MLI_NUM_SMS, "sm limit must be in [8, %d]", MLI_NUM_SMS);
+  g_sm_limit = n_sms;
+  return MLI_OK;
+}
 extern "C" int mli_abi_version(void) { return MLI_ABI_VERSION; }
 
 extern "C" int mli_device_ok(void) {

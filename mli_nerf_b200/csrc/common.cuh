@@ -38,6 +38,9 @@ int mli_check_device();
 static inline unsigned mli_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 #define MLI_NUM_SMS 148
+// SMs the persistent (one CTA per SM, full shared memory) kernels may occupy; the rest stay free for concurrently
+// running communication kernels (mli_set_sm_limit, capi.cu)
+int mli_sm_limit();
 
 // block-wide sum of one float (blockDim.x multiple of 32, <= 1024); result valid in thread 0
 __device__ __forceinline__ float mli_block_sum(float v, float* smem32) {

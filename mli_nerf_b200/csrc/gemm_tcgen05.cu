@@ -1088,7 +1088,7 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ part, int S, int 
 // splits of the contraction dimension: the TN kernel's shared-memory stages allow one CTA per SM, so aim for exactly
 // one wave (300 CTAs on 148 SMs ran as 2.03 waves before)
 int tn_splits(int n_row_tiles, int out_tiles) {
-  int s = MLI_NUM_SMS / out_tiles;
+  int s = mli_sm_limit() / out_tiles;
   if (s > n_row_tiles) s = n_row_tiles;
   if (s > 74) s = 74;
   return s < 1 ? 1 : s;
@@ -1191,7 +1191,7 @@ int launch_nt(const TcNT& p, int N, int batch, cudaStream_t st) {
   if (n_stages >= 3) {  // persistent weight-stationary kernel
     const int n_tiles_n = N / BN, groups = n_tiles_n * batch;
     const int n_row_tiles = (int)mli_cdiv(p.M, kTileM);
-    int per_group = MLI_NUM_SMS / groups;
+    int per_group = mli_sm_limit() / groups;
     if (per_group < 1) per_group = 1;
     if (per_group > n_row_tiles) per_group = n_row_tiles;
     dim3 pgrid(per_group, groups);
@@ -1343,7 +1343,7 @@ extern "C" int mli_tc_sdf_trunk_fused(const void* X, int32_t x_chunks, int32_t K
   MLI_REQUIRE(smem + 3584 <= 232448, "tc_sdf_trunk_fused: weight tile does not fit in shared memory");
   if (int e = set_smem((const void*)tc_sdf_trunk_fused_kernel, smem)) return e;
   int grid = (int)(M / kTileM);
-  if (grid > MLI_NUM_SMS) grid = MLI_NUM_SMS;
+  if (grid > mli_sm_limit()) grid = mli_sm_limit();
   tc_sdf_trunk_fused_kernel<<<grid, kP_Threads, smem, (cudaStream_t)stream>>>(p);
   MLI_LAUNCH_OK();
   return MLI_OK;

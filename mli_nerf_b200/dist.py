@@ -12,13 +12,14 @@ import torch.distributed as dist
 
 
 class GradReducer:
-    def __init__(self, model, world_size=None, level_slices=None, side_stream=True):
+    def __init__(self, model, world_size=None, level_slices=None, side_stream=True, comm_sms=16):
+        self.comm_sms = comm_sms
         self.model = model
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.level_slices = level_slices  # [(start, end)] element ranges of the hash table per level (optional)
         self.stream = None
         if side_stream and torch.cuda.is_available():
-            self.stream = torch.cuda.Stream()
+            self.stream = torch.cuda.Stream(priority=-1)  # communication kernels go first when SMs free up
         self._early = {}  # data_ptr of gradients whose slabs were already reduced through the engine hook
 
     # -- overlap of the hash-table gradient exchange with the rest of the backward pass ------------------------------
@@ -27,6 +28,11 @@ class GradReducer:
         been launched: the all-reduce of that slab then runs on the side stream (NCCL over NVLink) while the compute
         stream continues with the next level group and the deferred weight-gradient GEMMs."""
         engine.table_grad_hook = self._on_table_slab if self.world > 1 else None
+        if self.world > 1 and torch.cuda.is_available():
+            from . import _lib
+            # leave SMs for the NCCL kernels: a persistent GEMM CTA owns its SM's whole shared memory, so without
+            # this the all-reduce only advances in the gaps between kernels
+            _lib.set_sm_limit(148 - self.comm_sms)
 
     def _avg(self, t):
         if dist.get_backend() == "nccl":

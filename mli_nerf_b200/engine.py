@@ -147,24 +147,26 @@ class RenderEngine:
             return tg
         return self._z(self.n_table_params())
 
-    def level_groups(self):
-        """Level ranges launched separately by the table-gradient scatter: the small dense levels together, then one
-        (128 MB at T = 2^22) hashed level at a time.  -> [(level_begin, level_end, elem_begin, elem_end)]"""
+    def level_groups(self, max_groups=4):
+        """Level ranges launched separately by the table-gradient scatter when a multi-GPU hook wants the slabs early.
+        NCCL's all-reduce is markedly more efficient on large messages (measured at N = 2: 2.6 ms for the whole 1.46 GB,
+        3.3 ms in 11 slabs), so the levels are grouped into at most `max_groups` slabs of similar size.
+        -> [(level_begin, level_end, elem_begin, elem_end)]"""
         F, lv = self.cfg.feat_per_level, self.grid.level
         n = self.cfg.n_levels
-        first = 0
-        while first < n and not lv[first].hashed:
-            first += 1
-        bounds = ([0, first] if first > 0 else [0]) + list(range(first + 1, n + 1))
+        total = int(self.grid.n_entries)
+        target = total / max_groups
+        bounds, acc = [0], 0
+        for l in range(n):
+            acc += int(lv[l].size)
+            if acc >= target * len(bounds) and l + 1 < n and len(bounds) < max_groups:
+                bounds.append(l + 1)
+        bounds.append(n)
         out = []
         for a, b in zip(bounds[:-1], bounds[1:]):
-            end = (lv[b].offset if b < n else int(self.grid.n_entries)) * F
+            end = (int(lv[b].offset) if b < n else total) * F
             out.append((a, b, int(lv[a].offset) * F, int(end)))
         return out
-
-    def set_active_levels(self, active):
-        self.active_levels = int(active)
-        self.grid.active_levels = int(active) if self.cfg.c2f_enabled else self.cfg.n_levels
 
     def _f(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
