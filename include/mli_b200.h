@@ -392,6 +392,22 @@ int mli_losses_fwd_bwd(const mli_loss_cfg_t* cfg, int32_t mode, const float* out
 /* ------------------------------------------------------------------------------------------------------
  * "Next" rows
  * ---------------------------------------------------------------------------------------------------- */
+/* Light visibility by sphere tracing (NeuralLumen/model.py:133-200; neuralangelo/model.py:298-325), the stage-a export.
+ * The SDF values of each marching iteration come from the sampling-path kernels (mli_encode_rays[_tcl] with one
+ * sample per ray at distance dist[r] + the SDF trunk); these entry points are the per-ray state around them.
+ *   step:   dist[mask] += sdf[mask]; mask[dist > far] = 0; mask[dist < near] = 0; last != 0: dist = clamp(dist, near, far)
+ *   rays:   intersection point center + ray_unit*inter_dist -> unit light ray from pts_light, its marching interval
+ *           [near_light, far_tracing = |light ray| - 1e-3] inside the visibility bound (sphere of `radius`, or the
+ *           box host_aabb6 when not NULL) and inside_bounding = near < far_tracing < far & ~outside
+ *   finish: visibility = ~mask_light | ~inside_bounding; normal_x_light = relu(normalize(-gradient) . light_unit) */
+int mli_sphere_trace_step(float* dist, uint8_t* mask, const float* sdf, const float* near, const float* far, int64_t R,
+                          int32_t last, void* stream);
+int mli_light_rays(const float* center, const float* ray_unit, const float* inter_dist, const float* pts_light, int64_t R,
+                   float radius, const float* host_aabb6, float* light_unit, float* near_light, float* far_tracing,
+                   uint8_t* inside_bounding, void* stream);
+int mli_light_finish(const uint8_t* mask_light, const uint8_t* inside_bounding, const float* gradient,
+                     const float* light_unit, int64_t R, uint8_t* visibility, float* normal_x_light, void* stream);
+
 /* dense AdamW step (torch.optim.AdamW semantics, get_trainer.py:106-150) fused with gradient scaling (1/world). */
 int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,

@@ -168,6 +168,10 @@ class RenderEngine:
             out.append((a, b, int(lv[a].offset) * F, int(end)))
         return out
 
+    def set_active_levels(self, active):
+        self.active_levels = int(active)
+        self.grid.active_levels = int(active) if self.cfg.c2f_enabled else self.cfg.n_levels
+
     def _f(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
@@ -421,6 +425,39 @@ class RenderEngine:
                 call("mli_sample_merge", dists, None, N, R, n, fine, None, cfg.fine)
             n += cfg.fine
         return dists
+
+    # ------------------------------------------------------------------------------------------------------
+    def sphere_trace(self, table, center, ray_unit, near, far, dist_start=None, iters=20):
+        """Model.sphere_tracing_intersection (neuralangelo/model.py:298-325): [R] tensors -> (dist, mask uint8)."""
+        R = center.shape[0]
+        dist = (dist_start if dist_start is not None else near).clone().contiguous()
+        mask = torch.ones(R, dtype=torch.uint8, device=self.device)
+        for it in range(iters):
+            sdf = self.sdf_query(table, center, ray_unit, dist.view(R, 1), 1, 1)
+            call("mli_sphere_trace_step", dist, mask, sdf, near, far, R, int(it == iters - 1))
+        return dist, mask
+
+    def light_visibility(self, table, center, ray_unit, pts_light, near, far, blend_dist, gradient, camera_ray_type,
+                         radius, aabb=None):
+        """Model.get_light_visibility with type 'sphere_tracing' (NeuralLumen/model.py:133-184), eval mode.
+        -> visibility uint8 [R], normal_x_light [R], inter_dist [R], inter_mask uint8 [R]"""
+        R = center.shape[0]
+        if camera_ray_type == "blend_z_sphere_tracing":
+            inter_dist, inter_mask = self.sphere_trace(table, center, ray_unit, near, far, dist_start=blend_dist)
+        elif camera_ray_type == "blend_z":
+            inter_dist, inter_mask = blend_dist.contiguous(), (blend_dist > 0.0).to(torch.uint8)
+        elif camera_ray_type == "sphere_tracing":
+            inter_dist, inter_mask = self.sphere_trace(table, center, ray_unit, near, far)
+        else:
+            raise NotImplementedError(f"camera_ray_type {camera_ray_type}")
+        light_unit, near_l, far_tr = self._f(R, 3), self._f(R), self._f(R)
+        inside = torch.empty(R, dtype=torch.uint8, device=self.device)
+        call("mli_light_rays", center, ray_unit, inter_dist, pts_light, R, float(radius), aabb, light_unit, near_l, far_tr,
+             inside)
+        _, mask_l = self.sphere_trace(table, pts_light, light_unit, near_l, far_tr)
+        vis, nxl = torch.empty(R, dtype=torch.uint8, device=self.device), self._f(R)
+        call("mli_light_finish", mask_l, inside, gradient.contiguous(), light_unit, R, vis, nxl)
+        return vis, nxl, inter_dist, inter_mask
 
     # ------------------------------------------------------------------------------------------------------
     def forward(self, p, center, ray_unit, pts_light, dists, near, far, outside, training, progress, keep_dz=True):

@@ -205,8 +205,19 @@ class Model(torch.nn.Module):
         self.rand_rays_val = getattr(cfg_model.render, "rand_rays_val", cfg_model.render.rand_rays)
         lv = getattr(cfg_model, "light_visibility", None)
         self.flag_light_visibility = bool(lv is not None and lv.enabled)
-        if self.flag_light_visibility:
-            raise NotImplementedError("light_visibility (stage-a export) is a SURVEY section 8f 'next' row")
+        self.flag_gamma_correlation = False
+        if self.flag_light_visibility:  # NeuralLumen/model.py:25-35
+            self.para_light_visibility = lv
+            if lv.type != "sphere_tracing":
+                raise NotImplementedError("light_visibility.type 'render_light_visibility' reads an attribute the reference "
+                                          "never defines (model.py:217); only 'sphere_tracing' is usable")
+            if lv.visibility_bounding_type == "box":
+                self.visibility_bounding_box_aabb = torch.tensor(lv.visibility_bounding_box_aabb)
+            elif lv.visibility_bounding_type != "sphere":
+                raise NotImplementedError
+            if hasattr(lv, "gamma_correlation"):
+                self.flag_gamma_correlation = True
+                self.gamma_for_shading = lv.gamma_correlation
         hg = sdf_cfg.encoding.hashgrid
         ns = cfg_model.render.num_samples
         self.path_cfg = PathCfg(
@@ -292,6 +303,26 @@ class Model(torch.nn.Module):
             res["opacity"] = extras[:, 0:1].view(B, R, 1)
             res["gradient"] = extras[:, 1:4].view(B, R, 3)
             res["_dist"] = extras[:, 4:5].view(B, R, 1)
+        if self.flag_light_visibility:  # NeuralLumen/model.py:325-334 (the stage-a export of pseudo shading labels)
+            if self.training:
+                raise NotImplementedError("light_visibility is built for the eval / export path (test_all_light)")
+            lv, eng = self.para_light_visibility, self.engine
+            with torch.no_grad():
+                near, far, _ = eng.bounds(c, r)
+                aabb = None
+                if lv.visibility_bounding_type == "box":
+                    aabb = [float(v) for v in self.visibility_bounding_box_aabb]
+                vis, nxl, inter_dist, inter_mask = eng.light_visibility(
+                    dict(zip(names, params))["neural_sdf.tcnn_encoding.params"], c, r, l, near, far,
+                    extras[:, 4].contiguous(), extras[:, 1:4].contiguous(), lv.camera_ray_type,
+                    getattr(lv, "visibility_sphere_radius", 1.0), aabb)
+            res["visibility"] = vis.view(B, R, 1).bool()
+            res["normal_x_light"] = nxl.view(B, R, 1)
+            res["pseudo_shading"] = res["normal_x_light"] * res["visibility"].float()
+            res["inter_dist"] = inter_dist.view(B, R, 1)
+            res["inter_mask"] = inter_mask.view(B, R, 1).bool()
+            if self.flag_gamma_correlation:
+                res["pseudo_shading"] = torch.pow(res["pseudo_shading"], 1.0 / self.gamma_for_shading)
         return res
 
     @torch.no_grad()
@@ -425,4 +456,7 @@ class Model(torch.nn.Module):
         for key in ("o_r", "o_s", "o_re"):
             if key in output:
                 output[key + "_map"] = to_img(output[key])
+        if self.flag_light_visibility:  # NeuralLumen/model.py:78-83
+            for key in ("visibility", "normal_x_light", "pseudo_shading", "inter_dist", "inter_mask"):
+                output[key + "_map"] = to_img(output[key]).float()
         return output

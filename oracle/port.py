@@ -399,6 +399,56 @@ def render_rays(p, cfg, center, ray_unit, pts_light, rands=None, training=True, 
 # ----------------------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------------------
+def sphere_tracing_intersection(p, cfg, center, ray_unit, near, far, num_iters=20, dist_start=None):
+    """Model.sphere_tracing_intersection (projects/neuralangelo/model.py:298-325)."""
+    dist = dist_start.clone() if dist_start is not None else near.clone()
+    mask = torch.ones_like(dist, dtype=torch.bool)
+    for _ in range(num_iters):
+        pts = center + ray_unit * dist
+        sdfs = sdf_only(p, cfg, pts)
+        dist[mask] += sdfs[mask]
+        mask[dist > far] = False
+        mask[dist < near] = False
+    dist = torch.clamp(dist, near, far)
+    return dist, center + ray_unit * dist, mask
+
+
+def light_visibility(p, cfg, center, ray_unit, pts_light, near, far, blend_dist, gradient,
+                     camera_ray_type="blend_z_sphere_tracing", radius=0.95):
+    """Model.get_light_visibility with type 'sphere_tracing' and a sphere visibility bound
+    (projects/NeuralLumen/model.py:133-200).  blend_dist = composite(dists, weights), gradient = composited gradient.
+    -> visibility (bool), normal_x_light, inter_dist, inter_mask   (all [B,R,1])"""
+    if camera_ray_type == "blend_z_sphere_tracing":
+        inter_dist, inter_pts, inter_mask = sphere_tracing_intersection(p, cfg, center, ray_unit, near, far,
+                                                                        dist_start=blend_dist)
+    elif camera_ray_type == "blend_z":
+        inter_dist = blend_dist
+        inter_pts = center + ray_unit * inter_dist
+        inter_mask = inter_dist > 0.0
+    elif camera_ray_type == "sphere_tracing":
+        inter_dist, inter_pts, inter_mask = sphere_tracing_intersection(p, cfg, center, ray_unit, near, far)
+    else:
+        raise NotImplementedError
+    light_ray = inter_pts - pts_light
+    light_ray_unit = F.normalize(light_ray, dim=-1)
+    # get_dist_bounds_visibility, sphere branch (model.py:192-197)
+    ctc = (pts_light * pts_light).sum(dim=-1, keepdim=True)
+    ctv = (pts_light * light_ray_unit).sum(dim=-1, keepdim=True)
+    disc = ctv ** 2 - (ctc - radius ** 2)
+    near_l = (-ctv - disc.sqrt()).relu()
+    far_l = -ctv + disc.sqrt()
+    outside_l = near_l.isnan()
+    near_l = torch.where(outside_l, torch.ones_like(near_l), near_l)
+    far_l = torch.where(outside_l, torch.full_like(far_l, 1.2), far_l)
+    far_tracing = light_ray.norm(dim=-1, keepdim=True) - 1e-3
+    inside_bounding = (near_l < far_tracing) & (far_tracing < far_l) & ~outside_l
+    _, _, mask_light = sphere_tracing_intersection(p, cfg, pts_light, light_ray_unit, near_l, far_tracing)
+    visibility = ~mask_light | ~inside_bounding
+    normal_ray_unit = F.normalize(-gradient, dim=-1)
+    normal_x_light = (normal_ray_unit * light_ray_unit).sum(dim=-1, keepdim=True).relu()
+    return visibility, normal_x_light, inter_dist, inter_mask
+
+
 def eikonal_loss(gradients, outside):
     """projects/neuralangelo/utils/misc.py:74-80."""
     err = ((gradients.norm(dim=-1) - 1.0) ** 2).nan_to_num(nan=0.0, posinf=0.0, neginf=0.0)

@@ -478,3 +478,64 @@ def test_model_sdf_sweep_matches_oracle(lib):
         got = model.cuda().eval().sdf(pts.cuda()).cpu()
         assert got.shape == ref.shape
         assert torch.allclose(got, ref, rtol=1e-3, atol=tol), (prec, float((got - ref).abs().max()))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_light_visibility_sphere_tracing_vs_oracle(lib, prec):
+    """get_light_visibility (blend_z_sphere_tracing + sphere_tracing, sphere bound r = 0.95), the
+    stage-a export of pseudo shading labels, against the oracle's restatement of the reference loop."""
+    from mli_nerf_b200.engine import RenderEngine
+    case = make_case(R=256, progress=1.0, miss_rays=8)
+    ocfg = case["ocfg"]
+    # the reference's own (geometric) init: sphere tracing d <- d + sdf(d) is a fixed-point iteration that only settles
+    # when |grad sdf| ~ 1; on the noisy "generic" parameter set it is chaotic and amplifies 1e-6 differences
+    params = port.init_params(ocfg, seed=0, generic=False, table_scale=1e-4)
+    with torch.no_grad():
+        ref = port.render_rays(params, ocfg, case["center"], case["ray_unit"], case["light"], rands=None, training=False,
+                               progress=1.0, keep=True)
+        near, far, _ = port.dist_bounds(ocfg, case["center"], case["ray_unit"])
+        blend = port.composite(ref["dists"], ref["weights"])
+        vis, nxl, idist, imask = port.light_visibility(params, ocfg, case["center"], case["ray_unit"], case["light"], near, far,
+                                                       blend, ref["gradient"], "blend_z_sphere_tracing", 0.95)
+    eng = RenderEngine(product_cfg(ocfg, precision=1 if prec == "bf16" else 0))
+    p = {k: cu(v) for k, v in params.items()}
+    eng.pack_weights(p)
+    c, r, l = cu(case["center"][0]), cu(case["ray_unit"][0]), cu(case["light"][0])
+    g_near, g_far, _ = eng.bounds(c, r)
+    # feed the oracle's blended distance / gradient so that only the tracing itself is compared
+    g_vis, g_nxl, g_idist, g_imask = eng.light_visibility(p["neural_sdf.tcnn_encoding.params"], c, r, l, g_near, g_far,
+                                                          cu(blend[0, :, 0]), cu(ref["gradient"][0]),
+                                                          "blend_z_sphere_tracing", 0.95)
+    tol = 1e-4 if prec == "fp32" else 2e-3
+    ok = (g_idist.cpu() - idist[0, :, 0]).abs() < tol * (1 + idist[0, :, 0].abs())
+    assert float(ok.float().mean()) > 0.98, float(ok.float().mean())
+    assert float((g_imask.cpu().bool() == imask[0, :, 0]).float().mean()) > 0.98
+    assert float((g_vis.cpu().bool() == vis[0, :, 0]).float().mean()) > 0.97
+    nxl_ok = (g_nxl.cpu() - nxl[0, :, 0]).abs() < (1e-3 if prec == "fp32" else 5e-3)
+    assert float(nxl_ok.float().mean()) > 0.98, float(nxl_ok.float().mean())
+
+
+def test_model_inference_with_light_visibility_maps(lib):
+    """inference() of the stage-a export configuration (--model.light_visibility.enabled=True): the extra per-ray outputs
+    and *_map images of NeuralLumen/model.py:78-83,325-334 exist with the reference's shapes / dtypes."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.model import Model
+    cfg = config.experiment("syn_hotdog_a", dict_size=14)
+    cfg.data.val.image_size = [24, 32]
+    cfg.model.render.rand_rays_val = 500
+    cfg.model.light_visibility.enabled = True
+    model = Model(cfg.model, cfg.data).cuda()
+    model.neural_sdf.set_active_levels(10 ** 9)   # stage a: coarse-to-fine fully open
+    model.neural_sdf.set_normal_epsilon()
+    pose = torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[40.0, 0, 16], [0, 40.0, 12], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, -1.0], [0, 1, 0, 2.0], [0, 0, 1, -3.0]]], dtype=torch.float32)  # light at (1,-2,3)
+    out = model.inference(dict(pose=cu(pose), intr=cu(intr), pose_light=cu(pose_light), idx=torch.zeros(1).long()))
+    assert out["visibility"].dtype == torch.bool and out["inter_mask"].dtype == torch.bool
+    for k in ("visibility", "normal_x_light", "pseudo_shading", "inter_dist", "inter_mask"):
+        assert out[k].shape == (1, 24 * 32, 1), k
+        assert out[k + "_map"].shape == (1, 1, 24, 32) and out[k + "_map"].dtype == torch.float32, k
+    assert float(out["normal_x_light"].min()) >= 0.0 and float(out["normal_x_light"].max()) <= 1.0 + 1e-5
+    # geometric init = sphere of radius ~0.5, camera at (0,0,3), light at (1,-2,3): part of the visible cap is lit
+    ps = out["pseudo_shading"]
+    assert float((ps > 0).float().mean()) > 0.01 and bool(torch.isfinite(ps).all())
