@@ -397,11 +397,12 @@ def test_model_inference_outputs(lib):
     assert torch.equal(out["outside"].cpu(), ref["outside"])
 
 
-def test_render_bf16_tensor_core_mode(lib):
+@pytest.mark.parametrize("taps,bounding,white", [(4, "unit_sphere", True), (6, "box", False)])
+def test_render_bf16_tensor_core_mode(lib, taps, bounding, white):
     """bf16 MLP-tile mode (layer 1 + all head layers on tcgen05): the looser, stated bound of the north star.
     Bounds: per-ray colours |err| <= 2e-2 (mean <= 3e-3); parameter gradients: relative L2 error <= 6e-2."""
     from mli_nerf_b200.engine import RenderEngine
-    case = make_case(R=256, progress=0.5)
+    case = make_case(R=256, progress=0.5, taps=taps, bounding=bounding, white=white)
     ocfg, params = case["ocfg"], case["params"]
     pp = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     out_ref = port.render_rays(pp, ocfg, case["center"], case["ray_unit"], case["light"], rands=case["rands"],
@@ -419,8 +420,9 @@ def test_render_bf16_tensor_core_mode(lib):
         err = (out[:, a:b] - out_ref[k][0].detach()).abs()
         assert float(err.max()) < 2e-2 and float(err.mean()) < 3e-3, (k, float(err.max()), float(err.mean()))
     # SDF trunk: split-bf16 operands (3 tcgen05 products, ~16 mantissa bits) + fp32-formed tap deltas.  Stated bounds:
-    # sdf |err| <= 1e-3*|sdf| + 1e-5; numerical gradients: relative L2 error <= 2e-3 over the rays that hit the
-    # bounds; Hessians: mean |err| <= 1.0 (the fp32 reference's own cancellation noise is ~0.35)
+    # sdf |err| <= 1e-3*|sdf| + 1e-5; numerical gradients: relative L2 error <= 5e-4 over the rays that hit the
+    # bounds (measured 2e-5 .. 4e-5); Hessians: mean |err| <= 1.0 (measured 0.26 .. 0.36 on |hess| ~ 2000, i.e. the fp32
+    # reference's own cancellation noise of ~0.35)
     assert torch.allclose(res["sdf"].cpu()[:256 * 128].view(256, 128), out_ref["sdfs"][0, :, :, 0], rtol=1e-3, atol=1e-5)
     inside = ~out_ref["outside"][0, :, 0]
     g_got, g_ref = res["gradients"].cpu().view(256, 128, 3)[inside], out_ref["gradients"][0].detach()[inside]
@@ -428,7 +430,7 @@ def test_render_bf16_tensor_core_mode(lib):
     h_got, h_ref = res["hessians"].cpu().view(256, 128, 3)[inside], out_ref["hessians"][0].detach()[inside]
     h_err = float((h_got - h_ref).abs().mean())
     print(f"bf16 mode: gradient rel L2 err {g_err:.2e}, hessian mean abs err {h_err:.3f} (|hess| mean {float(h_ref.abs().mean()):.1f})")
-    assert g_err < 2e-3, g_err
+    assert g_err < 5e-4, g_err
     assert h_err < 1.0, h_err
     tg = {k: cu(v[0]) for k, v in case["targets"].items()}
     _, d_out, d_grad, d_hess = eng.losses(loss_cfg(ocfg0), res["out"], res["gradients"], res["hessians"], outside, tg)
