@@ -158,13 +158,16 @@ int mli_tc_from_tcl(const void* src, int32_t src_chunks, int32_t chunk0, int32_t
  * A: TCL-128 activations, columns [8*(a_chunk0 + b*a_batch_chunks), +K) for batch member b.
  * B: weights [N, K] in TCL with BN-row tiles ([N/BN][K/8][BN][8]), b_batch_elems elements between batch members.
  * out: bf16 TCL-128 (out_chunks per tile row, first chunk out_chunk0 + b*out_batch_chunks) or, if out_is_f32, fp32
- * row-major (ldo; first column out_col0 + b*out_batch_cols; rows >= M are not written). */
+ * row-major (ldo; first column out_col0 + b*out_batch_cols; rows >= M are not written).
+ * relu_mask (may be NULL; act must be relu): sign bits of the layer output, one uint32 per row and 32-column chunk,
+ * [ceil(M/128)][mask_chunks][128], first chunk mask_chunk0 + b*mask_batch_chunks.  epi 0 WRITES it next to `out`;
+ * epi 1 READS it in place of `aux` (16x fewer bytes than the bf16 output for the same relu'). */
 int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t a_batch_chunks, const void* B,
                   int64_t b_batch_elems, int32_t K, int32_t N, int32_t BN, const float* bias, int32_t bias_batch,
                   const void* aux, int32_t aux_chunks, int32_t aux_chunk0, int32_t aux_batch_chunks, int32_t act,
                   void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
                   int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
-                  void* stream);
+                  void* relu_mask, int32_t mask_chunks, int32_t mask_chunk0, int32_t mask_batch_chunks, void* stream);
 /* relu hidden layer (N = 256 per batch member, as mli_tc_linear epi 0) with the narrow output layer that follows it
  * (nerf_util.py:191, 256 -> 3/3/1) fused into the epilogue: S[m, j] = act_j(w_out[j] . out[m, batch(j) block] + b_out[j])
  * for j in [host_j0[b], host_j0[b] + host_nj[b]) of batch member b (nj <= 4, batch <= 4); the dot uses the fp32 layer
@@ -173,7 +176,8 @@ int mli_tc_linear_dot(const void* A, int32_t a_chunks, int32_t a_chunk0, int32_t
                       int64_t b_batch_elems, int32_t K, const float* bias, int32_t bias_batch, void* out,
                       int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks, int64_t M, int32_t batch,
                       const float* w_out, const float* b_out, const int32_t* host_j0, const int32_t* host_nj,
-                      int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* stream);
+                      int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* relu_mask, int32_t mask_chunks,
+                      int32_t mask_chunk0, int32_t mask_batch_chunks, void* stream);
 
 /* SDF trunk on the tensor cores (replaces MLPforNeuralSDF layer 0 + softplus + linear_sdf, mlp.py:55-69, for every
  * stencil plane; the numerical-gradient taps of modules.py:131-177 go through as fp32-formed deltas).
@@ -224,12 +228,14 @@ int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n
 
 /* Narrow output layers on TCL activations (same maths as mli_rowdot_*): A is TCL-128 with a_chunks chunks per tile row;
  * col_off (host array, multiples of 8, non-decreasing) selects the K-wide column window of each output.
- * bwd_data writes dZ = (dS W) * act_prev'(A) as bf16 TCL with the same geometry as A (all a_chunks chunks). */
+ * bwd_data writes dZ = (dS W) * act_prev'(A) as bf16 TCL with the same geometry as A (all a_chunks chunks); with
+ * act_prev = relu and relu_mask != NULL ([tiles][a_chunks/4][128] uint32 sign bits) A itself is not read. */
 int mli_tc_rowdot_fwd(const void* A, int32_t a_chunks, int64_t M, const float* w, const float* b,
                       const int32_t* host_col_off, int32_t J, int32_t K, int32_t act, uint32_t act_mask, float* out,
                       int64_t ldo, void* stream);
 int mli_tc_rowdot_bwd_data(const float* dS, int64_t lds, const void* A, int32_t a_chunks, int64_t M, const float* w,
-                           const int32_t* host_col_off, int32_t J, int32_t K, int32_t act_prev, void* dZ, void* stream);
+                           const int32_t* host_col_off, int32_t J, int32_t K, int32_t act_prev, void* dZ,
+                           const void* relu_mask, void* stream);
 
 /* Narrow output layers (SDF head 256->1, mlp.py:50,66; head output layers 256->3/3/1, nerf_util.py:191):
  * out[m, j] = act_j(sum_k A[m, col_off[j] + k] * w[j, k] + b[j]),  j < J <= 8, k < K; act_j = act if bit j of

@@ -143,6 +143,9 @@ struct TcNT {
   // EPI_BIAS_ACT_DOT: the narrow output layer that follows this layer, fused into its epilogue.  Batch member b owns
   // outputs [dot_j0[b], dot_j0[b] + dot_nj[b]) (<= 4 each): S[row, j] = act_j(w_out[j] . out_row + b_out[j])
   const float* wdot; const float* bdot; float* S; int64_t lds; int dot_j0[4], dot_nj[4]; int dot_act; uint32_t dot_act_mask;
+  // relu sign bits: one uint32 per row and 32-column chunk, [tile][mask_chunks][128].  Written by the relu forward
+  // epilogues, read by the relu data-gradient epilogue instead of the bf16 layer output (16x fewer aux bytes).
+  uint32_t* mask; int mask_chunks, mask_chunk0, mask_batch_chunks;
 };
 
 // a < b ? x : y as a predicated select: both sides are always evaluated.  Written as `cond ? cheap : MUFU-chain` the
@@ -487,6 +490,17 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
       const uint32_t acc = it & 1;
       const int64_t row = (int64_t)tile_m * kTileM + r_local;
       uint4 auxr[4][4];
+      uint32_t maskr[4] = {0u, 0u, 0u, 0u};
+      if constexpr (EPI == EPI_MUL_DACT && ACT == MLI_ACT_RELU) {
+        if (p.mask) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cc = half + 2 * k;
+            if (cc < n_cc)
+              maskr[k] = __ldg(p.mask + ((int64_t)tile_m * p.mask_chunks + p.mask_chunk0 + (int64_t)batch * p.mask_batch_chunks + (n0 + cc * 32) / 32) * kTileM + r_local);
+          }
+        }
+      }
       if constexpr (EPI == EPI_MUL_DACT) {
         if (has_aux) {  // issue every load of this row before waiting: latency hides behind the tile's MMAs
 #pragma unroll
@@ -526,7 +540,23 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
           }
           const int ncol = min(32, BN - c0);
           if constexpr (!kSdf) {
+            if constexpr (EPI == EPI_MUL_DACT && ACT == MLI_ACT_RELU) {
+              if (p.mask) {  // relu'(layer output) from its sign bits
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ((maskr[k] >> i) & 1u) ? v[i] : 0.0f;
+              }
+            }
             epi_generic_chunk<EPI, ACT, OUT_F32>(p, v, ncol, c0, n0, batch, tile_m, r_local, row, bias, has_aux ? auxr[k] : nullptr);
+            if constexpr ((EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ACT_DOT) && ACT == MLI_ACT_RELU) {
+              if (p.mask) {
+                // v >= +0 after relu, so v > 0 <=> bits(v) + 0x7fffffff carries into the sign bit; a funnel shift moves
+                // that bit into the mask: 2 instructions per element (columns >= ncol hold relu(garbage), never read)
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 31; i >= 0; --i) bits = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, bits, 1);
+                p.mask[((int64_t)tile_m * p.mask_chunks + p.mask_chunk0 + (int64_t)batch * p.mask_batch_chunks + (n0 + c0) / 32) * kTileM + r_local] = bits;
+              }
+            }
             if constexpr (kDot) {  // v[] now holds the activated layer output: feed the fused output layer
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -1226,9 +1256,15 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
                              const void* aux, int32_t aux_chunks, int32_t aux_chunk0, int32_t aux_batch_chunks, int32_t act,
                              void* out, int32_t out_is_f32, int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks,
                              int64_t ldo, int32_t out_col0, int32_t out_batch_cols, int64_t M, int32_t batch, int32_t epi,
+                             void* relu_mask, int32_t mask_chunks, int32_t mask_chunk0, int32_t mask_batch_chunks,
                              void* stream) {
   MLI_ENTRY();
   MLI_REQUIRE(M >= 1 && batch >= 1 && K >= 16 && K % 16 == 0, "tc_linear: K must be a positive multiple of 16");
+  if (relu_mask) {
+    MLI_REQUIRE(act == MLI_ACT_RELU && N % 32 == 0 && BN % 32 == 0, "tc_linear: relu_mask needs relu and N, BN multiples of 32");
+    MLI_REQUIRE(mask_chunk0 >= 0 && mask_chunk0 + (batch - 1) * mask_batch_chunks + N / 32 <= mask_chunks, "tc_linear: mask chunk range");
+    MLI_REQUIRE((size_t)(K / 8) * BN * 16 + 3 * 16384 + 1536 <= 232448, "tc_linear: relu_mask needs the persistent kernel (weight tile must fit in shared memory)");
+  }
   MLI_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "tc_linear: BN multiple of 16 <= 256 dividing N");
   MLI_REQUIRE(a_chunk0 >= 0 && a_chunk0 + (batch - 1) * a_batch_chunks + K / 8 <= a_chunks, "tc_linear: A chunk range");
   MLI_REQUIRE(epi == EPI_BIAS_ACT || epi == EPI_MUL_DACT, "tc_linear: unknown epilogue");
@@ -1246,6 +1282,7 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
   p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks;
   p.ldo = ldo; p.out_col0 = out_col0; p.out_batch_cols = out_batch_cols; p.M = M;
   p.split = 0; p.stage_chunks = kStageChunks;
+  p.mask = (uint32_t*)relu_mask; p.mask_chunks = mask_chunks; p.mask_chunk0 = mask_chunk0; p.mask_batch_chunks = mask_batch_chunks;
   cudaStream_t st = (cudaStream_t)stream;
   const bool f32 = out_is_f32 != 0;
   if (epi == EPI_BIAS_ACT) {
@@ -1256,7 +1293,7 @@ extern "C" int mli_tc_linear(const void* A, int32_t a_chunks, int32_t a_chunk0, 
       default: return launch_nt_f<EPI_BIAS_ACT, MLI_ACT_NONE>(p, N, batch, f32, st);
     }
   }
-  if (aux == nullptr) act = MLI_ACT_NONE;
+  if (aux == nullptr && relu_mask == nullptr) act = MLI_ACT_NONE;
   switch (act) {
     case MLI_ACT_RELU: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_RELU>(p, N, batch, f32, st);
     case MLI_ACT_SOFTPLUS100: return launch_nt_f<EPI_MUL_DACT, MLI_ACT_SOFTPLUS100>(p, N, batch, f32, st);
@@ -1269,8 +1306,10 @@ extern "C" int mli_tc_linear_dot(const void* A, int32_t a_chunks, int32_t a_chun
                                  int64_t b_batch_elems, int32_t K, const float* bias, int32_t bias_batch, void* out,
                                  int32_t out_chunks, int32_t out_chunk0, int32_t out_batch_chunks, int64_t M, int32_t batch,
                                  const float* w_out, const float* b_out, const int32_t* host_j0, const int32_t* host_nj,
-                                 int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* stream) {
+                                 int32_t act_out, uint32_t act_mask, float* S, int64_t lds, void* relu_mask,
+                                 int32_t mask_chunks, int32_t mask_chunk0, int32_t mask_batch_chunks, void* stream) {
   MLI_ENTRY();
+  if (relu_mask) MLI_REQUIRE(mask_chunk0 >= 0 && mask_chunk0 + (batch - 1) * mask_batch_chunks + 8 <= mask_chunks, "tc_linear_dot: mask chunk range");
   MLI_REQUIRE(M >= 1 && batch >= 1 && batch <= 4 && K >= 16 && K % 16 == 0, "tc_linear_dot: bad M/batch/K");
   MLI_REQUIRE(a_chunk0 >= 0 && a_chunk0 + (batch - 1) * a_batch_chunks + K / 8 <= a_chunks, "tc_linear_dot: A chunk range");
   MLI_REQUIRE(out_chunk0 >= 0 && out_chunk0 + (batch - 1) * out_batch_chunks + 32 <= out_chunks, "tc_linear_dot: out chunk range");
@@ -1284,6 +1323,7 @@ extern "C" int mli_tc_linear_dot(const void* A, int32_t a_chunks, int32_t a_chun
   p.out = out; p.out_chunks = out_chunks; p.out_chunk0 = out_chunk0; p.out_batch_chunks = out_batch_chunks; p.M = M;
   p.split = 0; p.stage_chunks = kStageChunks;
   p.wdot = w_out; p.bdot = b_out; p.S = S; p.lds = lds; p.dot_act = act_out; p.dot_act_mask = act_mask;
+  p.mask = (uint32_t*)relu_mask; p.mask_chunks = mask_chunks; p.mask_chunk0 = mask_chunk0; p.mask_batch_chunks = mask_batch_chunks;
   for (int b = 0; b < 4; ++b) {
     p.dot_j0[b] = b < batch ? host_j0[b] : 0;
     p.dot_nj[b] = b < batch ? host_nj[b] : 0;

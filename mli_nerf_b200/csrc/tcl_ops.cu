@@ -79,7 +79,8 @@ constexpr int kBwdChunksPerCta = 32;
 __global__ void __launch_bounds__(kTile) rowdot_tcl_bwd_kernel(const float* __restrict__ dS, int64_t lds,
                                                                const __nv_bfloat16* __restrict__ A, int a_chunks, int64_t M,
                                                                const float* __restrict__ w, RdArgs a, int act_prev,
-                                                               __nv_bfloat16* __restrict__ dZ) {
+                                                               __nv_bfloat16* __restrict__ dZ,
+                                                               const uint32_t* __restrict__ relu_mask) {
   extern __shared__ float sw[];  // [J][K]
   for (int i = threadIdx.x; i < a.J * a.K; i += kTile) sw[i] = w[i];
   __syncthreads();
@@ -103,7 +104,11 @@ __global__ void __launch_bounds__(kTile) rowdot_tcl_bwd_kernel(const float* __re
         for (int i = 0; i < 8; ++i) v[i] = fmaf(d[j], ww[i], v[i]);
       }
     }
-    if (act_prev != MLI_ACT_NONE) {
+    if (act_prev == MLI_ACT_RELU && relu_mask) {  // sign bits instead of the bf16 activations
+      const uint32_t bits = __ldg(relu_mask + ((tile * (a_chunks / 4) + (c >> 2)) * kTile + threadIdx.x)) >> ((c & 3) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.0f;
+    } else if (act_prev != MLI_ACT_NONE) {
       float y[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(A + idx)), y);
       if (act_prev == MLI_ACT_RELU) {
@@ -148,15 +153,16 @@ extern "C" int mli_tc_rowdot_fwd(const void* A, int32_t a_chunks, int64_t M, con
 
 extern "C" int mli_tc_rowdot_bwd_data(const float* dS, int64_t lds, const void* A, int32_t a_chunks, int64_t M,
                                       const float* w, const int32_t* host_col_off, int32_t J, int32_t K, int32_t act_prev,
-                                      void* dZ, void* stream) {
+                                      void* dZ, const void* relu_mask, void* stream) {
   MLI_ENTRY();
   RdArgs a;
   if (int e = make_args(&a, host_col_off, J, K)) return e;
   MLI_REQUIRE(lds >= J, "rowdot_tcl: lds < J");
+  MLI_REQUIRE(relu_mask == nullptr || a_chunks % 4 == 0, "rowdot_tcl: relu_mask needs a_chunks % 4 == 0");
   if (M <= 0) return MLI_OK;
   dim3 grid(mli_cdiv(M, kTile), mli_cdiv(a_chunks, kBwdChunksPerCta));
   rowdot_tcl_bwd_kernel<<<grid, kTile, (size_t)J * K * sizeof(float), (cudaStream_t)stream>>>(
-      dS, lds, (const __nv_bfloat16*)A, a_chunks, M, w, a, act_prev, (__nv_bfloat16*)dZ);
+      dS, lds, (const __nv_bfloat16*)A, a_chunks, M, w, a, act_prev, (__nv_bfloat16*)dZ, (const uint32_t*)relu_mask);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

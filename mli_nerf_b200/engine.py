@@ -358,10 +358,16 @@ class RenderEngine:
         return out
     # ---- tensor-core (bf16 TCL) building blocks -------------------------------------------------------------------
     def _tc_linear(self, A, a_chunk0, a_bchunks, B, b_belems, K, N, BN, bias, bias_b, aux, aux_chunk0, aux_bchunks, act,
-                   out, out_f32, out_chunk0, out_bchunks, ldo, M, batch, epi):
+                   out, out_f32, out_chunk0, out_bchunks, ldo, M, batch, epi, mask=None, mask_bchunks=0):
+        """mask: relu sign bits [tiles, chunks32, 128] int32 -- written by a relu forward (epi 0), read instead of `aux`
+        by a relu data gradient (epi 1)."""
         call("mli_tc_linear", A, A.shape[1], a_chunk0, a_bchunks, B, b_belems, K, N, BN, bias, bias_b, aux,
              aux.shape[1] if aux is not None else 0, aux_chunk0, aux_bchunks, act, out, int(out_f32),
-             0 if out_f32 else out.shape[1], out_chunk0, out_bchunks, ldo, 0, 0, M, batch, epi)
+             0 if out_f32 else out.shape[1], out_chunk0, out_bchunks, ldo, 0, 0, M, batch, epi, mask,
+             mask.shape[1] if mask is not None else 0, 0, mask_bchunks)
+
+    def _mask(self, rows, cols):
+        return torch.empty((rows + 127) // 128, cols // 32, 128, dtype=torch.int32, device=self.device)
 
     def _tc_wgrad(self, L, l_chunk0, l_b, R, r_chunk0, r_b, M, rows, cols, batch, out, ldo, bstride, transpose=0,
                   db=None):
@@ -517,11 +523,14 @@ class RenderEngine:
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
                  pts_light, dists, N, gradients, hessians, None, 0, 0, 1, XH, KH_PAD // 8, XH_OFF // 8)
             A = [self._tcl(M, nh * 32) for _ in range(4)]
+            # relu sign bits of every hidden activation (only when a backward pass follows): the data-gradient
+            # epilogues read these 4 bytes per 32 columns instead of the 64-byte bf16 activations
+            Am = [self._mask(M, nh * HID) if keep_dz else None for _ in range(4)]
             self._tc_linear(XH, 0, 0, T["Wh0"], 0, KH_PAD, nh * HID, 256, W["bh"][0], 0, None, 0, 0, ACT_RELU, A[0], False,
-                            0, 0, 0, M, 1, 0)
+                            0, 0, 0, M, 1, 0, mask=Am[0])
             for l in range(2):
                 self._tc_linear(A[l], 0, 32, T["Whl"][l], HID * HID, HID, HID, 256, W["bh"][l + 1], HID, None, 0, 0,
-                                ACT_RELU, A[l + 1], False, 0, 32, 0, M, nh, 0)
+                                ACT_RELU, A[l + 1], False, 0, 32, 0, M, nh, 0, mask=Am[l + 1], mask_bchunks=8)
             # last hidden layer with the 256 -> 3/3/1 output layers + sigmoid fused into its epilogue
             j0s, njs, j = [], [], 0
             for h in self.heads:
@@ -529,14 +538,15 @@ class RenderEngine:
                 njs.append(h[2])
                 j += h[2]
             call("mli_tc_linear_dot", A[2], nh * 32, 0, 32, T["Whl"][2], HID * HID, HID, W["bh"][3], HID, A[3], nh * 32, 0,
-                 32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, 8)
+                 32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, 8, Am[3],
+                 Am[3].shape[1] if Am[3] is not None else 0, 0, 8)
         ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
                                  min(progress / cfg.anneal_end, 1.0))
         weights, out = self._f(R, N), self._f(R, self.n_out)
         extras = self._f(R, 5) if not training else None
         call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, 8, R, None, weights, out,
              extras)
-        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, Xd=Xd, S0=S0, DZ=DZ, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
+        ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, Xd=Xd, S0=S0, DZ=DZ, Am=Am if self.tc else None, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
                    ccfg=ccfg, center=center, ray_unit=ray_unit, dists=dists, far=far, outside=outside)
         res = dict(out=out, weights=weights, gradients=gradients, hessians=hessians, extras=extras, S=S, sdf=sdf)
         return res, ctx
@@ -614,7 +624,8 @@ class RenderEngine:
             # and its exchange overlaps the weight-gradient GEMMs.
             T, XH = W["T"], ctx["XH"]
             dZ = self._tcl(M, nh * 32)
-            call("mli_tc_rowdot_bwd_data", dS, 8, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ)
+            Am = ctx["Am"] if ctx["Am"][0] is not None else [None] * 4
+            call("mli_tc_rowdot_bwd_data", dS, 8, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, Am[3])
             if need_heads:
                 def _out_layer():
                     dSt = self._to_tcl(dS, 8, M, 8, self._tcl(M, 2), 128, 0, 2)
@@ -629,8 +640,9 @@ class RenderEngine:
                     later.append(lambda dZ=dZ, l=l: self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID,
                                                                    HID * HID, db=dbh[l + 1]))
                 dZp = self._tcl(M, nh * 32)
-                self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0, A[l], 0, 32, ACT_RELU, dZp,
-                                False, 0, 32, 0, M, nh, 1)
+                self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0,
+                                A[l] if Am[l] is None else None, 0, 32, ACT_RELU, dZp, False, 0, 32, 0, M, nh, 1,
+                                mask=Am[l], mask_bchunks=8)
                 dZ = dZp
             if need_heads:
                 dbh[0] = self._f(nh * HID)

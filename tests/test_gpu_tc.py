@@ -63,13 +63,13 @@ def test_tc_linear_forward(lib, M, N, K, BN, act, batch):
     # bf16 TCL output
     out = torch.zeros((M + 127) // 128, batch * N // 8, 128, 8, dtype=torch.bfloat16, device="cuda")
     lib.call("mli_tc_linear", A, batch * K // 8, 0, K // 8, Wt, N * K, K, N, BN, b.cuda(), N, None, 0, 0, 0, act, out, 0,
-             batch * N // 8, 0, N // 8, 0, 0, 0, M, batch, 0)
+             batch * N // 8, 0, N // 8, 0, 0, 0, M, batch, 0, None, 0, 0, 0)
     got = from_tcl_host(out.cpu(), M).view(M, batch, N)
     assert torch.allclose(got, ref, rtol=1e-2, atol=1e-2), float((got - ref).abs().max())
     # fp32 row-major output: only fp32 accumulation-order differences remain
     out32 = torch.zeros(M, batch * N, device="cuda")
     lib.call("mli_tc_linear", A, batch * K // 8, 0, K // 8, Wt, N * K, K, N, BN, b.cuda(), N, None, 0, 0, 0, act, out32, 1,
-             0, 0, 0, batch * N, 0, N, M, batch, 0)
+             0, 0, 0, batch * N, 0, N, M, batch, 0, None, 0, 0, 0)
     assert torch.allclose(out32.cpu().view(M, batch, N), ref, rtol=1e-4, atol=1e-4), float((out32.cpu().view(M, batch, N) - ref).abs().max())
 
 
@@ -80,7 +80,7 @@ def test_tc_linear_dgrad_epilogue(lib):
     Yp = torch.randn(M, K_in).abs() * 0.01
     out = torch.zeros(3, K_in // 8, 128, 8, dtype=torch.bfloat16, device="cuda")
     lib.call("mli_tc_linear", to_tcl_host(dZ).cuda(), N_out // 8, 0, 0, to_tcl_host(Wt, 256).cuda(), 0, N_out, K_in, 256, None,
-             0, to_tcl_host(Yp).cuda(), K_in // 8, 0, 0, 2, out, 0, K_in // 8, 0, 0, 0, 0, 0, M, 1, 1)
+             0, to_tcl_host(Yp).cuda(), K_in // 8, 0, 0, 2, out, 0, K_in // 8, 0, 0, 0, 0, 0, M, 1, 1, None, 0, 0, 0)
     y = bf(Yp)
     ref = (bf(dZ) @ bf(Wt).t()) * torch.where(y > 0.2, torch.ones_like(y), -torch.expm1(-100 * y))
     got = from_tcl_host(out.cpu(), M)
@@ -349,3 +349,35 @@ def test_encode_rays_bwd_delta_basis_equals_absolute_basis(lib):
     for lv0, lv1 in ((0, 6), (6, 7), (7, 16)):  # level groups, as the overlapped multi-GPU backward launches them
         lib.call("mli_encode_rays_bwd_tcl", *args, dXt, 16, tg_tcl, lv0, lv1)
     assert float((tg_ref - tg_tcl).abs().max()) < 1e-5 * float(tg_ref.abs().max())
+
+
+def test_relu_sign_mask_roundtrip(lib):
+    """relu forward writes one sign bit per output; the relu data gradient with that mask equals the one that reads the
+    bf16 activations (both batched, as the head layers use them)."""
+    torch.manual_seed(13)
+    M, N, K, batch = 640, 256, 256, 3
+    X = torch.randn(M, batch * K) * 0.5
+    W = torch.randn(batch, N, K) / math.sqrt(K)
+    b = torch.randn(batch, N) * 0.1
+    A = to_tcl_host(X).cuda()
+    Wt = torch.stack([to_tcl_host(W[i], 256) for i in range(batch)]).cuda()
+    out = torch.zeros(M // 128, batch * N // 8, 128, 8, dtype=torch.bfloat16, device="cuda")
+    mask = torch.zeros(M // 128, batch * N // 32, 128, dtype=torch.int32, device="cuda")
+    lib.call("mli_tc_linear", A, batch * K // 8, 0, K // 8, Wt, N * K, K, N, 256, b.cuda(), N, None, 0, 0, 0, 1, out, 0,
+             batch * N // 8, 0, N // 8, 0, 0, 0, M, batch, 0, mask, batch * N // 32, 0, N // 32)
+    y = from_tcl_host(out.cpu(), M)                                  # [M, batch*N] relu outputs
+    bits = mask.cpu().permute(0, 2, 1).reshape(M, batch * N // 32)   # [M, chunks32]
+    got = ((bits.unsqueeze(-1) >> torch.arange(32)) & 1).reshape(M, batch * N).bool()
+    # bf16 rounding can flush a tiny positive fp32 output to +0: the mask (taken before rounding) may only have MORE ones
+    assert bool((got | ~(y > 0)).all()) and float((got != (y > 0)).float().mean()) < 1e-3
+    dZ = to_tcl_host(torch.randn(M, batch * N)).cuda()
+    Wtt = torch.stack([to_tcl_host(W[i].t().contiguous(), 256) for i in range(batch)]).cuda()
+    o1 = torch.zeros(M // 128, batch * K // 8, 128, 8, dtype=torch.bfloat16, device="cuda")
+    o2 = torch.zeros_like(o1)
+    # data gradient of a layer whose INPUT activations are `out` (N == K here): relu' from aux vs from the mask
+    lib.call("mli_tc_linear", dZ, batch * N // 8, 0, N // 8, Wtt, N * K, N, K, 256, None, 0, out, batch * N // 8, 0, N // 8, 1,
+             o1, 0, batch * K // 8, 0, K // 8, 0, 0, 0, M, batch, 1, None, 0, 0, 0)
+    lib.call("mli_tc_linear", dZ, batch * N // 8, 0, N // 8, Wtt, N * K, N, K, 256, None, 0, None, 0, 0, 0, 1,
+             o2, 0, batch * K // 8, 0, K // 8, 0, 0, 0, M, batch, 1, mask, batch * N // 32, 0, N // 32)
+    d = (from_tcl_host(o1.cpu(), M) != from_tcl_host(o2.cpu(), M)).float().mean()
+    assert float(d) < 1e-3, float(d)

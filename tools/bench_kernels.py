@@ -30,7 +30,7 @@ def timeit(fn, n=10, warm=3):
     return a.elapsed_time(b) / n * 1e3  # us
 
 
-def bench_linear(K, N, BN, batch, epi, act, aux, out_f32=False, nbuf=3, label=""):
+def bench_linear(K, N, BN, batch, epi, act, aux, out_f32=False, nbuf=3, label="", mask=False):
     A = [tcl(M, batch * K // 8) for _ in range(nbuf)]
     W = tcl(batch * N, K // 8, BN)
     bias = torch.zeros(batch * N, device=dev)
@@ -40,13 +40,17 @@ def bench_linear(K, N, BN, batch, epi, act, aux, out_f32=False, nbuf=3, label=""
     else:
         O = [tcl(M, batch * N // 8) for _ in range(nbuf)]
 
+    MK = [torch.randint(-2 ** 31, 2 ** 31 - 1, ((M + 127) // 128, batch * N // 32, 128), dtype=torch.int32, device=dev)
+          for _ in range(nbuf)] if mask else [None] * nbuf
+
     def fn(i):
         j = i % nbuf
         _lib.call("mli_tc_linear", A[j], batch * K // 8, 0, K // 8, W, N * K, K, N, BN, bias if epi == 0 else None, N,
                   AUX[j], batch * N // 8 if aux else 0, 0, N // 8, act, O[j], int(out_f32), 0 if out_f32 else batch * N // 8,
-                  0, N // 8, batch * N if out_f32 else 0, 0, N, M, batch, epi)
+                  0, N // 8, batch * N if out_f32 else 0, 0, N, M, batch, epi, MK[j], batch * N // 32 if mask else 0, 0,
+                  N // 32 if mask else 0)
     us = timeit(fn)
-    by = M * batch * (K * 2 + N * (4 if out_f32 else 2) + (N * 2 if aux else 0))
+    by = M * batch * (K * 2 + N * (4 if out_f32 else 2) + (N * 2 if aux else 0) + (N // 8 if mask else 0))
     fl = 2.0 * M * batch * K * N
     print(f"tc_linear {label:28s} K={K} N={N} BN={BN} b={batch} epi={epi}: {us:8.1f} us  {by / us / 1e6:6.2f} TB/s  "
           f"{fl / us / 1e6:7.1f} TFLOP/s  stages={os.environ.get('MLI_NT_STAGES', 'max')}")
@@ -97,6 +101,14 @@ def main():
     if not which or "encode" in which:
         for t in (14, 17, 19, 22):
             bench_encode(t)
+    if "mask" in which:
+        for st in ("4", "5", "6"):
+            os.environ["MLI_NT_STAGES"] = st
+            bench_linear(256, 256, 256, 3, 0, 1, False, label="fwd relu (no mask)")
+            bench_linear(256, 256, 256, 3, 0, 1, False, label="fwd relu + mask out", mask=True)
+            bench_linear(256, 256, 256, 3, 1, 1, True, label="dgrad relu' from aux")
+            bench_linear(256, 256, 256, 3, 1, 1, False, label="dgrad relu' from mask", mask=True)
+        os.environ.pop("MLI_NT_STAGES", None)
     if not which or "linear" in which:
         for st in ("4", "6", None):
             if st is None:
