@@ -541,3 +541,47 @@ def test_model_inference_with_light_visibility_maps(lib):
     # geometric init = sphere of radius ~0.5, camera at (0,0,3), light at (1,-2,3): part of the visible cap is lit
     ps = out["pseudo_shading"]
     assert float((ps > 0).float().mean()) > 0.01 and bool(torch.isfinite(ps).all())
+
+
+def test_model_autograd_path_bf16_mode(lib):
+    """The drop-in autograd path (Model.forward -> torch losses -> backward) in the tensor-core mode: gradients reach every
+    parameter and agree with the fused train step of the same model; a no-grad forward skips the backward-only saves."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    from mli_nerf_b200.model import Model
+    R = 128
+    cfg = config.experiment("syn_hotdog_b", dict_size=14, rand_rays=R)
+    cfg.model.render.stratified = False
+    cfg.model.mli_precision = "bf16"
+    torch.manual_seed(0)
+    model = Model(cfg.model, cfg.data)
+    model.load_state_dict(port.init_params(port.PathConfig(log2_hashmap_size=14), seed=0, generic=True, table_scale=5e-3))
+    model = model.cuda().train()
+    model.progress = 0.5
+    pose = torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[711.0, 0, 256], [0, 711.0, 256], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, 1.0], [0, 1, 0, -2.0], [0, 0, 1, 3.0]]], dtype=torch.float32)
+    ray_idx = torch.randperm(512 * 512, generator=torch.Generator().manual_seed(0))[:R][None]
+    tg = port.synthetic_targets(R)
+    data = {k: cu(v) for k, v in dict(pose=pose, intr=intr, pose_light=pose_light, ray_idx=ray_idx, **tg).items()}
+    # fused step (render + 3 SDF-side losses only, so that the torch-side loss below is the same function)
+    cfg.trainer.loss_weight.intrinsic = 0.0
+    cfg.trainer.loss_weight.regularize_re = 0.0
+    cfg.trainer.loss_weight.curvature = 0.0
+    losses = model.fused_train_step(data, loss_cfg_from_trainer(cfg.trainer))
+    fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    out = model(data)
+    render = (out["rgb"] - data["image_sampled"]).abs().mean() * 3
+    eik = ((out["gradients"].norm(dim=-1) - 1.0) ** 2 * (~out["outside"]).float()).mean()
+    total = render + 0.1 * eik
+    total.backward()
+    assert abs(float(total) - float(losses[0])) < 1e-4 * abs(float(total)) + 1e-5
+    for n, p in model.named_parameters():
+        assert p.grad is not None, n
+        err = float((p.grad - fused[n]).norm() / (fused[n].norm() + 1e-20))
+        assert err < 1e-3, (n, err)
+    with torch.no_grad():
+        out2 = model(data)
+    assert torch.allclose(out2["rgb"], out["rgb"], atol=1e-6)
