@@ -193,7 +193,7 @@ def main():
         for n, p in model.named_parameters():
             p.requires_grad_("neural_rgb" in n)
     lcfg = loss_cfg_from_trainer(cfg.trainer)
-    reducer = GradReducer(model, world, comm_sms=int(os.environ.get("MLI_COMM_SMS", "16"))) if world > 1 else None
+    reducer = GradReducer(model, world, comm_sms=int(os.environ.get("MLI_COMM_SMS", "8"))) if world > 1 else None
     if reducer is not None:
         reducer.attach(model.engine)  # hash-table gradient slabs are all-reduced while the backward is still running
 

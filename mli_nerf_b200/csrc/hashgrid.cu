@@ -347,11 +347,11 @@ __global__ void __launch_bounds__(KS * 7) encode_rays_tcl_kernel(mli_grid_t grid
 constexpr int kBwdThreads = 128;
 
 // Two threads per (sample, level), four features each: the per-thread state (corner accumulators 8x4, gradient slices
-// PLANES x 8 B) halves, which lifts the kernel from 16 to 24+ resident warps per SM; every corner update is still one
+// PLANES x 8 B) halves, which lifts the kernel from 16 to 20 resident warps per SM without spills; every corner update is still one
 // 16-byte RED per thread.  The cell / weight arithmetic is done by both threads of a pair (the kernel is latency bound,
 // not issue bound).  Ray origin / direction / distance are loaded once, not once per plane.
 template <int PLANES>
-__global__ void __launch_bounds__(kBwdThreads, 6) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
+__global__ void __launch_bounds__(kBwdThreads, 5) encode_rays_bwd_tcl_kernel(mli_grid_t grid, RayArgs a,
                                                                              const __nv_bfloat16* __restrict__ dX, int x_chunks,
                                                                              float* __restrict__ table_grad, int level0) {
   constexpr int FH = 4;
