@@ -657,10 +657,11 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
 // Fused SDF trunk: centre rows AND all tap rows of a 128-sample tile in one persistent CTA.
 //   TMEM (512 columns): [0,256) centre accumulator z0, overwritten IN PLACE by the centre epilogue with
 //   sigma0 = sigmoid(100 z0) (tcgen05.st), which the tap epilogues then read back with tcgen05.ld -- the tap rows never
-//   fetch sigma0 from HBM (that re-read was half of the unfused tap kernel's traffic); [256,384) / [384,512): the two
-//   128-column halves of a tap plane's accumulator, used ping-pong so the epilogue of one half overlaps the MMAs of the
-//   next (the tap's A tile is streamed once per half; the second pass hits L2).
-// Work order per sample tile: centre (N = 256), then (tap 1, half 0), (tap 1, half 1), (tap 2, half 0), ...
+//   fetch sigma0 from HBM (that re-read was half of the unfused tap kernel's traffic); [256,512): the tap plane's
+//   accumulator.  (A ping-pong of two 128-column half accumulators overlapped MMAs and epilogue but had to stream every
+//   tap's A tile twice and ended up latency bound on the 72 KB activation ring: 395 us.  One pass per tap with the
+//   producer running a full tile ahead is faster.)
+// Work order per sample tile: centre, tap 1, tap 2, ... (N = 256 each)
 // Outputs: sdf[plane 0] = w_sdf . softplus(z0) + b_sdf, sdf[plane i] = w_sdf . (softplus(z0 + dz_i) - softplus(z0)),
 // h0 (bf16 TCL), and -- for the backward pass only -- sigma0 (fp32 TCL32) and dz (bf16 TCL).
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,8 +732,8 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
       }
       uint32_t cnt = 0;
       for (int st = blockIdx.x; st < n_st; st += gridDim.x) {
-        for (int u = 0; u < 1 + 2 * taps; ++u) {  // unit 0 = centre, then (tap, half) pairs: each streams one A tile
-          const int plane = u == 0 ? 0 : 1 + (u - 1) / 2;
+        for (int u = 0; u < 1 + taps; ++u) {  // unit 0 = centre, then one unit per tap plane: each streams one A tile
+          const int plane = u;
           const __nv_bfloat16* a_src = p.X + ((int64_t)plane * n_st + st) * p.x_chunks * (kTileM * 8);
           for (int kt = 0; kt < n_kt; ++kt, ++cnt) {
             const uint32_t s = cnt % kF_Stages;
@@ -745,20 +746,21 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_c = make_idesc(256, 0, 0), idesc_t = make_idesc(128, 0, 0);
+      const uint32_t idesc = make_idesc(256, 0, 0);
       const uint32_t lbo_a = kTileM * 16, lbo_b = 256 * 16;
       mbar_wait(b_full, 0);
       uint32_t cnt = 0, it = 0;
       for (int st = blockIdx.x; st < n_st; st += gridDim.x, ++it) {
-        for (int u = 0; u < 1 + 2 * taps; ++u) {
-          uint32_t d_tmem, idesc, b_row_off;
+        for (int u = 0; u < 1 + taps; ++u) {
+          uint32_t d_tmem;
+          const uint32_t b_row_off = 0;
           if (u == 0) {
             if (it >= 1) mbar_wait(c_empty, (it - 1) & 1);  // every tap epilogue of the previous tile has read sigma0
-            d_tmem = tmem_base; idesc = idesc_c; b_row_off = 0;
+            d_tmem = tmem_base;
           } else {
-            const uint32_t h = (u - 1) & 1, n_use = it * taps + (u - 1) / 2;  // uses of this half-buffer so far
-            if (n_use >= 1) mbar_wait(t_empty0 + 8 * h, (n_use - 1) & 1);
-            d_tmem = tmem_base + 256 + h * 128; idesc = idesc_t; b_row_off = h * 128 * 16;
+            const uint32_t n_use = it * taps + (u - 1);  // uses of the tap accumulator so far
+            if (n_use >= 1) mbar_wait(t_empty0, (n_use - 1) & 1);
+            d_tmem = tmem_base + 256;
           }
           tc_fence_after();
           uint32_t first = 1;
@@ -783,7 +785,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
             }
             umma_commit(a_empty0 + 8 * s);
           }
-          umma_commit(u == 0 ? c_full : t_full0 + 8 * ((u - 1) & 1));
+          umma_commit(u == 0 ? c_full : t_full0);
         }
       }
     }
@@ -836,29 +838,25 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
         float dt = 0.0f;
         const uint32_t n_use = it * taps + tp;
         const int64_t trow_tile = (int64_t)tp * n_st + st;  // tile index inside the [taps*M, 256] dz matrix
+        mbar_wait(t_full0, n_use & 1);
+        tc_fence_after();
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(t_full0 + 8 * h, n_use & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int k = 0; k < 2; ++k) {
-            const int cl = (sub + 2 * k) * 32;   // column inside the half
-            const int c0 = h * 128 + cl;         // hidden unit
-            float v[32], sg[32];
-            tmem_ld32(tmem_base + lane_addr + 256 + h * 128 + cl, v);
-            tmem_ld32(tmem_base + lane_addr + c0, sg);
-            if (k == 1) {  // last read of this half-accumulator by this warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(t_empty0 + 8 * h);
-            }
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = (sub + 2 * k) * 32;   // hidden unit
+          float v[32], sg[32];
+          tmem_ld32(tmem_base + lane_addr + 256 + c0, v);
+          tmem_ld32(tmem_base + lane_addr + c0, sg);
+          if (k == 3) {  // last read of the tap accumulator by this warp: the MMAs of the next tap may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty0);
+          }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dt = tap_dot(dt, s_w2[c0 + i], v[i], sg[i]);
-            if (p.dz) {
-              __nv_bfloat16* dst = p.dz + (trow_tile * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
+          for (int i = 0; i < 32; ++i) dt = tap_dot(dt, s_w2[c0 + i], v[i], sg[i]);
+          if (p.dz) {
+            __nv_bfloat16* dst = p.dz + (trow_tile * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
-            }
+            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
           }
         }
         if (tp == taps - 1) {  // sigma0 of this tile is not needed any more: the centre accumulator may be reused
