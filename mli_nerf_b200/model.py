@@ -352,7 +352,7 @@ class Model(torch.nn.Module):
                                       stratified=self.cfg_render.stratified)
 
     @torch.no_grad()
-    def fused_train_step(self, data, loss_cfg, accumulate=False, use_graph=False):
+    def fused_train_step(self, data, loss_cfg, accumulate=False, use_graph=False, after_backward=None):
         """forward + in-kernel losses + hand-written backward in one pass (no autograd graph).
 
         Equivalent to ``total = trainer.model_forward(data); total.backward()`` of the reference
@@ -361,7 +361,7 @@ class Model(torch.nn.Module):
         ``use_graph``: replay the ~130 kernel launches of the step from a CUDA graph (captured on first use and
         re-captured whenever a host-side scalar baked into the launches changes)."""
         if use_graph and not accumulate:
-            return self._graphed_train_step(data, loss_cfg)
+            return self._graphed_train_step(data, loss_cfg, after_backward)
         eng = self.engine
         B, R = data["ray_idx"].shape
         c, r, l, _ = self._rays(data["pose"], data["intr"], data["pose_light"], self.image_size_train, data["ray_idx"])
@@ -392,9 +392,11 @@ class Model(torch.nn.Module):
                 else:
                     q.grad = g
         self._last_render = res
+        if after_backward is not None:  # e.g. GradReducer.allreduce_grads: part of the step (and of its CUDA graph)
+            after_backward()
         return losses
 
-    def _graphed_train_step(self, data, loss_cfg):
+    def _graphed_train_step(self, data, loss_cfg, after_backward=None):
         tensors = {k: v for k, v in data.items() if isinstance(v, torch.Tensor) and v.is_cuda}
         eng = self.engine
         key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())),
@@ -410,11 +412,11 @@ class Model(torch.nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # eager warm-up off the capture stream (lazy loads, smem attributes)
                 for _ in range(2):
-                    self.fused_train_step(static, loss_cfg)
+                    self.fused_train_step(static, loss_cfg, after_backward=after_backward)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                losses = self.fused_train_step(static, loss_cfg)
+                losses = self.fused_train_step(static, loss_cfg, after_backward=after_backward)
             grads = {n: p.grad for n, p in self.named_parameters() if p.grad is not None}
             st = (graph, static, losses, grads)
             self._graphs[key] = st
