@@ -123,6 +123,9 @@ class RenderEngine:
         # level group has been launched (that slab of the hash-table gradient is final once the kernel completes)
         self.table_grad_hook = None
         self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._wg_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.overlap_wgrad = True  # weight-gradient GEMMs on a second stream, concurrent with trunk backward + scatter
+        self._wg_keep = []
         self._tg_early = None
 
     # ------------------------------------------------------------------------------------------------------
@@ -139,6 +142,26 @@ class RenderEngine:
             tg = torch.zeros(self.n_table_params(), dtype=torch.float32, device=self.device)
         tg.record_stream(cur)
         self._tg_early = tg
+
+    def _flush_later(self, later, after_event=None):
+        """Launch the deferred weight-gradient work.  Tensor-core mode: on the weight-gradient stream, ordered after
+        `after_event` (recorded on the main stream where the operands became final), so that these HBM-bound GEMMs run
+        concurrently with the latency-bound hash-grid scatter and the trunk backward on the main stream."""
+        if not later:
+            return
+        if self.tc and self.overlap_wgrad and self._wg_stream is not None:
+            if after_event is not None:
+                self._wg_stream.wait_event(after_event)
+            with torch.cuda.stream(self._wg_stream):
+                for fn in later:
+                    fn()
+            # the closures hold the operand tensors: keep them alive until the streams have joined, or the caching
+            # allocator could hand their memory to a main-stream allocation while the second stream still reads it
+            self._wg_keep.extend(later)
+        else:
+            for fn in later:
+                fn()
+        later.clear()
 
     def _take_table_grad(self):
         if self._tg_early is not None:
@@ -660,17 +683,24 @@ class RenderEngine:
                     later.append(lambda: self._tc_wgrad(dZ1, 0, 0, ctx["H0c"], 0, 0, M, HID, HID, 1, dW1, HID, 0, db=db1))
                 self._tc_linear(dZ1, 0, 0, T["W1t"], 0, HID, HID, 256, None, 0, None, 0, 0, ACT_NONE, dH0, False, 0, 0, 0,
                                 M, 1, 1)
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record()  # every operand of the head / layer-1 weight gradients is final here
         if need_sdf:
             grads.update(self._backward_sdf(p, ctx, need, train_mlp, d_grad, d_hessians, dXx, d_sdf_c, dZ0, dH0, dW1, db1,
-                                            later))
-        for fn in later:
-            fn()
-        later.clear()
+                                            later, ev))
+        self._flush_later(later, ev)  # whatever has not been started yet (heads-only training, fp32 mode)
         if self.tc:
             # weight_norm backward of every matrix in one launch; biases are plain column sums (already computed)
             dW0 = grads.pop("_dW0", None)
             if need_heads or dW0 is not None:
-                grads.update(self._unpack_grads_tc(p, dW0, dW1, dWh0, dWh, dWout, need_heads, dW0 is not None))
+                unp = {}
+                self._flush_later([lambda: unp.update(self._unpack_grads_tc(p, dW0, dW1, dWh0, dWh, dWout, need_heads,
+                                                                             dW0 is not None))])
+                grads.update(unp)
+            if self.overlap_wgrad and self._wg_stream is not None:
+                cur.wait_stream(self._wg_stream)  # join: all gradients are complete for whoever reads them next
+                self._wg_keep.clear()
             if need_heads:
                 j0 = 0
                 for hi, (name, kind, odim, _) in enumerate(self.heads):
@@ -703,7 +733,8 @@ class RenderEngine:
                 j0 += odim
         return grads
 
-    def _backward_sdf(self, p, ctx, need, train_mlp, d_grad, d_hessians, dXx, d_sdf_c, dZ0, dH0, dW1, db1, later):
+    def _backward_sdf(self, p, ctx, need, train_mlp, d_grad, d_hessians, dXx, d_sdf_c, dZ0, dH0, dW1, db1, later,
+                      ev_heads=None):
         """SDF stencil -> SDF trunk -> hash table part of backward().  The table gradient is launched here, level group
         by level group; the trunk's weight gradients are appended to `later`."""
         cfg, W = self.cfg, self.W
@@ -725,10 +756,14 @@ class RenderEngine:
             ws = torch.empty(_lib.load().mli_tc_sdf_trunk_bwd_ws_bytes(M), dtype=torch.uint8, device=self.device)
             call("mli_tc_sdf_trunk_bwd", d_sdf, M, cfg.taps, ctx["S0"], ctx["DZ"], dH0, ctx["H0c"], W["w_sdf"], Ed, dw_sdf,
                  db_sdf, ws)
+            self._flush_later(later, ev_heads)  # head / layer-1 weight gradients: start them on the second stream now
             if train_mlp:
                 db0 = self._f(HID)
-                later.append(lambda: self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0))
-                later.append(lambda: self._tc_colsum(Ed, 0, 32, M, out=db0))  # plane 0 = E = sum of the per-plane grads
+                ev_ed = torch.cuda.Event()
+                ev_ed.record()  # E_d is final
+                self._flush_later([lambda: self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0),
+                                   lambda: self._tc_colsum(Ed, 0, 32, M, out=db0)],  # plane 0 = E = sum over the planes
+                                  ev_ed)
             if "table" in need:
                 dX0 = self._tcl(P * M, 16)  # bf16 TCL: chunk l = level l, read back coalesced by the scatter kernel
                 self._tc_linear(Ed, 0, 0, T["W0t_enc"], 0, HID, 128, 128, None, 0, None, 0, 0, ACT_NONE, dX0, False, 0, 0,
