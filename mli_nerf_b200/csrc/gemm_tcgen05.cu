@@ -16,13 +16,20 @@
 //   * epilogues write 16 B per thread with the 32 lanes of a warp covering 512 contiguous bytes.
 // Weights use the same layout with the tile height equal to the CTA's N tile (BN <= 256).
 //
-// NT kernel (forward / data gradient): one CTA = one [128 x BN] output tile, K streamed in stages of 64 through a
-// 2-stage smem ring; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM allocator), warps 2..5 = epilogue
-// (tcgen05.ld -> bias/activation or activation-derivative -> bf16 TCL or fp32 row-major store).  Two CTAs per SM
-// (2 x 96 KB smem, 2 x 256 TMEM columns) so one tile's epilogue overlaps the other's MMAs.
-// TN kernel (weight gradient): one CTA = one [128 x BN] tile of dW^T-free dW, contraction over row tiles split across
-// CTAs, fp32 partials + fixed-order reduction (deterministic).
-// Roofline: tensor pipe (2 * M * N * K flops per call); operands stream from L2/HBM at (128+BN)*2 B per 128*BN MACs.
+// Kernels in this file (all tcgen05.mma cta_group::1, kind::f16, fp32 accumulation in TMEM):
+//   tc_gemm_nt_persist_kernel  forward / data-gradient layers.  Persistent, one CTA per SM: the [BN x K] weight tile is
+//       loaded once and stays in shared memory, 128-row activation tiles stream through a 4..6-stage TMA ring, two TMEM
+//       accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  Warp 0 = TMA producer, warp 1 = MMA
+//       issuer (+ TMEM allocator), warps 2..9 = epilogue.  Epilogues are template parameters: bias + activation (+ relu
+//       sign bits, + the fused 256->3/3/1 output layers), activation-derivative (from the previous layer's output or
+//       from its sign bits), and the SDF-trunk variants (split-bf16 operands, softplus + SDF head fused).
+//   tc_sdf_trunk_fused_kernel  SDF layer 0 for the centre rows and every tap plane of a sample tile in one CTA, with
+//       sigmoid(100 z0) kept in TMEM between them.
+//   tc_gemm_nt_kernel          non-persistent fallback when the weight tile does not fit (K = 768 feature data gradient).
+//   tc_gemm_tn_kernel          weight gradients dW = dZ^T X: contraction over row tiles split across one wave of CTAs,
+//       fp32 partials + fixed-order reduction (deterministic); the idle epilogue warps also produce the bias gradient.
+// Roofline: at this fusion level every one of them is bound by HBM (operands in, activations out), not by the tensor
+// pipe; measured 5.3..6.4 TB/s of the 6.5 TB/s copy bandwidth (profiles/r01_launches_bf16.md).
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>

@@ -11,13 +11,19 @@ Reference call stack being replaced (relative to /root/reference/):
   projects/NeuralLumen/utils/modules.py:106-174 LumenRGB forward
   + the autograd backward of all of it (projects/NeuralLumen/trainer.py:189-206).
 
-HBM layout (fp32, row-major; M = R*N samples, P = 1+taps stencil planes)
+HBM layout, fp32 mode (row-major; M = R*N samples, P = 1+taps stencil planes)
   X0   [P*M, 144]  = [hash encoding 0:128 | xyz 128:131 | 0-pad]          input of SDF layer 0 (K padded to 16)
   H0   [P*M, 256]  = softplus100(X0 W0^T + b0)                            (plane 0 = centre rows)
   sdf  [P*M]       = H0 w_sdf + b_sdf
   XH   [M, 304]    = [feat 0:256 | xyz | SH(view) | normal | SH(light) | 0-pad]   input of the fused head layer 0
   A1..A4 [M, nh*256] hidden activations of the nh heads side by side (batched block-diagonal layers 1..3)
   S    [M, 8]      per-sample head outputs (rgb3|o_r3|o_s1 for rgb_r_s)
+
+bf16 (tensor-core) mode: every matrix above lives in bf16 "TCL" [rows/128][cols/8][128][8] (csrc/gemm_tcgen05.cu); the
+trunk input is the split-bf16 delta-basis matrix Xd [P*M, 2*144] (plane 0 = centre rows, plane i = tap - centre; hi | lo
+halves), sdf planes >= 1 hold sdf_tap - sdf_centre, S0 = sigmoid(100 z0) (fp32) and DZ = W0 (x_tap - x_centre) (bf16) are
+kept for the backward pass, Am[l] are the relu sign bits of the head activations.  Backward: data-gradient chain first
+(main stream), weight-gradient GEMMs deferred to a second stream, table gradient scattered per level group.
 """
 import math
 from dataclasses import dataclass
