@@ -585,3 +585,30 @@ def test_model_autograd_path_bf16_mode(lib):
     with torch.no_grad():
         out2 = model(data)
     assert torch.allclose(out2["rgb"], out["rgb"], atol=1e-6)
+
+
+def test_model_inference_bf16_mode_ragged_chunks(lib):
+    """inference() in the tensor-core mode with chunk sizes that are not multiples of anything convenient (500 rays of a
+    24x37 image -> chunks of 500 and 388): agrees with the fp32 CUDA-core mode of the same model within the bf16 bounds."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.model import Model
+    outs = {}
+    params = make_case(R=8)["params"]
+    pose = torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[45.0, 0, 18.5], [0, 45.0, 12], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, -1.0], [0, 1, 0, 2.0], [0, 0, 1, -3.0]]], dtype=torch.float32)
+    for prec in ("fp32", "bf16"):
+        cfg = config.experiment("syn_hotdog_b", dict_size=14)
+        cfg.data.val.image_size = [24, 37]
+        cfg.model.render.rand_rays_val = 500
+        cfg.model.mli_precision = prec
+        model = Model(cfg.model, cfg.data)
+        model.load_state_dict(params)
+        outs[prec] = model.cuda().inference(dict(pose=cu(pose), intr=cu(intr), pose_light=cu(pose_light),
+                                                 idx=torch.zeros(1).long()), per_sample=False)
+    a, b = outs["bf16"], outs["fp32"]
+    assert "dists" not in a and a["rgb_map"].shape == (1, 3, 24, 37)
+    for k in ("rgb", "o_r", "o_s", "o_re", "opacity"):
+        err = (a[k] - b[k]).abs()
+        assert float((err.amax(dim=-1) < 2e-2).float().mean()) > 0.97, (k, float(err.max()))
+    assert torch.equal(a["outside"], b["outside"])
