@@ -257,10 +257,27 @@ def main():
     barrier()
     ms_e2e = t0.elapsed_time(t1)
 
+    # ---- informational: the same device-resident step followed by the fused AdamW update of every parameter -----
+    # (the metric is fwd+bwd, SURVEY.md 8f rank 1 keeps the optimizer out of it; this line shows what it adds)
+    from mli_nerf_b200.optim import FusedAdamW
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-2)
+    for i in range(3):
+        step(dev[i % n_batches])
+        opt.step()
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for i in range(args.steps):
+        step(dev[i % n_batches])
+        opt.step()
+    o1.record()
+    barrier()
+    ms_opt = o0.elapsed_time(o1)
+
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_opt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_opt = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -272,7 +289,7 @@ def main():
     # Dominant kernel class = the dense layers (the fused-MLP work, 806.0 MFLOP per ray fwd+bwd at 4 taps,
     # full-grad; 631.3 heads-only), i.e. every tcgen05 GEMM entry point (+ the CUDA-core ones in fp32 mode).  Their
     # summed CUDA-event time over the timed steps is the denominator of `achieved`.
-    dense_keys = ("mli_linear", "mli_rowdot", "mli_tc_linear", "mli_tc_wgrad", "mli_tc_sdf_trunk_fwd", "mli_tc_rowdot")
+    dense_keys = ("mli_linear", "mli_rowdot", "mli_tc_linear", "mli_tc_wgrad", "mli_tc_sdf_trunk", "mli_tc_rowdot")
     dense = [k for k in prof if k.startswith(dense_keys)]
     dense_ms = sum(prof[k][1] for k in dense)
     prof_ms = sum(v[1] for v in prof.values())
@@ -296,6 +313,9 @@ def main():
                    "l2": "inputs larger than L2: 1.46 GB hash table + 1.46 GB gradient "
                    "buffer streamed every step (L2 = 126 MB), 8 rotating ray batches"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
+        "with_optimizer": {"value": world * RAYS * args.steps / (ms_opt * 1e-3), "unit": UNIT,
+                           "ms_per_step": ms_opt / args.steps,
+                           "note": "informational: step + FusedAdamW over every trainable parameter (not the metric)"},
         "gpu_launches": launches,  # our kernels per `steps` steps (counted on the eager pass; the graph replays the same)
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dense layers: " + ", ".join(sorted(dense)),

@@ -419,6 +419,15 @@ int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                    void* stream);
 
+/* The same update for every tensor of an optimizer group in ONE launch (descriptors in HOST memory, at most
+ * MLI_ADAMW_MAX_TENSORS; they travel as kernel parameters).  Tensors of any size / alignment. */
+#define MLI_ADAMW_MAX_TENSORS 64
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t n;
+} mli_adamw_desc_t;
+int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

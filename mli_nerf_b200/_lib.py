@@ -57,6 +57,15 @@ class WnDesc(C.Structure):
                 ("row_begin", C.c_int32)]
 
 
+ADAMW_MAX_TENSORS = 64
+
+
+class AdamwDesc(C.Structure):
+    """mli_adamw_desc_t (one tensor of a batched AdamW launch)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64)]
+
+
 # Signature table derived from include/mli_b200.h itself (single source of truth for the ABI):
 #   p = device pointer (tensor / None / int), i = int32, l = int64, f = float, d = double, u = uint32,
 #   s = stream, h / H = HOST int32 / float array (parameter names starting with host_).

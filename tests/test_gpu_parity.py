@@ -447,19 +447,33 @@ def test_fused_adamw_matches_torch(lib):
     """the dense AdamW step of the reference's optimizer (base.yaml:117-121) as one fused kernel."""
     from mli_nerf_b200.optim import FusedAdamW
     torch.manual_seed(0)
-    shapes = [(1 << 16, 8), (256, 131), (3, 256), (), (1,)]
+    # one launch per group: large / ragged / scalar tensors, more tensors than one descriptor table holds (64), a
+    # parameter without gradient, and one that joins late (its own step count -> its own launch)
+    shapes = [(1 << 16, 8), (256, 131), (3, 256), (), (1,), (4097,), (4096,), (3,)] + [(5, 7)] * 70
     ref_p = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
     our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
     ref = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-2)
     ours = FusedAdamW(our_p, lr=1e-3, weight_decay=1e-2)
     for it in range(3):
-        for a, b in zip(ref_p, our_p):
+        for k, (a, b) in enumerate(zip(ref_p, our_p)):
+            if k == 2 or (k == 5 and it == 0):
+                a.grad = b.grad = None
+                continue
             g = torch.randn_like(a)
             a.grad, b.grad = g.clone(), g.clone()
         ref.step()
         ours.step()
     for a, b in zip(ref_p, our_p):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
+    assert torch.equal(our_p[2], ref_p[2])
+    # the single-tensor entry point computes the same update
+    p, g = torch.randn(1024, device="cuda"), torch.randn(1024, device="cuda")
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    q = p.clone().requires_grad_(True)
+    q.grad = g.clone()
+    torch.optim.AdamW([q], lr=2e-3, weight_decay=5e-2).step()
+    lib.call("mli_adamw_step", p, g, m, v, 1024, 2e-3, 0.9, 0.999, 1e-8, 5e-2, 1, 1.0)
+    assert torch.allclose(p, q.detach(), rtol=1e-5, atol=1e-6)
     assert set(ours.state_dict()["state"][0]) == set(ref.state_dict()["state"][0])
 
 
@@ -612,3 +626,32 @@ def test_model_inference_bf16_mode_ragged_chunks(lib):
         err = (a[k] - b[k]).abs()
         assert float((err.amax(dim=-1) < 2e-2).float().mean()) > 0.97, (k, float(err.max()))
     assert torch.equal(a["outside"], b["outside"])
+
+
+def test_mesh_lattice_sweep_matches_oracle(lib):
+    """the extract_mesh block sweep (mesh.py:25-49 of the reference) through Model.sdf, in
+    tensor-core mode, against the oracle evaluated on the same lattice; blocks are generated on the device."""
+    import numpy as np
+    from mli_nerf_b200 import config, mesh
+    from mli_nerf_b200.model import Model
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    params = port.init_params(ocfg, seed=0, generic=False, table_scale=1e-4)  # geometric init: a sphere of radius ~0.5
+    cfg = config.experiment("syn_hotdog_b", dict_size=14)
+    cfg.model.mli_precision = "bf16"
+    model = Model(cfg.model, cfg.data)
+    model.load_state_dict(params)
+    model = model.cuda().eval()
+    bounds, intv, br = [[-1.0, 1.0]] * 3, 2.0 / 24, 16
+    lat = mesh.LatticeBlocks(bounds, intv, br)
+    full = torch.stack(torch.meshgrid(*lat.axes, indexing="ij"), dim=-1)
+    want = -port.sdf_network(params, ocfg, full.view(1, -1, 3), with_feat=False)[0].view(*full.shape[:3]).numpy()
+    got = np.full(want.shape, np.nan, dtype=np.float32)
+    n = 0
+    for idx, xyz0, sdf in mesh.sdf_blocks(lambda x: -model.sdf(x), bounds, intv, br, device="cuda"):
+        s = lat.block_start(idx)
+        assert np.array_equal(xyz0, full[s].numpy())
+        got[s[0]:s[0] + sdf.shape[0], s[1]:s[1] + sdf.shape[1], s[2]:s[2] + sdf.shape[2]] = sdf
+        n += 1
+    assert n == len(lat) == 8
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-4), float(np.abs(got - want).max())
+    assert (want < 0).any() and (want > 0).any()  # the zero level set crosses the lattice
