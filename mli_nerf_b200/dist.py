@@ -7,6 +7,8 @@ torch.distributed (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU
 hash-table gradient is reduced in per-level slices so that NCCL can start on the coarse levels while the fine ones are
 still in flight on the compute stream; the ~3.6 MB of MLP gradients travel as one flat bucket.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -28,6 +30,9 @@ class GradReducer:
         been launched: the all-reduce of that slab then runs on the side stream (NCCL over NVLink) while the compute
         stream continues with the next level group and the deferred weight-gradient GEMMs."""
         engine.table_grad_hook = self._on_table_slab if self.world > 1 else None
+        # the table gradient is produced last; holding the weight-gradient GEMMs back until its scatter is launched gives
+        # the all-reduce independent work to overlap with (MLI_WGRAD_LAST=0: single-GPU schedule, for A/B runs)
+        engine.wgrad_after_scatter = self.world > 1 and os.environ.get("MLI_WGRAD_LAST", "1") == "1"
         if self.world > 1 and torch.cuda.is_available():
             from . import _lib
             # leave SMs for the NCCL kernels: a persistent GEMM CTA owns its SM's whole shared memory, so without

@@ -131,6 +131,10 @@ class RenderEngine:
         self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self._wg_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.overlap_wgrad = True  # weight-gradient GEMMs on a second stream, concurrent with trunk backward + scatter
+        # multi-GPU (set by GradReducer.attach): keep every weight-gradient GEMM back until the hash-grid scatter has been
+        # launched, so that the all-reduce of the 1.46 GB table gradient -- which can only start when the scatter, the last
+        # link of the data-gradient chain, has produced a slab -- has ~0.9 ms of independent work to hide behind
+        self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
 
@@ -762,14 +766,19 @@ class RenderEngine:
             ws = torch.empty(_lib.load().mli_tc_sdf_trunk_bwd_ws_bytes(M), dtype=torch.uint8, device=self.device)
             call("mli_tc_sdf_trunk_bwd", d_sdf, M, cfg.taps, ctx["S0"], ctx["DZ"], dH0, ctx["H0c"], W["w_sdf"], Ed, dw_sdf,
                  db_sdf, ws)
-            self._flush_later(later, ev_heads)  # head / layer-1 weight gradients: start them on the second stream now
+            hold = self.wgrad_after_scatter and "table" in need
+            if not hold:
+                self._flush_later(later, ev_heads)  # head / layer-1 weight gradients: start them on the second stream now
             if train_mlp:
                 db0 = self._f(HID)
                 ev_ed = torch.cuda.Event()
                 ev_ed.record()  # E_d is final
-                self._flush_later([lambda: self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0),
-                                   lambda: self._tc_colsum(Ed, 0, 32, M, out=db0)],  # plane 0 = E = sum over the planes
-                                  ev_ed)
+                w0 = [lambda: self._tc_wgrad(Ed, 0, 0, ctx["Xd"], 0, 0, P * M, HID, K0_PAD, 1, dW0, K0_PAD, 0),
+                      lambda: self._tc_colsum(Ed, 0, 32, M, out=db0)]  # plane 0 = E = sum over the planes
+                if hold:
+                    later.extend(w0)
+                else:
+                    self._flush_later(w0, ev_ed)
             if "table" in need:
                 dX0 = self._tcl(P * M, 16)  # bf16 TCL: chunk l = level l, read back coalesced by the scatter kernel
                 self._tc_linear(Ed, 0, 0, T["W0t_enc"], 0, HID, 128, 128, None, 0, None, 0, 0, ACT_NONE, dX0, False, 0, 0,
@@ -803,6 +812,10 @@ class RenderEngine:
                          cfg.taps, self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 16, tg, lv0, lv1)
                     if self.table_grad_hook is not None:
                         self.table_grad_hook(tg, e0, e1)
+                if later and self.wgrad_after_scatter:
+                    ev_sc = torch.cuda.Event()
+                    ev_sc.record()
+                    self._flush_later(later, ev_sc)
             else:
                 call("mli_encode_rays_bwd", self.grid, ctx["center"], ctx["ray_unit"], ctx["dists"], N, R, N, cfg.taps,
                      self.tap_eps, cfg.vol_range[0], cfg.vol_range[1], dX0, 128, tg, 0)
