@@ -428,6 +428,23 @@ typedef struct {
 int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, float lr, float beta1, float beta2,
                          float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange of the hash-table gradient over NVLink peer memory (mli_nerf_b200/dist.py): replaces the DDP
+ * all-reduce of this gradient (imaginaire/trainers/utils/get_trainer.py:80-88).  Every rank owns 1/W of a slab: it pulls
+ * that shard from every peer's buffer with the copy engines (mli_copy_async on IPC-mapped peer pointers), reduces
+ * (mli_reduce_slots: dst = (dst + sum of the n_slots staged shards) * scale) and pushes the mean back.
+ * ---------------------------------------------------------------------------------------------------- */
+int mli_enable_peer_access(int32_t peer_device);
+/* gradient buffer other ranks can map: cudaMalloc + its 64-byte CUDA IPC handle / map a peer's buffer into the current
+ * device's address space (cudaIpcOpenMemHandle with lazy peer access) / unmap / free */
+int mli_peer_alloc(int64_t bytes, void** host_out_ptr, void* host_out_handle64);
+int mli_peer_open(const void* host_handle64, void** host_out_ptr);
+int mli_peer_close(void* mapped_ptr);
+int mli_peer_free(void* ptr);
+int mli_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int mli_reduce_slots(float* dst, const float* slots, int32_t n_slots, int64_t slot_stride, int64_t n, float scale,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

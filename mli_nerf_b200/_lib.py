@@ -100,7 +100,8 @@ def _parse_header(path=HEADER_PATH):
 
 
 _SIGS = {k: v for k, v in _parse_header().items() if k not in ("mli_abi_version", "mli_device_ok", "mli_grid_init",
-                                                                "mli_set_sm_limit")}
+                                                                "mli_set_sm_limit", "mli_peer_alloc", "mli_peer_open")}
+HOST_ONLY = {"mli_enable_peer_access", "mli_peer_close", "mli_peer_free"}  # management calls: no stream argument
 _CTYPE = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "d": C.c_double, "u": C.c_uint32,
           "s": C.c_void_p, "h": C.c_void_p, "H": C.c_void_p}
 
@@ -124,6 +125,10 @@ def load():
     lib.mli_device_ok.restype = C.c_int
     lib.mli_set_sm_limit.argtypes = [C.c_int32]
     lib.mli_set_sm_limit.restype = C.c_int
+    lib.mli_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.mli_peer_alloc.restype = C.c_int
+    lib.mli_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mli_peer_open.restype = C.c_int
     lib.mli_grid_init.argtypes = [C.POINTER(Grid), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]
     lib.mli_grid_init.restype = C.c_int
     for name, sig in _SIGS.items():
@@ -204,6 +209,8 @@ def _n_launches(name, args):
         return 1 + (1 if args[18] is not None else 0)
     if name in ("mli_weightnorm_pack_batch", "mli_weightnorm_unpack_grad_batch"):
         return 1
+    if name in ("mli_copy_async", "mli_enable_peer_access"):
+        return 0  # copy-engine transfer / host call: no kernel
     if name == "mli_losses_fwd_bwd":
         return 3 + (1 if args[0].has_intrinsic else 0)
     return 1
@@ -267,6 +274,35 @@ def make_grid(n_levels, feat, log2_hashmap_size, base_resolution, per_level_scal
 
 def device_ok():
     return bool(load().mli_device_ok())
+
+
+class _RawCudaBuffer:
+    """A raw device pointer seen by torch as a 1-D fp32 tensor (torch.as_tensor over __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def peer_alloc(n_floats, device):
+    """-> (fp32 tensor over a fresh cudaMalloc allocation, its CUDA IPC handle as bytes, raw pointer)."""
+    ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+    with torch.cuda.device(device):
+        code = load().mli_peer_alloc(4 * int(n_floats), C.byref(ptr), handle)
+    if code != 0:
+        _raise(code, "mli_peer_alloc")
+    t = torch.as_tensor(_RawCudaBuffer(ptr.value, n_floats), device=torch.device(device))
+    return t, bytes(handle.raw), ptr.value
+
+
+def peer_open(handle, device):
+    """Map a peer rank's buffer (IPC handle bytes) into `device`'s address space -> raw pointer."""
+    ptr, buf = C.c_void_p(), C.create_string_buffer(handle, 64)
+    with torch.cuda.device(device):
+        code = load().mli_peer_open(buf, C.byref(ptr))
+    if code != 0:
+        _raise(code, "mli_peer_open")
+    return ptr.value
 
 
 def set_sm_limit(n_sms):

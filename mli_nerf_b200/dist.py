@@ -4,10 +4,20 @@ semantics of the reference (/root/reference/imaginaire/trainers/utils/get_traine
 because the reference toggles requires_grad after the DDP wrap (projects/NeuralLumen/trainer.py:44-54).
 
 torch.distributed (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests) is the plumbing.  The 1.46 GB
-hash-table gradient is reduced in per-level slices so that NCCL can start on the coarse levels while the fine ones are
-still in flight on the compute stream; the ~3.6 MB of MLP gradients travel as one flat bucket.
+hash-table gradient is exchanged in per-level-group slabs as soon as the scatter kernel of a group has been launched; the
+~3.6 MB of MLP gradients travel as one flat NCCL bucket.
+
+Table-gradient exchange (`PeerTableReducer`, default on CUDA): NCCL's all-reduce needs 32 resident CTAs to reach 2.55 ms
+for this payload at N = 2 (16 channels: 4.3 ms) and therefore cannot overlap with the weight-gradient GEMMs that own the
+SMs at that point of the step.  Here every rank maps its peers' gradient buffers (CUDA IPC) and moves the data with the
+copy engines instead: rank r owns shard r of each slab, pulls that shard of every peer's buffer over NVLink, sums
+(`mli_reduce_slots`), and pushes the mean back into every peer's buffer -- zero SMs for the transfers, inbound and outbound
+links busy at the same time.  Cross-rank ordering ("your scatter of this slab has finished", "every push has landed")
+is a one-element NCCL all-reduce enqueued in stream order.  Default for two ranks; with more ranks NCCL (in-switch
+reduction) is faster and stays the default -- `MLI_TABLE_ALLREDUCE=peer|nccl` overrides.
 """
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -23,6 +33,9 @@ class GradReducer:
         if side_stream and torch.cuda.is_available():
             self.stream = torch.cuda.Stream(priority=-1)  # communication kernels go first when SMs free up
         self._early = {}  # data_ptr of gradients whose slabs were already reduced through the engine hook
+        self.peer = None  # PeerTableReducer (set by attach)
+        self._engine = None
+        self._limit_sms = False
 
     # -- overlap of the hash-table gradient exchange with the rest of the backward pass ------------------------------
     def attach(self, engine):
@@ -30,14 +43,44 @@ class GradReducer:
         been launched: the all-reduce of that slab then runs on the side stream (NCCL over NVLink) while the compute
         stream continues with the next level group and the deferred weight-gradient GEMMs."""
         engine.table_grad_hook = self._on_table_slab if self.world > 1 else None
+        self._engine = engine
         # the table gradient is produced last; holding the weight-gradient GEMMs back until its scatter is launched gives
-        # the all-reduce independent work to overlap with (MLI_WGRAD_LAST=0: single-GPU schedule, for A/B runs)
+        # the exchange independent work to overlap with (MLI_WGRAD_LAST=0: single-GPU schedule, for A/B runs)
         engine.wgrad_after_scatter = self.world > 1 and os.environ.get("MLI_WGRAD_LAST", "1") == "1"
         if self.world > 1 and torch.cuda.is_available():
             from . import _lib
-            # leave SMs for the NCCL kernels: a persistent GEMM CTA owns its SM's whole shared memory, so without
-            # this the all-reduce only advances in the gaps between kernels
-            _lib.set_sm_limit(148 - self.comm_sms)
+            # measured (bench.py, full-grad): N = 2  peer 7.05 ms / NCCL 7.42 ms per step;  N = 8  peer 10.26 ms / NCCL
+            # 9.32 ms (NCCL reduces inside the NVSwitch there; the copy engines reach only 400-460 GB/s inbound with
+            # seven sources) -> the peer exchange is the default for two ranks, NCCL beyond
+            mode = os.environ.get("MLI_TABLE_ALLREDUCE", "peer" if self.world == 2 else "nccl")
+            backend = str(dist.get_backend())
+            if dist.get_rank() == 0:
+                print(f"[mli] table-gradient exchange: {mode} (torch.distributed backend {backend})", file=sys.stderr,
+                      flush=True)
+            if mode == "peer" and "nccl" in backend:
+                groups = engine.level_groups()
+                self.peer = PeerTableReducer(engine.n_table_params(), engine.device, max_slabs=len(groups))
+                engine.table_grad_buffer = self.peer.buf  # the scatter writes straight into the IPC-shared buffer
+            elif mode in ("peer", "nccl"):
+                # NCCL needs its 32 channels = 32 resident CTAs to move this payload at full rate (16 channels: 4.3 ms
+                # instead of 2.55 ms at N = 2) and a persistent GEMM CTA owns its SM's whole shared memory: from the
+                # first slab on, the persistent kernels of the step are launched on 148 - comm_sms SMs (_on_table_slab)
+                self._limit_sms = True
+            else:
+                raise _lib.MliError(f"MLI_TABLE_ALLREDUCE={mode}: expected peer or nccl")
+
+    def close(self):
+        """Unmap / free the peer-shared table-gradient buffer (collective: every rank calls it)."""
+        if self.peer is None:
+            return
+        for p in self.model.parameters():
+            if p.grad is not None and p.grad.data_ptr() == self.peer.buf.data_ptr():
+                p.grad = None
+        if self._engine is not None:
+            self._engine.table_grad_buffer = None
+            self._engine.table_grad_hook = None
+        self.peer.close()
+        self.peer = None
 
     def _avg(self, t):
         if dist.get_backend() == "nccl":
@@ -47,9 +90,16 @@ class GradReducer:
             t.mul_(1.0 / self.world)
 
     def _on_table_slab(self, flat, a, b):
-        if self.stream is None:
+        if self.peer is not None:
+            if flat.data_ptr() != self.peer.buf.data_ptr():
+                raise RuntimeError("table gradient was not accumulated in the peer-shared buffer")
+            self.peer.reduce_slab(a, b)
+        elif self.stream is None:
             self._avg(flat[a:b])
         else:
+            if self._limit_sms:
+                from . import _lib
+                _lib.set_sm_limit(148 - self.comm_sms)  # until allreduce_grads() has joined
             ev = torch.cuda.Event()
             ev.record()  # the slab is final once everything enqueued so far on the compute stream has run
             self.stream.wait_event(ev)
@@ -75,6 +125,8 @@ class GradReducer:
         if self.world <= 1:
             return
         big, small = self._buckets()
+        if self.peer is not None:
+            self.peer.gather()  # ahead of the MLP bucket in the NCCL queue: that one waits for the end of the backward
         cur = torch.cuda.current_stream() if self.stream is not None else None
         if self.stream is not None:
             self.stream.wait_stream(cur)
@@ -94,7 +146,172 @@ class GradReducer:
                     off += g.numel()
         if self.stream is not None:
             cur.wait_stream(self.stream)
+        if self.peer is not None:
+            self.peer.finish()
+        if self._limit_sms:
+            from . import _lib
+            _lib.set_sm_limit(148)
 
+
+def shard_bounds(a, b, rank, world):
+    """Element range of slab [a, b) owned by `rank`: equal shards, multiples of 4 elements (16-byte vector access)."""
+    n = b - a
+    sh = ((n + world - 1) // world + 3) // 4 * 4
+    return a + min(rank * sh, n), a + min((rank + 1) * sh, n)
+
+
+class PeerTableReducer:
+    """all-reduce(mean) of one large fp32 buffer, slab by slab, over NVLink peer memory with the copy engines.
+
+    Reduce-scatter: once every rank's scatter of a slab has finished [one-element NCCL all-reduce in stream order], rank r
+    pulls shard r of every peer's buffer into staging (cudaMemcpyAsync on IPC-mapped pointers: DMA, no SMs) and
+    `mli_reduce_slots` writes the mean into its own shard.  All-gather: once every rank has summed a slab [NCCL token],
+    rank r pulls the finished shard p from every peer p.  All copies of a rank run back to back on ONE stream -- two
+    concurrent inbound transfers share the link at a lower total rate (measured: 400-540 GB/s together, 735 GB/s alone;
+    a push runs at 544 GB/s, hence pull for both phases) -- while the sums run beside them on a second stream.  Both link
+    directions carry 2 (W-1)/W of the buffer per step, like a ring all-reduce, without occupying SMs."""
+
+    def __init__(self, n_elems, device, max_slab=None, max_slabs=16):
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if not 2 <= self.world <= 8:
+            raise _lib.MliError("PeerTableReducer: world size 2..8 (one NVSwitch domain)")
+        self.device = torch.device(device)
+        self.n = int(n_elems)
+        # the persistent gradient buffer: its own cudaMalloc allocation (outside the caching allocator) + IPC handle
+        self.buf, handle, self._own_ptr = _lib.peer_alloc(self.n, self.device)
+        self.buf.zero_()
+        # staging for the pulled shards of every slab of one step (the sums run behind the copies)
+        self.stage_cap = (self.world - 1) * ((self.n + self.world - 1) // self.world + 8 * max_slabs)
+        self.stage = torch.empty(self.stage_cap, dtype=torch.float32, device=self.device)
+        self._stage_off = 0
+        self._slabs = []
+        self.token = torch.zeros(1, dtype=torch.float32, device=self.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.n, handle))
+        self.peer_ptr = []
+        for p, (n_p, h) in enumerate(handles):
+            if n_p != self.n:
+                raise _lib.MliError("PeerTableReducer: ranks disagree on the buffer size")
+            self.peer_ptr.append(self._own_ptr if p == self.rank else _lib.peer_open(h, self.device))
+        self.s_sig = torch.cuda.Stream(device=self.device, priority=-1)
+        self.s_copy = torch.cuda.Stream(device=self.device)
+        self.s_add = torch.cuda.Stream(device=self.device, priority=-1)
+        self._pending = False
+        # MLI_PEER_TRACE=1: CUDA-event timeline of one exchange (rank 0 prints it once, after a few warm-up steps)
+        self._trace = [] if os.environ.get("MLI_PEER_TRACE", "0") == "1" else None
+        self._trace_step = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+
+    def _mark(self, label, stream=None):
+        if self._trace is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream) if stream is not None else ev.record()
+        self._trace.append((label, ev))
+
+    def _others(self):
+        return [(self.rank + k) % self.world for k in range(1, self.world)]  # rotated: spreads the load over the peers
+
+    def _token(self, after):
+        """Cross-rank ordering point: completes (in stream order) once every rank has reached it.  -> event"""
+        self.s_sig.wait_event(after)
+        with torch.cuda.stream(self.s_sig):
+            dist.all_reduce(self.token)
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev
+
+    def reduce_slab(self, a, b):
+        """Enqueue the reduce-scatter of buf[a:b]; the slab is final once everything enqueued so far on the current stream
+        has run.  Returns at once (stream-ordered); `gather()` + `finish()` complete the exchange."""
+        call, r, W = self._lib.call, self.rank, self.world
+        if not 0 <= a <= b <= self.n:
+            raise self._lib.MliError("PeerTableReducer: bad slab")
+        ev = torch.cuda.Event()
+        ev.record()
+        self._mark(f"slab {a}: scatter launched (compute stream position)")
+        ready = self._token(ev)  # every rank's scatter of this slab has completed
+        self._mark(f"slab {a}: all ranks scattered", self.s_sig)
+        m0, m1 = shard_bounds(a, b, r, W)
+        n = m1 - m0
+        slot = (n + 3) // 4 * 4
+        off = self._stage_off
+        if off + (W - 1) * slot > self.stage_cap:
+            raise self._lib.MliError("PeerTableReducer: staging buffer exhausted (too many slabs in one step)")
+        self._stage_off += (W - 1) * slot
+        self.s_copy.wait_event(ready)
+        with torch.cuda.stream(self.s_copy):
+            if n > 0:
+                for k, p in enumerate(self._others()):
+                    call("mli_copy_async", self.stage.data_ptr() + 4 * (off + k * slot), self.peer_ptr[p] + 4 * m0, 4 * n)
+            pulled = torch.cuda.Event()
+            pulled.record()
+            self._mark(f"slab {a}: own shard pulled")
+        self.s_add.wait_event(pulled)
+        with torch.cuda.stream(self.s_add):
+            if n > 0:
+                call("mli_reduce_slots", self._own_ptr + 4 * m0, self.stage.data_ptr() + 4 * off, W - 1, slot, n, 1.0 / W)
+            summed = torch.cuda.Event()
+            summed.record()
+            self._mark(f"slab {a}: own shard summed")
+        self._slabs.append((a, b, summed))
+        self._pending = True
+
+    def gather(self):
+        """Enqueue the all-gather of every slab reduced since the last call (after the last `reduce_slab` of the step)."""
+        call, W = self._lib.call, self.world
+        for a, b, summed in self._slabs:
+            all_summed = self._token(summed)  # every rank's shard of this slab holds the mean
+            self._mark(f"slab {a}: all ranks summed", self.s_sig)
+            self.s_copy.wait_event(all_summed)
+            with torch.cuda.stream(self.s_copy):
+                for p in self._others():
+                    p0, p1 = shard_bounds(a, b, p, W)
+                    if p1 > p0:
+                        call("mli_copy_async", self._own_ptr + 4 * p0, self.peer_ptr[p] + 4 * p0, 4 * (p1 - p0))
+                self._mark(f"slab {a}: gathered")
+        self._slabs = []
+
+    def finish(self):
+        """Current stream waits until the whole buffer holds the mean on every rank and nobody reads this rank's
+        buffer any more (it may be zeroed for the next step)."""
+        if not self._pending:
+            return
+        self.gather()
+        self._mark("finish(): compute stream position")
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self.s_copy):
+            ev.record()
+        done = self._token(ev)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(done)
+        cur.wait_stream(self.s_add)
+        self._mark("finish(): joined")
+        self._pending = False
+        self._stage_off = 0
+        if self._trace is not None:
+            self._trace_step += 1
+            if self._trace_step == 50 and self.rank == 0:
+                torch.cuda.synchronize(self.device)
+                t0 = self._trace[0][1]
+                print("\n".join(f"[peer trace] {t0.elapsed_time(e):8.3f} ms  {lbl}" for lbl, e in self._trace), flush=True)
+            self._trace = []
+
+    def close(self):
+        if not self.peer_ptr:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        for p, ptr in enumerate(self.peer_ptr):
+            if p != self.rank:
+                self._lib.call("mli_peer_close", ptr)
+        self.peer_ptr = []
+        dist.barrier()
+        self.buf = None
+        self._lib.call("mli_peer_free", self._own_ptr)
 
 class _null:
     def __enter__(self):

@@ -137,6 +137,9 @@ class RenderEngine:
         self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
+        # persistent buffer the table gradient is accumulated in (multi-GPU: the IPC-shared buffer of PeerTableReducer);
+        # None: a fresh zero-filled buffer per step
+        self.table_grad_buffer = None
 
     # ------------------------------------------------------------------------------------------------------
     def n_table_params(self):
@@ -149,7 +152,10 @@ class RenderEngine:
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            tg = torch.zeros(self.n_table_params(), dtype=torch.float32, device=self.device)
+            if self.table_grad_buffer is not None:
+                tg = self.table_grad_buffer.zero_()
+            else:
+                tg = torch.zeros(self.n_table_params(), dtype=torch.float32, device=self.device)
         tg.record_stream(cur)
         self._tg_early = tg
 
@@ -178,6 +184,8 @@ class RenderEngine:
             tg, self._tg_early = self._tg_early, None
             torch.cuda.current_stream().wait_stream(self._side)
             return tg
+        if self.table_grad_buffer is not None:
+            return self.table_grad_buffer.zero_()
         return self._z(self.n_table_params())
 
     def level_groups(self, max_groups=4):

@@ -22,7 +22,8 @@ def test_every_declared_symbol_is_exported(mli_lib):
 
 def test_signature_table_covers_header(mli_lib):
     assert set(_lib._SIGS) >= {"mli_encode_rays", "mli_tc_linear", "mli_tc_wgrad", "mli_composite_bwd", "mli_losses_fwd_bwd"}
-    assert all(sig.endswith("s") for sig in _lib._SIGS.values())  # every compute entry point takes a stream last
+    # every compute entry point takes a stream last
+    assert all(sig.endswith("s") for name, sig in _lib._SIGS.items() if name not in _lib.HOST_ONLY)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -81,3 +81,15 @@ def test_shard_rays_partition():
         spans = [shard_rays(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+
+
+def test_peer_shard_bounds_partition_every_slab():
+    from mli_nerf_b200.dist import shard_bounds
+    for world in (2, 3, 4, 8):
+        for a, b in ((0, 8), (0, 8 * 1000), (8 * 1000, 8 * 300_000), (64, 64), (8, 8 * 1_000_003)):
+            parts = [shard_bounds(a, b, r, world) for r in range(world)]
+            assert parts[0][0] == a and parts[-1][1] == b
+            assert all(x[1] == y[0] for x, y in zip(parts, parts[1:]))
+            assert all((p0 - a) % 4 == 0 for p0, _ in parts)
+            slot = ((b - a + world - 1) // world + 3) // 4 * 4
+            assert all(0 <= p1 - p0 <= slot for p0, p1 in parts)
