@@ -58,9 +58,14 @@ class GradReducer:
                 print(f"[mli] table-gradient exchange: {mode} (torch.distributed backend {backend})", file=sys.stderr,
                       flush=True)
             if mode == "peer" and "nccl" in backend:
-                groups = engine.level_groups()
-                self.peer = PeerTableReducer(engine.n_table_params(), engine.device, max_slabs=len(groups))
-                engine.table_grad_buffer = self.peer.buf  # the scatter writes straight into the IPC-shared buffer
+                try:
+                    self.peer = PeerTableReducer(engine.n_table_params(), engine.device,
+                                                 max_slabs=len(engine.level_groups()))
+                    engine.table_grad_buffer = self.peer.buf  # the scatter writes straight into the IPC-shared buffer
+                except _lib.MliError as e:  # raised on every rank or on none: all ranks take the NCCL exchange together
+                    print(f"[mli] rank {dist.get_rank()}: {e}; using the NCCL exchange", file=sys.stderr, flush=True)
+                    self.peer = None
+                    self._limit_sms = True
             elif mode in ("peer", "nccl"):
                 # NCCL needs its 32 channels = 32 resident CTAs to move this payload at full rate (16 channels: 4.3 ms
                 # instead of 2.55 ms at N = 2) and a persistent GEMM CTA owns its SM's whole shared memory: from the
@@ -179,22 +184,37 @@ class PeerTableReducer:
             raise _lib.MliError("PeerTableReducer: world size 2..8 (one NVSwitch domain)")
         self.device = torch.device(device)
         self.n = int(n_elems)
-        # the persistent gradient buffer: its own cudaMalloc allocation (outside the caching allocator) + IPC handle
-        self.buf, handle, self._own_ptr = _lib.peer_alloc(self.n, self.device)
-        self.buf.zero_()
-        # staging for the pulled shards of every slab of one step (the sums run behind the copies)
-        self.stage_cap = (self.world - 1) * ((self.n + self.world - 1) // self.world + 8 * max_slabs)
-        self.stage = torch.empty(self.stage_cap, dtype=torch.float32, device=self.device)
+        # the persistent gradient buffer: its own cudaMalloc allocation (outside the caching allocator) + IPC handle.
+        # Setup errors (no peer access, a rank that does not see its peers' GPUs, out of memory) are agreed on
+        # collectively so that every rank raises -- or none.
+        err, handle = None, None
+        self.buf = self._own_ptr = None
+        try:
+            self.buf, handle, self._own_ptr = _lib.peer_alloc(self.n, self.device)
+            self.buf.zero_()
+            # staging for the pulled shards of every slab of one step (the sums run behind the copies)
+            self.stage_cap = (self.world - 1) * ((self.n + self.world - 1) // self.world + 8 * max_slabs)
+            self.stage = torch.empty(self.stage_cap, dtype=torch.float32, device=self.device)
+        except Exception as e:  # noqa: BLE001
+            err = e
         self._stage_off = 0
         self._slabs = []
         self.token = torch.zeros(1, dtype=torch.float32, device=self.device)
         handles = [None] * self.world
         dist.all_gather_object(handles, (self.n, handle))
         self.peer_ptr = []
-        for p, (n_p, h) in enumerate(handles):
-            if n_p != self.n:
-                raise _lib.MliError("PeerTableReducer: ranks disagree on the buffer size")
-            self.peer_ptr.append(self._own_ptr if p == self.rank else _lib.peer_open(h, self.device))
+        try:
+            for p, (n_p, h) in enumerate(handles):
+                if n_p != self.n or h is None:
+                    raise _lib.MliError(f"PeerTableReducer: rank {p} has no matching buffer")
+                self.peer_ptr.append(self._own_ptr if p == self.rank else _lib.peer_open(h, self.device))
+        except Exception as e:  # noqa: BLE001
+            err = err or e
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            self._release()
+            raise _lib.MliError(f"PeerTableReducer: setup failed on at least one rank (this rank: {err})")
         self.s_sig = torch.cuda.Stream(device=self.device, priority=-1)
         self.s_copy = torch.cuda.Stream(device=self.device)
         self.s_add = torch.cuda.Stream(device=self.device, priority=-1)
@@ -300,18 +320,23 @@ class PeerTableReducer:
                 print("\n".join(f"[peer trace] {t0.elapsed_time(e):8.3f} ms  {lbl}" for lbl, e in self._trace), flush=True)
             self._trace = []
 
+    def _release(self):
+        for p, ptr in enumerate(self.peer_ptr):
+            if p != self.rank and ptr is not None:
+                self._lib.call("mli_peer_close", ptr)
+        self.peer_ptr = []
+        dist.barrier()  # nobody maps this rank's buffer any more
+        self.buf = None
+        if self._own_ptr is not None:
+            self._lib.call("mli_peer_free", self._own_ptr)
+            self._own_ptr = None
+
     def close(self):
         if not self.peer_ptr:
             return
         torch.cuda.synchronize(self.device)
         dist.barrier()
-        for p, ptr in enumerate(self.peer_ptr):
-            if p != self.rank:
-                self._lib.call("mli_peer_close", ptr)
-        self.peer_ptr = []
-        dist.barrier()
-        self.buf = None
-        self._lib.call("mli_peer_free", self._own_ptr)
+        self._release()
 
 class _null:
     def __enter__(self):
