@@ -277,9 +277,34 @@ class Model(torch.nn.Module):
                   int(image_size[1]), center, ray_unit, norm, light)
         return center, ray_unit, light, norm
 
+    def _empty_render(self, B, R, device):
+        """Output dict of an EMPTY ray batch (B*R == 0): the keys and trailing dimensions of the regular path, no launch
+        (the reference's torch code returns empty tensors as well)."""
+        N = self.path_cfg.n_samples
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=device)  # noqa: E731
+        res = dict(rgb=z(B, R, 3), opacity=None, outside=torch.zeros(B, R, 1, dtype=torch.bool, device=device),
+                   dists=z(B, R, N, 1), weights=z(B, R, N, 1), gradient=None, gradients=z(B, R, N, 3),
+                   hessians=z(B, R, N, 3) if self.training else None)
+        m = self.rgb_network_mode
+        if m == "rgb_r_s":
+            res.update(o_r=z(B, R, 3), o_s=z(B, R, 1), o_re=z(B, R, 3))
+        elif m in ("rgb_r", "r_s"):
+            res.update(o_r=z(B, R, 3), o_s=z(B, R, 3))
+        elif m == "r_s_re":
+            res.update(o_r=z(B, R, 3), o_s=z(B, R, 3), o_re=z(B, R, 3))
+        if not self.training:
+            res.update(opacity=z(B, R, 1), gradient=z(B, R, 3), _dist=z(B, R, 1))
+            if self.flag_light_visibility:
+                res.update(visibility=torch.zeros(B, R, 1, dtype=torch.bool, device=device), normal_x_light=z(B, R, 1),
+                           pseudo_shading=z(B, R, 1), inter_dist=z(B, R, 1),
+                           inter_mask=torch.zeros(B, R, 1, dtype=torch.bool, device=device))
+        return res
+
     def render_rays_lumen(self, center, ray_unit, pts_light, sample_idx=None, stratified=False, rands=None):
         """[B,R,3] rays -> the reference's output dict (NeuralLumen/model.py:232-336)."""
         B, R = center.shape[:2]
+        if B * R == 0:
+            return self._empty_render(B, R, center.device)
         c, r, l = (t.reshape(B * R, 3).contiguous().float() for t in (center, ray_unit, pts_light))
         if stratified and rands is None:
             rands = torch.rand(B, R, self.path_cfg.coarse, 1, device=c.device)  # nerf_util.py:33, same shape/order
@@ -364,6 +389,8 @@ class Model(torch.nn.Module):
             return self._graphed_train_step(data, loss_cfg, after_backward)
         eng = self.engine
         B, R = data["ray_idx"].shape
+        if B * R == 0:  # the reference's mean-reduced losses are NaN for an empty batch: refuse instead of training on NaN
+            raise ValueError("fused_train_step: empty ray batch")
         c, r, l, _ = self._rays(data["pose"], data["intr"], data["pose_light"], self.image_size_train, data["ray_idx"])
         names, params = self._named()
         p = dict(zip(names, params))
@@ -376,7 +403,7 @@ class Model(torch.nn.Module):
         near, far, outside = eng.bounds(c, r)
         dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], c, r, near, far, rands)
         res, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, self.progress)
-        tg = {k: v.reshape(B * R, -1) for k, v in data.items() if k.endswith("_sampled")}
+        tg = {k: v.reshape(B * R, v.shape[-1]) for k, v in data.items() if k.endswith("_sampled")}
         losses, d_out, d_grad, d_hess = eng.losses(loss_cfg, res["out"], res["gradients"], res["hessians"], outside, tg)
         need = set()
         for n, q in zip(names, params):

@@ -698,3 +698,59 @@ def test_multi_gpu_backward_schedule_same_gradients(lib):
             assert err < 1e-5, (n, err)
         else:
             assert torch.equal(p.grad, base[n]), n
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_ragged_and_empty_ray_counts(lib, prec):
+    """Edge cases of the ray batch: a single ray, a count that is not a multiple of any tile (37) and an EMPTY batch
+    (the reference's torch code returns empty tensors for it), through the drop-in Model in train and eval mode."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    from mli_nerf_b200.model import Model
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    params = port.init_params(ocfg, seed=0, generic=True, table_scale=5e-3)
+    cfg = config.experiment("syn_hotdog_b", dict_size=14, rand_rays=64)
+    cfg.model.render.stratified = False
+    cfg.model.mli_precision = prec
+    model = Model(cfg.model, cfg.data)
+    model.load_state_dict(params)
+    model = model.cuda()
+    model.progress = 0.5
+    tol = 1e-3 if prec == "fp32" else 2e-2
+    for R in (1, 37, 0):
+        center, ray_unit, light = port.synthetic_rays(max(R, 1), seed=11)
+        center, ray_unit, light = center[:, :R], ray_unit[:, :R], light[:, :R]
+        for training in (True, False):
+            model.train(training)
+            with torch.no_grad():
+                out = model.render_rays_lumen(cu(center), cu(ray_unit), cu(light), stratified=False)
+            assert out["rgb"].shape == (1, R, 3) and out["weights"].shape == (1, R, 128, 1)
+            assert out["gradients"].shape == (1, R, 128, 3) and out["outside"].shape == (1, R, 1)
+            if R == 0:
+                continue
+            with torch.no_grad():
+                ref = port.render_rays(params, ocfg, center, ray_unit, light, rands=None, training=training, progress=0.5)
+            assert torch.equal(out["outside"].cpu(), ref["outside"])
+            for k in ("rgb", "o_r", "o_s"):
+                # end to end the sample positions are the product's own: a sample that lands in the neighbouring
+                # importance bin (1-ulp cdf differences) moves a ray's colour by ~1e-2, so: all rays close, most tight
+                err = (out[k].cpu() - ref[k]).abs().amax(dim=-1).view(-1)
+                assert float(err.max()) < 5e-2 and float((err < tol).float().mean()) >= 0.9, (R, training, k, err)
+        # the fused train step on the same ray counts
+        model.train()
+        tg = port.synthetic_targets(max(R, 1), seed=3)
+        data = dict(pose=torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32),
+                    intr=torch.tensor([[[711.0, 0, 256], [0, 711.0, 256], [0, 0, 1]]]),
+                    pose_light=torch.tensor([[[1, 0, 0, 1.0], [0, 1, 0, -2.0], [0, 0, 1, 3.0]]], dtype=torch.float32),
+                    ray_idx=torch.randperm(512 * 512, generator=torch.Generator().manual_seed(R))[:R][None],
+                    **{k: v[:, :R] for k, v in tg.items()})
+        data = {k: cu(v) for k, v in data.items()}
+        if R == 0:  # mean-reduced losses of an empty batch are NaN in the reference: the fused step refuses it
+            with pytest.raises(ValueError):
+                model.fused_train_step(data, loss_cfg_from_trainer(cfg.trainer))
+            continue
+        losses = model.fused_train_step(data, loss_cfg_from_trainer(cfg.trainer))
+        torch.cuda.synchronize()
+        assert torch.isfinite(losses).all(), (R, losses)
+        for n, p in model.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), (R, n)
