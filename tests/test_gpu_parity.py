@@ -754,3 +754,45 @@ def test_ragged_and_empty_ray_counts(lib, prec):
         assert torch.isfinite(losses).all(), (R, losses)
         for n, p in model.named_parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all(), (R, n)
+
+
+def test_edge_rays_bounds_and_flat_cdf(lib):
+    """AABB rays with ZERO direction components (t = +-inf / nan in the slab test), rays starting inside
+    the box / the sphere, rays that miss; and importance sampling from all-zero / denormal weights (flat cdf -> idx = N)."""
+    from mli_nerf_b200.engine import RenderEngine
+    # ---- bounds -------------------------------------------------------------------------------------------------
+    dirs = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [0, 0, -1.0], [0.6, 0.8, 0], [0, 0.6, -0.8], [-1.0, 0, 0],
+                         [0.57735, 0.57735, 0.57735], [0, -1.0, 0]])
+    origins = torch.tensor([[-2.0, 0.1, 0.05], [0.2, -3.0, 0.1], [0.1, 0.1, 2.0], [-2.0, -2.5, 0.0], [0.3, -1.0, 1.4],
+                            [0.0, 0.0, 0.0],  # starts inside
+                            [-1.0, -1.0, -1.0], [0.9, 3.0, 0.9]])  # the last one runs parallel to a slab, outside of it
+    center = origins.repeat(2, 1)[None]
+    ray = torch.cat([dirs, -dirs])[None]
+    for bounding in ("box", "unit_sphere"):
+        case = make_case(R=16, bounding=bounding)
+        ocfg = case["ocfg"]
+        eng, _ = _engine(case, lib)
+        near, far, outside = eng.bounds(cu(center[0]), cu(ray[0]))
+        n_ref, f_ref, o_ref = port.dist_bounds(ocfg, center, ray)
+        assert torch.equal(outside.cpu().bool(), o_ref[0, :, 0]), bounding
+        assert 0 < int(o_ref.sum()) < 16
+        assert torch.allclose(near.cpu(), n_ref[0, :, 0], rtol=1e-6, atol=1e-7), bounding
+        assert torch.allclose(far.cpu(), f_ref[0, :, 0], rtol=1e-6, atol=1e-7), bounding
+    # ---- flat / degenerate cdfs ------------------------------------------------------------------------------------
+    for n_w in (63, 111):
+        g = torch.Generator().manual_seed(n_w)
+        R = 512
+        w = torch.rand(R, n_w, generator=g) * (torch.rand(R, n_w, generator=g) > 0.5)
+        w[:64] = 0.0            # all-zero weights: normalize() leaves zeros, flat cdf, every u lands past the end (idx = N)
+        w[64:128, 5:] = 0.0     # all mass in the first bins
+        w[128:192] *= 1e-30     # denormal-scale mass
+        w[192:256, :-1] = 0.0   # all mass in the last bin
+        idx, low, high = (torch.empty(R, 16, dtype=torch.int32, device="cuda") for _ in range(3))
+        cdf = torch.empty(R, n_w + 1, device="cuda")
+        lib.call("mli_pdf_bins", cu(w), n_w, R, n_w, 16, idx, low, high, cdf)
+        bins = torch.arange(n_w + 1, dtype=torch.float32).expand(R, -1)[None, ..., None]
+        _, info = port.sample_from_pdf(bins, w[None], 16)
+        assert torch.equal(cdf.cpu(), info["cdf"][0])
+        assert torch.equal(idx.cpu().long(), info["idx"][0])
+        assert int(info["idx"][0, :64].min()) == n_w + 1 or int(info["idx"][0, :64].min()) == n_w  # past-the-end bin
+        assert torch.equal(low.cpu().long(), info["low"][0]) and torch.equal(high.cpu().long(), info["high"][0])
