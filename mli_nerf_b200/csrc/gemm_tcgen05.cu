@@ -692,14 +692,38 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 }
 
 constexpr int kF_Stages = 6;   // x 12 KB (6-chunk K slices): 72 KB of activations in flight next to the 147 KB weight tile
+// 16 epilogue warps (four per TMEM lane quarter, 64 of the 256 hidden units each, 16-column chunks to stay under the
+// 112 registers a 576-thread CTA allows): the tap epilogue is two dependent MUFU ops per element and with two warps per
+// scheduler the MUFU pipe was 47 % busy
+constexpr int kF_EpiWarps = 16;
+constexpr int kF_Threads = 64 + 32 * kF_EpiWarps;
+__device__ __forceinline__ void epi16_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kF_EpiWarps) : "memory"); }
 
-__global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdfFused p) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kF_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdfFused p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * kF_Stages + 2 + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_b0[256];
   __shared__ __align__(16) float s_w2[256];
-  __shared__ float s_part[2][kTileM];
+  __shared__ float s_part[2][3][kTileM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kc = p.k_chunks, kc_total = 2 * p.k_chunks, stage_chunks = p.stage_chunks;
   const uint32_t b_bytes = (uint32_t)kc_total * 256 * 16;
@@ -716,11 +740,11 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
   if (threadIdx.x == 0) {
     mbar_init(b_full, 1);
     for (int s = 0; s < kF_Stages; ++s) { mbar_init(a_full0 + 8 * s, 1); mbar_init(a_empty0 + 8 * s, 1); }
-    mbar_init(c_full, 1); mbar_init(c_empty, kP_EpiWarps);
-    for (int h = 0; h < 2; ++h) { mbar_init(t_full0 + 8 * h, 1); mbar_init(t_empty0 + 8 * h, kP_EpiWarps); }
+    mbar_init(c_full, 1); mbar_init(c_empty, kF_EpiWarps);
+    for (int h = 0; h < 2; ++h) { mbar_init(t_full0 + 8 * h, 1); mbar_init(t_empty0 + 8 * h, kF_EpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 256; i += kP_Threads) { s_b0[i] = p.b0[i]; s_w2[i] = p.w2[i]; }
+  for (int i = threadIdx.x; i < 256; i += kF_Threads) { s_b0[i] = p.b0[i]; s_w2[i] = p.w2[i]; }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -798,7 +822,7 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
     }
   } else {
     const int q = warp & 3;            // TMEM lane quarter
-    const int sub = (warp - 2) >> 2;   // which of the two warps of the quarter: takes the 32-column chunks of its parity
+    const int sub = (warp - 2) >> 2;   // which of the four warps of the quarter: takes the 16-column chunks sub, sub+4, ...
     const int r_local = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t it = 0, sync_cnt = 0;
@@ -810,11 +834,12 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
       tc_fence_after();
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
-        const int c0 = (sub + 2 * k) * 32;
-        float v[32], sg[32];
-        tmem_ld32(tmem_base + lane_addr + c0, v);
+        const int c0 = (sub + 4 * k) * 16;
+        float v[16], sg[16];
+        tmem_ld16(tmem_base + lane_addr + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const float z = v[i] + s_b0[c0 + i];
           const float bz = 100.0f * z;
           const float e = __expf(-fabsf(bz));
@@ -824,21 +849,22 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
           dot = fmaf(s_w2[c0 + i], h, dot);
           v[i] = h;
         }
-        tmem_st32(tmem_base + lane_addr + c0, sg);
+        tmem_st16(tmem_base + lane_addr + c0, sg);
         if (p.s0) {
           float* sdst = p.s0 + ((int64_t)st * 64 * kTileM + (int64_t)(c0 / 4) * kTileM + r_local) * 4;
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
+          for (int g = 0; g < 4; ++g)
             *reinterpret_cast<float4*>(sdst + (int64_t)g * kTileM * 4) = make_float4(sg[g * 4], sg[g * 4 + 1], sg[g * 4 + 2], sg[g * 4 + 3]);
         }
         __nv_bfloat16* dst = p.h0 + ((int64_t)st * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+        for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      if (sub == 1) s_part[sync_cnt & 1][r_local] = dot;
-      epi_bar_sync();
-      if (sub == 0 && row < p.M) p.sdf[row] = dot + s_part[sync_cnt & 1][r_local] + p.b2[0];
+      if (sub > 0) s_part[sync_cnt & 1][sub - 1][r_local] = dot;
+      epi16_bar_sync();
+      if (sub == 0 && row < p.M)
+        p.sdf[row] = ((dot + s_part[sync_cnt & 1][0][r_local]) + s_part[sync_cnt & 1][1][r_local]) + s_part[sync_cnt & 1][2][r_local] + p.b2[0];
       ++sync_cnt;
       // ---- taps: dz -> dh = log1p(expm1(100 dz) sigma0) / 100 -> d_i ---------------------------------------------
       for (int tp = 0; tp < taps; ++tp) {
@@ -849,21 +875,22 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
         tc_fence_after();
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
-          const int c0 = (sub + 2 * k) * 32;   // hidden unit
-          float v[32], sg[32];
-          tmem_ld32(tmem_base + lane_addr + 256 + c0, v);
-          tmem_ld32(tmem_base + lane_addr + c0, sg);
+          const int c0 = (sub + 4 * k) * 16;   // hidden unit
+          float v[16], sg[16];
+          tmem_ld16(tmem_base + lane_addr + 256 + c0, v);
+          tmem_ld16(tmem_base + lane_addr + c0, sg);
+          tmem_ld_wait();
           if (k == 3) {  // last read of the tap accumulator by this warp: the MMAs of the next tap may start
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty0);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dt = tap_dot(dt, s_w2[c0 + i], v[i], sg[i]);
+          for (int i = 0; i < 16; ++i) dt = tap_dot(dt, s_w2[c0 + i], v[i], sg[i]);
           if (p.dz) {
             __nv_bfloat16* dst = p.dz + (trow_tile * 32 + c0 / 8) * (kTileM * 8) + r_local * 8;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
+            for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4*>(dst + (int64_t)g * kTileM * 8) = pack8(v + g * 8);
           }
         }
         if (tp == taps - 1) {  // sigma0 of this tile is not needed any more: the centre accumulator may be reused
@@ -871,9 +898,11 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_sdf_trunk_fused_kernel(TcSdf
           __syncwarp();
           if (lane == 0) mbar_arrive(c_empty);
         }
-        if (sub == 1) s_part[sync_cnt & 1][r_local] = dt;
-        epi_bar_sync();
-        if (sub == 0 && row < p.M) p.sdf[(int64_t)(1 + tp) * p.M + row] = (dt + s_part[sync_cnt & 1][r_local]) * kTapDotScale;
+        if (sub > 0) s_part[sync_cnt & 1][sub - 1][r_local] = dt;
+        epi16_bar_sync();
+        if (sub == 0 && row < p.M)
+          p.sdf[(int64_t)(1 + tp) * p.M + row] =
+              (((dt + s_part[sync_cnt & 1][0][r_local]) + s_part[sync_cnt & 1][1][r_local]) + s_part[sync_cnt & 1][2][r_local]) * kTapDotScale;
         ++sync_cnt;
       }
     }
@@ -1385,11 +1414,11 @@ extern "C" int mli_tc_sdf_trunk_fused(const void* X, int32_t x_chunks, int32_t K
   p.W0s = (const __nv_bfloat16*)W0s; p.b0 = b0; p.w2 = w_sdf; p.b2 = b_sdf; p.M = M; p.taps = taps;
   p.s0 = sigma0; p.h0 = (__nv_bfloat16*)h0; p.dz = (__nv_bfloat16*)dz; p.sdf = sdf;
   const size_t smem = (size_t)2 * p.k_chunks * 256 * 16 + (size_t)kF_Stages * p.stage_chunks * kTileM * 16;
-  MLI_REQUIRE(smem + 3584 <= 232448, "tc_sdf_trunk_fused: weight tile does not fit in shared memory");
+  MLI_REQUIRE(smem + 6656 <= 232448, "tc_sdf_trunk_fused: weight tile does not fit in shared memory");
   if (int e = set_smem((const void*)tc_sdf_trunk_fused_kernel, smem)) return e;
   int grid = (int)(M / kTileM);
   if (grid > mli_sm_limit()) grid = mli_sm_limit();
-  tc_sdf_trunk_fused_kernel<<<grid, kP_Threads, smem, (cudaStream_t)stream>>>(p);
+  tc_sdf_trunk_fused_kernel<<<grid, kF_Threads, smem, (cudaStream_t)stream>>>(p);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }
