@@ -9,7 +9,11 @@ Workload (BASELINE.json configs[1], SURVEY.md section 8d "C1"): syn_hotdog_b sha
 all five losses, FULL-GRAD (every parameter incl. the 1.46 GB hash table receives a gradient), synthetic rays from a
 pinhole camera at distance 3 (f = 711 px, 512x512), random-init weights (reference init).  One "step" = ray generation
 + bounds + hierarchical sampling + forward + in-kernel losses + full backward (optimizer excluded, as in the metric);
-with N>1 ranks it also includes the NCCL all-reduce(mean) of all parameter gradients.  One JSON line on rank 0.
+with N>1 ranks it also includes the all-reduce(mean) of all parameter gradients (table gradient: copy engines over NVLink
+peer memory at N = 2, NCCL beyond -- MLI_TABLE_ALLREDUCE=peer|nccl; MLP gradients: one NCCL bucket).  One JSON line on
+rank 0.  Extra keys next to the contract's: `host_enqueue_ms_per_step` (host time to enqueue a step, no sync),
+`with_optimizer` (informational: the same step followed by FusedAdamW over every parameter), `profile_ms_per_step`
+(CUDA-event time per C-ABI entry point on an eager pass).
 """
 import argparse
 import json

@@ -75,3 +75,16 @@ def test_trainer_facing_attributes():
     groups = mb.get_param_groups(cfgb.optim)
     names = {n for n, p in mb.named_parameters() if any(p is q for q in groups)}
     assert names and all("neural_rgb" in n for n in names)
+
+
+def test_fused_adamw_has_no_cpu_path():
+    """The optimizer is part of the product: parameters that are not contiguous fp32 CUDA tensors are refused, not
+    updated on the host."""
+    from mli_nerf_b200.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.zeros(8))
+    p.grad = torch.ones(8)
+    with pytest.raises(_lib.MliError):
+        FusedAdamW([p], lr=1e-3).step()
+    assert float(p.detach().abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        FusedAdamW([p], lr=-1.0)
