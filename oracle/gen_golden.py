@@ -138,8 +138,35 @@ def gen_render(name, cfg_name, overrides, cfgkw, R, training, progress, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
 
 
+def gen_light_visibility(name, R=64, seed=3):
+    """Model.get_light_visibility of the reference (stage-a export of pseudo shading labels, NeuralLumen/model.py:133-180)
+    reached through render_rays_lumen in eval mode; geometric init (sphere tracing is a fixed-point iteration that is only
+    stable for |grad sdf| ~ 1)."""
+    store = {}
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    p = port.init_params(ocfg, seed=seed, generic=False)
+    center, ray_unit, light = port.synthetic_rays(R, seed=seed + 1)
+    for ray_type in ("blend_z_sphere_tracing", "sphere_tracing", "blend_z"):
+        over = {"model.object.sdf.encoding.hashgrid.dict_size": 14, "model.light_visibility.enabled": True,
+                "model.light_visibility.camera_ray_type": ray_type}
+        cfg_ref = ref_import.load_config("syn_hotdog_b", over)
+        model = ref_import.build_model(cfg_ref, progress=1.0, training=False)
+        model.load_state_dict(p, strict=True)
+        with torch.no_grad():
+            out = model.render_rays_lumen(center, ray_unit, light, stratified=False)
+            blend = (out["dists"] * out["weights"]).sum(dim=2)  # render.composite(dists, weights), model.py:138
+        for k in ("visibility", "normal_x_light", "inter_dist", "inter_mask"):
+            store[f"{ray_type}_{k}"] = out[k].numpy()
+        store["radius"] = np.array(float(cfg_ref.model.light_visibility.visibility_sphere_radius))
+    store.update(center=center.numpy(), ray_unit=ray_unit.numpy(), light=light.numpy(), blend=blend.numpy(),
+                 gradient=out["gradient"].numpy(), rgb=out["rgb"].numpy(),
+                 params_sha256=np.frombuffer(params_digest(p).encode(), dtype=np.uint8), seed=np.array(seed))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gen_light_visibility("light_visibility_hotdog_b")
     gen_sampling()
     gen_hash_index()
     t14 = {"model.object.sdf.encoding.hashgrid.dict_size": 14}

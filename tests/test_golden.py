@@ -159,3 +159,58 @@ def test_cuda_reproduces_reference_render(name):
         assert abs(gn - ref) < ((0.5 if scalar else 1e-1) if loose else 1e-2) * ref + 1e-9, (k, gn, ref)
         if grads[k].numel() <= 4096 and not (loose and scalar):
             assert rel_err(grads[k].cpu().reshape(-1), torch.from_numpy(g["grad_" + k]).reshape(-1)) < (1e-1 if loose else 5e-3), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# light visibility: Model.get_light_visibility of the reference, three camera_ray_types
+# ---------------------------------------------------------------------------------------------------------------
+LV_TYPES = ("blend_z_sphere_tracing", "sphere_tracing", "blend_z")
+
+
+def _lv_case():
+    g = load("light_visibility_hotdog_b")
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    p = port.init_params(ocfg, seed=int(g["seed"]), generic=False)
+    assert digest(p) == bytes(g["params_sha256"]).decode(), "seeded weights differ from the ones the fixture was made with"
+    return g, ocfg, p
+
+
+@pytest.mark.parametrize("ray_type", LV_TYPES)
+def test_port_reproduces_reference_light_visibility(ray_type):
+    g, ocfg, p = _lv_case()
+    center, ray_unit, light = (torch.from_numpy(g[k]) for k in ("center", "ray_unit", "light"))
+    with torch.no_grad():
+        near, far, _ = port.dist_bounds(ocfg, center, ray_unit)
+        vis, nxl, idist, imask = port.light_visibility(p, ocfg, center, ray_unit, light, near, far, torch.from_numpy(g["blend"]),
+                                                       torch.from_numpy(g["gradient"]), ray_type, float(g["radius"]))
+    assert np.array_equal(imask.numpy(), g[ray_type + "_inter_mask"])
+    assert np.allclose(idist.numpy(), g[ray_type + "_inter_dist"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(nxl.numpy(), g[ray_type + "_normal_x_light"], rtol=1e-3, atol=1e-4)
+    assert (vis.numpy() == g[ray_type + "_visibility"]).mean() >= 0.97
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("ray_type", LV_TYPES)
+def test_cuda_reproduces_reference_light_visibility(ray_type, prec):
+    """RenderEngine.light_visibility (csrc/visibility.cu + the encode / SDF-trunk kernels in a 20 + 20 iteration loop)
+    against the reference's own outputs, fed the reference's composited distance and gradient."""
+    from mli_nerf_b200.engine import RenderEngine
+    g, ocfg, p = _lv_case()
+    eng = RenderEngine(product_cfg(ocfg, precision=1 if prec == "bf16" else 0))
+    pc = {k: v.cuda() for k, v in p.items()}
+    eng.pack_weights(pc)
+    c, r, l = (torch.from_numpy(g[k][0]).cuda() for k in ("center", "ray_unit", "light"))
+    near, far, _ = eng.bounds(c, r)
+    vis, nxl, idist, imask = eng.light_visibility(pc["neural_sdf.tcnn_encoding.params"], c, r, l, near, far,
+                                                  torch.from_numpy(g["blend"][0, :, 0]).cuda(),
+                                                  torch.from_numpy(g["gradient"][0]).cuda(), ray_type, float(g["radius"]))
+    R = c.shape[0]
+    ref_d, ref_m = g[ray_type + "_inter_dist"][0, :, 0], g[ray_type + "_inter_mask"][0, :, 0]
+    tol = 1e-4 if prec == "fp32" else 2e-3
+    ok = np.abs(idist.cpu().numpy().reshape(R) - ref_d) < tol * (1 + np.abs(ref_d))
+    assert ok.mean() > 0.97, ok.mean()
+    assert (imask.cpu().numpy().reshape(R).astype(bool) == ref_m).mean() > 0.97
+    assert (vis.cpu().numpy().reshape(R).astype(bool) == g[ray_type + "_visibility"][0, :, 0]).mean() > 0.95
+    d_n = np.abs(nxl.cpu().numpy().reshape(R) - g[ray_type + "_normal_x_light"][0, :, 0])
+    assert (d_n < (1e-3 if prec == "fp32" else 5e-3)).mean() > 0.97

@@ -78,3 +78,36 @@ def test_resolved_config_values_match_reference():
         assert getattr(ref.data, "bounding_type", None) == getattr(ours.data, "bounding_type", None)
         for k in ("render", "eikonal", "curvature"):
             assert getattr(ref.trainer.loss_weight, k) == getattr(ours.trainer.loss_weight, k)
+
+
+@pytest.mark.parametrize("ray_type", ["blend_z_sphere_tracing", "sphere_tracing", "blend_z"])
+def test_light_visibility_matches_reference(ray_type):
+    """Pins port.sphere_tracing_intersection / port.light_visibility on the reference's own
+    Model.get_light_visibility (projects/NeuralLumen/model.py:133-180, neuralangelo/model.py:298-325), reached through
+    render_rays_lumen in eval mode with model.light_visibility.enabled=True."""
+    over = {"model.object.sdf.encoding.hashgrid.dict_size": 14, "model.light_visibility.enabled": True,
+            "model.light_visibility.camera_ray_type": ray_type}
+    cfg_ref = ref_import.load_config("syn_hotdog_b", over)
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    p = port.init_params(ocfg, seed=3, generic=False)
+    model = ref_import.build_model(cfg_ref, progress=1.0, training=False)
+    model.load_state_dict(p, strict=True)
+    R = 48
+    center, ray_unit, light = port.synthetic_rays(R, seed=4)
+    with torch.no_grad():
+        ref_out = model.render_rays_lumen(center, ray_unit, light, stratified=False)
+        out = port.render_rays(p, ocfg, center, ray_unit, light, rands=None, training=False, progress=1.0, keep=True)
+        near, far, _ = port.dist_bounds(ocfg, center, ray_unit)
+        blend = port.composite(out["dists"], out["weights"])
+        radius = cfg_ref.model.light_visibility.visibility_sphere_radius
+        vis, nxl, idist, imask = port.light_visibility(p, ocfg, center, ray_unit, light, near, far, blend, out["gradient"],
+                                                       ray_type, radius)
+    for k in ("visibility", "normal_x_light", "inter_dist", "inter_mask"):
+        assert k in ref_out, k
+    assert 0 < int(ref_out["inter_mask"].sum()) <= R
+    # the tracing starts from composited quantities that agree to ~1e-6; the fixed-point iteration keeps them there on
+    # the geometric init (|grad sdf| ~ 1)
+    assert torch.equal(ref_out["inter_mask"].bool(), imask)
+    assert torch.allclose(ref_out["inter_dist"], idist, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ref_out["normal_x_light"], nxl, rtol=1e-3, atol=1e-4)
+    assert float((ref_out["visibility"].bool() == vis).float().mean()) >= 0.97
