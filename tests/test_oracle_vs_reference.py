@@ -111,3 +111,26 @@ def test_light_visibility_matches_reference(ray_type):
     assert torch.allclose(ref_out["inter_dist"], idist, rtol=1e-4, atol=1e-5)
     assert torch.allclose(ref_out["normal_x_light"], nxl, rtol=1e-3, atol=1e-4)
     assert float((ref_out["visibility"].bool() == vis).float().mean()) >= 0.97
+
+
+def test_ray_generation_matches_reference():
+    """Pins port.rays_from_pose (the restatement behind `mli_rays_from_pose`) on the reference's
+    camera.get_center_and_ray + nerf_util.slice_by_ray_idx + utils.get_center (NeuralLumen/model.py:120-128)."""
+    ref = ref_import.load()
+    import bench
+    H, W, R = 40, 56, 300
+    for seed in (0, 1, 2):
+        d = bench.synthetic_batch(R, seed, H=H, W=W)
+        pose = torch.cat([d["pose"], bench.synthetic_batch(R, seed + 10, H=H, W=W)["pose"]])  # batch of two cameras
+        intr = d["intr"].repeat(2, 1, 1)
+        intr[1, 0, 0], intr[1, 1, 1], intr[1, 0, 2] = 500.0, 480.0, 30.0
+        pose_light = torch.cat([d["pose_light"], bench.synthetic_batch(R, seed + 20, H=H, W=W)["pose_light"]])
+        ray_idx = torch.stack([torch.randperm(H * W, generator=torch.Generator().manual_seed(s))[:R] for s in (3, 4)])
+        center, ray = ref.camera.get_center_and_ray(pose, intr, (H, W))
+        c_ref = ref.nerf_util.slice_by_ray_idx(center, ray_idx)
+        r_ref = ref.nerf_util.slice_by_ray_idx(ray, ray_idx)
+        l_ref = ref.nerf_util.slice_by_ray_idx(ref.lumen_utils.get_center(pose_light, (H, W)), ray_idx)
+        c, r, l = port.rays_from_pose(pose, intr, pose_light, (H, W), ray_idx)
+        assert torch.allclose(c, c_ref, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(r, r_ref, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(l, l_ref, rtol=1e-6, atol=1e-6)
