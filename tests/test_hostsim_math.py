@@ -178,3 +178,25 @@ def test_neus_alpha_forward_backward(hostsim):
         assert torch.allclose(d_sdf, g_sdf, rtol=1e-3, atol=1e-4)
         assert torch.allclose(d_g, g_g, rtol=1e-3, atol=1e-5)
         assert abs(float(d_is.sum() * inv_s) - float(g_s)) < 1e-3 * max(1.0, abs(float(g_s)))
+
+
+def test_level_table_matches_float32_host_arithmetic_of_tcnn():
+    """tcnn sizes the table on the host with exp2f(l * log2f(s)) * base - 1 in float32 steps; the float64 formula rounded
+    once (oracle and product) must give the same resolutions -- incl. the knife-edge levels 5 / 10 / 15 of the
+    Neuralangelo config (2^0.4 growth: exact values 127 / 511 / 2047) -- so that reference checkpoints load."""
+    import math
+    import numpy as np
+    from oracle.torch_hashgrid import level_table
+    for lo, hi, n in ((5, 11, 16), (5, 12, 16), (4, 11, 16), (5, 11, 8)):
+        pls = math.exp((math.log(2 ** hi) - math.log(2 ** lo)) / (n - 1))
+        s = np.float32(pls)
+        l2 = np.float32(math.log2(float(s)))
+        res32 = []
+        for lv in range(n):
+            e = np.float32(math.pow(2.0, float(np.float32(np.float32(lv) * l2))))
+            scale = np.float32(np.float32(e * np.float32(2 ** lo)) - np.float32(1))
+            res32.append(int(math.ceil(float(scale))) + 1)
+        table, _ = level_table(n, 22, 2 ** lo, pls)
+        assert res32 == [t["res"] for t in table], (lo, hi, n)
+    table, total = level_table(16, 22, 32, math.exp((math.log(2048) - math.log(32)) / 15))
+    assert [table[i]["res"] for i in (5, 10, 15)] == [129, 513, 2049] and total == 45724048
