@@ -796,3 +796,48 @@ def test_edge_rays_bounds_and_flat_cdf(lib):
         assert torch.equal(idx.cpu().long(), info["idx"][0])
         assert int(info["idx"][0, :64].min()) == n_w + 1 or int(info["idx"][0, :64].min()) == n_w  # past-the-end bin
         assert torch.equal(low.cpu().long(), info["low"][0]) and torch.equal(high.cpu().long(), info["high"][0])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_coarse_to_fine_partial_levels(lib, prec):
+    """Stage-a coarse-to-fine (modules.py:97-113): only the first `active_levels` hash-grid levels contribute, the others
+    are masked to zero in the encoding and receive exactly zero gradient."""
+    from mli_nerf_b200.engine import RenderEngine
+    case = make_case(R=128, progress=0.5)
+    active = 6
+    ocfg = port.PathConfig(**{**case["ocfg"].__dict__, "c2f_enabled": True, "active_levels": active, "w_curvature": 0.0})
+    params = case["params"]
+    pp = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out_ref = port.render_rays(pp, ocfg, case["center"], case["ray_unit"], case["light"], rands=case["rands"],
+                               training=True, progress=case["progress"], keep=True)
+    port.total_loss(ocfg, out_ref, case["targets"])[0].backward()
+    eng = RenderEngine(product_cfg(ocfg, precision=1 if prec == "bf16" else 0))
+    eng.set_active_levels(active)
+    p = {k: cu(v) for k, v in params.items()}
+    eng.pack_weights(p)
+    c, r, l = cu(case["center"][0]), cu(case["ray_unit"][0]), cu(case["light"][0])
+    near, far, outside = eng.bounds(c, r)
+    res, ctx = eng.forward(p, c, r, l, cu(out_ref["dists"][0, :, :, 0]), near, far, outside, True, case["progress"])
+    R = 128
+    tol = dict(fp32=(1e-3, 2e-5, 5e-3), bf16=(2e-2, 2e-2, 6e-2))[prec]
+    assert torch.allclose(res["sdf"].cpu()[:R * 128].view(R, 128), out_ref["sdfs"][0, :, :, 0], rtol=1e-3, atol=1e-5)
+    out = res["out"].cpu()
+    for k, (a, b) in dict(rgb=(0, 3), o_r=(3, 6), o_s=(6, 7), o_re=(7, 10)).items():
+        assert torch.allclose(out[:, a:b], out_ref[k][0].detach(), rtol=tol[0], atol=tol[1]), k
+    # the masked levels matter: the same weights with every level active give a visibly different SDF
+    full = port.render_rays(params, port.PathConfig(**{**ocfg.__dict__, "c2f_enabled": False}), case["center"],
+                            case["ray_unit"], case["light"], rands=case["rands"], training=True, progress=0.5, keep=True)
+    assert float((full["sdfs"] - out_ref["sdfs"]).detach().abs().max()) > 1e-3
+    tg = {k: cu(v[0]) for k, v in case["targets"].items()}
+    _, d_out, d_grad, d_hess = eng.losses(loss_cfg(ocfg), res["out"], res["gradients"], res["hessians"], outside, tg)
+    grads = eng.backward(p, ctx, d_out, d_grad, d_hess, None)
+    for k, v in pp.items():
+        g = grads[k].cpu().view_as(v.grad)
+        err = float((g - v.grad).norm() / (v.grad.norm() + 1e-30))
+        assert err < tol[2], (k, err)
+    # inactive levels: exactly zero table gradient (oracle and product)
+    F, lv = ocfg.feat_per_level, eng.grid.level
+    first_masked = int(lv[active].offset) * F
+    tgrad = grads["neural_sdf.tcnn_encoding.params"].cpu().view(-1)
+    assert float(tgrad[first_masked:].abs().max()) == 0.0 and float(tgrad[:first_masked].abs().max()) > 0.0
+    assert float(pp["neural_sdf.tcnn_encoding.params"].grad.view(-1)[first_masked:].abs().max()) == 0.0
