@@ -134,3 +134,26 @@ def test_ray_generation_matches_reference():
         assert torch.allclose(c, c_ref, rtol=1e-6, atol=1e-6)
         assert torch.allclose(r, r_ref, rtol=1e-5, atol=1e-6)
         assert torch.allclose(l, l_ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["syn_hotdog_a", "syn_hotdog_b"])
+def test_c2f_schedule_matches_reference(name):
+    """Host logic of SURVEY 8a row a7: active levels and the numerical-gradient epsilon per iteration
+    (modules.py:97-107, driven by neuralangelo/trainer.py:65-76) of the drop-in NeuralSDF vs the reference's."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.model import Model
+    over = {"model.object.sdf.encoding.hashgrid.dict_size": 14}
+    cfg_ref = ref_import.load_config(name, over)
+    ref = ref_import.build_model(cfg_ref).neural_sdf
+    cfg = config.experiment(name, dict_size=14)
+    ours = Model(cfg.model, cfg.data).neural_sdf
+    assert list(ours.resolutions) == list(ref.resolutions)
+    for warm in (0, cfg_ref.optim.sched.warm_up_end):
+        ref.warm_up_end = ours.warm_up_end = warm
+        for it in (0, 1, 4999, 5000, 9999, 10000, 12345, 45000, 79999, 80000, 500000):
+            ref.set_active_levels(it)
+            ref.set_normal_epsilon()
+            ours.set_active_levels(it)
+            ours.set_normal_epsilon()
+            assert (ours.active_levels, ours.anneal_levels) == (ref.active_levels, ref.anneal_levels), (warm, it)
+            assert ours.normal_eps == ref.normal_eps, (warm, it)
