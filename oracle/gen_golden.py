@@ -164,9 +164,32 @@ def gen_light_visibility(name, R=64, seed=3):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
 
 
+def gen_inference(name, H=12, W=14, seed=3):
+    """Model.inference of the reference (NeuralLumen/model.py:60-83): full-image eval render in chunks, depth =
+    composited distance / |ray|, camera-space normal map, [B,HW,C] -> [B,C,H,W] maps."""
+    over = {"model.object.sdf.encoding.hashgrid.dict_size": 14, "data.val.image_size": [H, W],
+            "model.render.rand_rays_val": 50}  # 168 rays in chunks of 50: ragged last chunk
+    cfg_ref = ref_import.load_config("syn_hotdog_b", over)
+    ocfg = port.PathConfig(log2_hashmap_size=14)
+    p = port.init_params(ocfg, seed=seed, generic=False)
+    model = ref_import.build_model(cfg_ref, progress=1.0, training=False)
+    model.load_state_dict(p, strict=True)
+    pose = torch.tensor([[[0.96, 0.0, 0.28, 0.05], [0.0, -1.0, 0.0, 0.02], [0.28, 0.0, -0.96, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[17.0, 0.0, W / 2], [0.0, 17.0, H / 2], [0.0, 0.0, 1.0]]])
+    pose_light = torch.tensor([[[1.0, 0, 0, 1.0], [0, 1.0, 0, -2.0], [0, 0, 1.0, 3.0]]], dtype=torch.float32)
+    data = dict(pose=pose, intr=intr, pose_light=pose_light, idx=torch.zeros(1, dtype=torch.long))
+    out = model.inference(data)
+    store = dict(pose=pose.numpy(), intr=intr.numpy(), pose_light=pose_light.numpy(), image_size=np.array([H, W]),
+                 params_sha256=np.frombuffer(params_digest(p).encode(), dtype=np.uint8), seed=np.array(seed))
+    for k in ("rgb_map", "opacity_map", "depth_map", "normal_map", "o_r_map", "o_s_map", "o_re_map", "outside"):
+        store[k] = out[k].numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **store)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_light_visibility("light_visibility_hotdog_b")
+    gen_inference("inference_hotdog_b")
     gen_sampling()
     gen_hash_index()
     t14 = {"model.object.sdf.encoding.hashgrid.dict_size": 14}
