@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 
 class GradReducer:
-    def __init__(self, model, world_size=None, level_slices=None, side_stream=True, comm_sms=8):
+    def __init__(self, model, world_size=None, level_slices=None, side_stream=True, comm_sms=32):
         self.comm_sms = comm_sms
         self.model = model
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
