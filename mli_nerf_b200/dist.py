@@ -36,6 +36,7 @@ class GradReducer:
         self.peer = None  # PeerTableReducer (set by attach)
         self._engine = None
         self._limit_sms = False
+        self._hooked = None
 
     # -- overlap of the hash-table gradient exchange with the rest of the backward pass ------------------------------
     def attach(self, engine):
@@ -112,17 +113,26 @@ class GradReducer:
             with torch.cuda.stream(self.stream):
                 self._avg(flat[a:b])
         self._early[flat.data_ptr()] = self._early.get(flat.data_ptr(), 0) + (b - a)
+        self._hooked = flat  # the exchange runs in place on this buffer: the parameter's .grad must alias it
 
     def _buckets(self):
         """(big tensors reduced in place, list of small grads flattened into one bucket)."""
         big, small = [], []
+        hooked, self._hooked = self._hooked, None
+        aliased = hooked is None
         for n, p in self.model.named_parameters():
             if p.grad is None:
                 continue
             if self._early.get(p.grad.data_ptr(), 0) == p.grad.numel():
+                aliased = aliased or p.grad.data_ptr() == hooked.data_ptr()
                 continue  # every slab of this gradient already went through the hook during backward
             (big if p.grad.numel() >= (1 << 22) else small).append(p.grad)
         self._early = {}
+        if not aliased:
+            # e.g. backward() accumulated into an existing .grad (zero_grad(set_to_none=False), micro-batching): the
+            # parameter then holds a copy taken while the in-place exchange of the hooked buffer was still in flight
+            raise RuntimeError("the hash-table gradient exchanged during backward is not the parameter's .grad: clear the "
+                               "gradients with set_to_none=True before every backward, or do not attach() the engine")
         return big, small
 
     def allreduce_grads(self):

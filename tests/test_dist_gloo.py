@@ -61,6 +61,16 @@ def _worker_hook(rank, world, port_no, out):
     model["head"].weight.grad = torch.randn(3, 7, generator=g)
     red.allreduce_grads()
     torch.save({k: p.grad for k, p in model.named_parameters() if p.grad is not None}, out + f".{rank}")
+    # a .grad that does not alias the buffer the hook exchanged (accumulation into an existing gradient) is refused
+    for a, b in ((0, n // 2), (n // 2, n)):
+        eng.table_grad_hook(tg, a, b)
+    model["table"].weight.grad = tg.clone().view_as(model["table"].weight)
+    try:
+        red.allreduce_grads()
+        refused = False
+    except RuntimeError:
+        refused = True
+    assert refused
     dist.destroy_process_group()
 
 
