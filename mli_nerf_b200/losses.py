@@ -8,14 +8,23 @@ para_regularize_re_loss); ``fused_losses`` is what a maintainer calls instead of
 from . import _lib
 
 
-def loss_cfg_from_trainer(cfg_trainer):
+def loss_cfg_from_trainer(cfg_trainer, weights=None):
+    """`weights`: the trainer's LIVE `self.weights` dict (projects/nerf/trainers/base.py:47 keeps the non-zero entries of
+    cfg.trainer.loss_weight; projects/neuralangelo/trainer.py:56-63 re-schedules `curvature` every iteration when
+    coarse-to-fine is on).  Pass it from inside the trainer; without it the static YAML weights are used."""
     w = cfg_trainer.loss_weight
     c = _lib.LossCfg()
-    c.w_render = float(getattr(w, "render", 0.0))
-    c.w_eikonal = float(getattr(w, "eikonal", 0.0))
-    c.w_curvature = float(getattr(w, "curvature", 0.0))
-    c.w_intrinsic = float(getattr(w, "intrinsic", 0.0))
-    c.w_regularize_re = float(getattr(w, "regularize_re", 0.0))
+
+    def weight(name):
+        if weights is not None:
+            return float(weights.get(name, 0.0))  # a loss that is not in self.weights does not enter the total
+        return float(getattr(w, name, 0.0))
+
+    c.w_render = weight("render")
+    c.w_eikonal = weight("eikonal")
+    c.w_curvature = weight("curvature")
+    c.w_intrinsic = weight("intrinsic")
+    c.w_regularize_re = weight("regularize_re")
     c.has_intrinsic = int(hasattr(w, "intrinsic"))
     pi = getattr(cfg_trainer, "para_intrinsic_loss", None)
     rs = getattr(pi, "weight_map_range_shading", (0.25, 1.0)) if pi is not None else (0.25, 1.0)

@@ -157,3 +157,83 @@ def test_c2f_schedule_matches_reference(name):
             ours.set_normal_epsilon()
             assert (ours.active_levels, ours.anneal_levels) == (ref.active_levels, ref.anneal_levels), (warm, it)
             assert ours.normal_eps == ref.normal_eps, (warm, it)
+
+
+@pytest.mark.parametrize("name", ["syn_hotdog_b", "NRHints_Pikachu_b", "syn_hotdog_a"])
+def test_trainer_losses_match_reference(name):
+    """Pins port.total_loss AND mli_nerf_b200.losses.loss_cfg_from_trainer on the reference trainer's own
+    `_compute_loss(mode='train')` + the weighting of `_get_total_loss` (projects/NeuralLumen/trainer.py:56-71,133-149;
+    imaginaire/trainers/base.py:534-544), incl. the live curvature weight of neuralangelo/trainer.py:56-63."""
+    import sys
+    import types
+    from functools import partial
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    if "torchinfo" not in sys.modules:
+        try:
+            __import__("torchinfo")
+        except Exception:
+            stub = types.ModuleType("torchinfo")
+            stub.summary = lambda *a, **k: None
+            sys.modules["torchinfo"] = stub
+    ref = ref_import.load()
+    from projects.NeuralLumen import trainer as ref_trainer
+    cfg_ref = ref_import.load_config(name, {"model.object.sdf.encoding.hashgrid.dict_size": 14})
+    mode = getattr(cfg_ref.model.object.rgb, "network_mode", None)
+    box = getattr(cfg_ref.data, "bounding_type", None) == "box"
+    kw = dict(log2_hashmap_size=14, network_mode=mode)
+    if box:
+        kw.update(bounding="box", aabb=tuple(cfg_ref.data.bounding_box_aabb))
+    kw.update(white_background=bool(cfg_ref.model.background.white))
+    ocfg0 = port.PathConfig(**kw)
+    p = port.init_params(ocfg0, seed=5, generic=True, table_scale=5e-3)
+    model = ref_import.build_model(cfg_ref, progress=0.5, iteration=10 ** 9, training=True)
+    model.load_state_dict(p, strict=True)
+    R = 24
+    center, ray_unit, light = port.synthetic_rays(R, seed=6)
+    if box:
+        center = center * 0.5
+        ray_unit = torch.nn.functional.normalize(-center, dim=-1)
+    out = model.render_rays_lumen(center, ray_unit, light, stratified=False)
+    targets = port.synthetic_targets(R, seed=7)
+    # the trainer object without its CUDA / dataloader / wandb constructor: the attributes _compute_loss reads, built the
+    # way the constructors build them (projects/nerf/trainers/base.py:47; NeuralLumen/trainer.py:56-71)
+    tr = object.__new__(ref_trainer.Trainer)
+    tr.criteria = {"render": torch.nn.L1Loss()}
+    tr.weights = {k: v for k, v in cfg_ref.trainer.loss_weight.items() if v}
+    tr.losses, tr.metrics = {}, {}
+    if hasattr(cfg_ref.trainer.loss_weight, "intrinsic"):
+        pi = cfg_ref.trainer.para_intrinsic_loss
+        tr.criteria_intrinsic = partial(ref.lumen_utils.intrinsic_loss,
+                                        weight_map_range_shading=tuple(pi["weight_map_range_shading"]),
+                                        weight_map_range_visibility=tuple(pi["weight_map_range_visibility"]),
+                                        factor_ref=pi["factor_ref"], factor_sha=pi["factor_sha"])
+    if hasattr(cfg_ref.trainer.loss_weight, "regularize_re"):
+        pr = cfg_ref.trainer.para_regularize_re_loss
+        tr.criteria_regularize_re = partial(ref.lumen_utils.regularize_re_loss, factor_negative=pr["factor_negative"],
+                                            factor_positive=pr["factor_positive"],
+                                            exponent_positive=pr["exponent_positive"])
+    if cfg_ref.model.object.sdf.encoding.coarse2fine.enabled:  # live curvature weight (stage a)
+        tr.warm_up_end = cfg_ref.optim.sched.warm_up_end
+        tr.model_module = model
+        model.neural_sdf.warm_up_end = tr.warm_up_end
+        model.neural_sdf.set_active_levels(40000)
+        ref_trainer.Trainer.get_curvature_weight(tr, 40000, cfg_ref.trainer.loss_weight.curvature)
+        assert tr.weights["curvature"] != cfg_ref.trainer.loss_weight.curvature
+    tr._compute_loss({**out, **targets}, mode="train")
+    total_ref = sum(tr.losses[k] * tr.weights[k] for k in tr.weights if k in tr.losses)
+    # ours: the same trainer config through loss_cfg_from_trainer (+ the live weights), evaluated by the oracle
+    lc = loss_cfg_from_trainer(config.experiment(name, dict_size=14).trainer, weights=tr.weights)
+    ocfg = port.PathConfig(**{**ocfg0.__dict__, "w_render": lc.w_render, "w_eikonal": lc.w_eikonal,
+                              "w_curvature": lc.w_curvature, "w_intrinsic": lc.w_intrinsic,
+                              "w_regularize_re": lc.w_regularize_re, "range_shading": tuple(lc.range_sha),
+                              "range_visibility": tuple(lc.range_vis), "factor_ref": lc.factor_ref,
+                              "factor_sha": lc.factor_sha, "factor_negative": lc.factor_negative,
+                              "factor_positive": lc.factor_positive, "exponent_positive": lc.exponent_positive})
+    tg = targets if "intrinsic" in tr.weights else {"image_sampled": targets["image_sampled"]}
+    total, losses, _ = port.total_loss(ocfg, out, tg)
+    for k in tr.weights:
+        if k in tr.losses:
+            assert torch.allclose(losses[k], tr.losses[k], rtol=1e-5, atol=1e-8), k
+    assert torch.allclose(total, total_ref, rtol=1e-5, atol=1e-8)
+    assert set(k for k in tr.weights if k in tr.losses) >= {"render", "eikonal", "curvature"}
