@@ -841,3 +841,51 @@ def test_coarse_to_fine_partial_levels(lib, prec):
     tgrad = grads["neural_sdf.tcnn_encoding.params"].cpu().view(-1)
     assert float(tgrad[first_masked:].abs().max()) == 0.0 and float(tgrad[:first_masked].abs().max()) > 0.0
     assert float(pp["neural_sdf.tcnn_encoding.params"].grad.view(-1)[first_masked:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_model_stage_a_partial_coarse_to_fine(lib, prec):
+    """The drop-in Model on the stage-a config (single rgb head, coarse-to-fine) at an iteration where only some levels
+    are open: the trainer-side calls set_active_levels / set_normal_epsilon (neuralangelo/trainer.py:65-76) must reach
+    the kernels (level mask + tap epsilon)."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.model import Model
+    cfg = config.experiment("syn_hotdog_a", dict_size=14, rand_rays=64)
+    cfg.model.render.stratified = False
+    cfg.model.mli_precision = prec
+    model = Model(cfg.model, cfg.data)
+    iteration = 37000
+    model.neural_sdf.warm_up_end = 5000
+    model.neural_sdf.set_active_levels(iteration)
+    model.neural_sdf.set_normal_epsilon()
+    active, eps = int(model.neural_sdf.active_levels), float(model.neural_sdf.normal_eps)
+    assert 4 <= active < 16 and eps > 1.0 / 2048
+    ocfg = port.PathConfig(log2_hashmap_size=14, network_mode=None, c2f_enabled=True, active_levels=active, normal_eps=eps)
+    params = port.init_params(ocfg, seed=0, generic=True, table_scale=5e-3)
+    model.load_state_dict(params)
+    model = model.cuda().train()
+    model.progress = iteration / 500000
+    R = 96
+    center, ray_unit, light = port.synthetic_rays(R, seed=21)
+    with torch.no_grad():
+        out = model.render_rays_lumen(cu(center), cu(ray_unit), cu(light), stratified=False)
+        ref = port.render_rays(params, ocfg, center, ray_unit, light, rands=None, training=True, progress=model.progress)
+        # the same weights with every level open give a different picture: the mask is really applied
+        full = port.render_rays(params, port.PathConfig(**{**ocfg.__dict__, "c2f_enabled": False}), center, ray_unit,
+                                light, rands=None, training=True, progress=model.progress)
+    assert set(k for k, v in out.items() if v is not None and not k.startswith("_")) == \
+        set(k for k, v in ref.items() if v is not None)
+    assert torch.equal(out["outside"].cpu(), ref["outside"])
+    tol = 1e-3 if prec == "fp32" else 2e-2
+    err = (out["rgb"].cpu() - ref["rgb"]).abs().amax(dim=-1).view(-1)
+    assert float(err.max()) < 5e-2 and float((err < tol).float().mean()) >= 0.9, err
+    assert float((full["gradients"] - ref["gradients"]).abs().max()) > 1e-2
+    if prec == "fp32":
+        # numerical gradients at the partially annealed epsilon, on the rays whose independently drawn samples coincide
+        # (in tensor-core mode too few rays sample bit-identically end to end; its gradients are compared with the
+        # oracle's distances fed in by test_coarse_to_fine_partial_levels)
+        same = (out["dists"].cpu() - ref["dists"]).abs().amax(dim=(2, 3))[0] < 1e-6
+        inside = ~ref["outside"][0, :, 0] & same
+        assert int(inside.sum()) > R // 8
+        g_got, g_ref = out["gradients"].cpu()[0][inside], ref["gradients"][0][inside]
+        assert float((g_got - g_ref).norm() / g_ref.norm()) < 2e-3
