@@ -64,7 +64,8 @@ def test_state_dict_layout_matches_reference():
 def test_resolved_config_values_match_reference():
     """mli_nerf_b200.config reproduces the values the reference's Config() resolves for the shipped YAMLs."""
     from mli_nerf_b200 import config
-    for name in ("syn_hotdog_b", "NRHints_Pikachu_b", "rene_savannah_b", "syn_hotdog_a"):
+    for name in ("syn_hotdog_b", "NRHints_Pikachu_b", "rene_savannah_b", "syn_hotdog_a", "NRHints_Pikachu_a",
+                 "rene_savannah_a"):
         ref = ref_import.load_config(name)
         ours = config.experiment(name)
         r, o = ref.model, ours.model
