@@ -11,6 +11,8 @@ import math
 import os
 from functools import partial
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -82,6 +84,20 @@ class NeuralSDF(torch.nn.Module):
         self.anneal_levels = enc.levels
         self.warm_up_end = 0
         self.normal_eps = 1.0 / self.resolutions[-1]
+
+    def __getstate__(self):  # the back-reference to the owning Model is re-created by Model.__setstate__
+        state = dict(self.__dict__)
+        state.pop("_owner", None)
+        return state
+
+    def sdf(self, points_3D):
+        """`neural_sdf.sdf(x)` (modules.py:73-74) -- what scripts/extract_mesh.py:101 calls; the query runs in the owning
+        Model's engine (encode + SDF-trunk kernels), see Model.sdf."""
+        owner = self.__dict__.get("_owner")
+        model = owner() if owner is not None else None
+        if model is None:
+            raise _lib.MliError("NeuralSDF.sdf: this module is not attached to a mli_nerf_b200 Model")
+        return model.sdf(points_3D)
 
     def set_active_levels(self, current_iter=None):  # modules.py:97-100
         c2f = self.cfg_sdf.encoding.coarse2fine
@@ -191,6 +207,7 @@ class Model(torch.nn.Module):
         if sdf_cfg.gradient.taps not in (4, 6):
             raise ValueError("Only support 4 or 6 taps.")
         self.neural_sdf = NeuralSDF(sdf_cfg)
+        self.neural_sdf.__dict__["_owner"] = weakref.ref(self)  # plain attribute: no module cycle, not in the state_dict
         self.rgb_network_mode = getattr(cfg_model.object.rgb, "network_mode", None)
         self.neural_rgb = LumenRGB(cfg_model.object.rgb, feat_dim=sdf_cfg.mlp.hidden_dim,
                                    appear_embed=cfg_model.appear_embed)
@@ -239,6 +256,15 @@ class Model(torch.nn.Module):
     # -- trainer-facing helpers (imaginaire/models/base.py:16-30; NeuralLumen/model.py:422-438) ---------------------
     def device(self):
         return next(self.parameters()).device
+
+    def __getstate__(self):  # engines hold CUDA streams / ctypes structs: rebuilt lazily after unpickling / deepcopy
+        state = dict(self.__dict__)
+        state["_engine"] = None
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.neural_sdf.__dict__["_owner"] = weakref.ref(self)
 
     def get_param_groups(self, cfg_optim):
         if hasattr(cfg_optim, "partial_training"):

@@ -88,3 +88,25 @@ def test_fused_adamw_has_no_cpu_path():
     assert float(p.detach().abs().max()) == 0.0
     with pytest.raises(ValueError):
         FusedAdamW([p], lr=-1.0)
+
+
+def test_neural_sdf_query_delegates_and_model_copies_cleanly():
+    """`model.neural_sdf.sdf(x)` is what the reference's mesh script calls (scripts/extract_mesh.py:101): it must reach the
+    owning Model's engine (here: refuse on CPU, no fallback); the back-reference must survive deepcopy / pickling and must
+    not leak into the state_dict."""
+    import copy
+    import io
+    cfg = config.experiment("syn_hotdog_b", dict_size=14)
+    model = Model(cfg.model, cfg.data)
+    assert not [k for k in model.state_dict() if "owner" in k]
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.MliError):
+            model.neural_sdf.sdf(torch.zeros(4, 3))
+    clone = copy.deepcopy(model)
+    assert clone.neural_sdf.__dict__["_owner"]() is clone and model.neural_sdf.__dict__["_owner"]() is model
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    again = torch.load(buf, weights_only=False)
+    assert again.neural_sdf.__dict__["_owner"]() is again
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), again.state_dict().values()))
