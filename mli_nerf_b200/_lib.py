@@ -233,6 +233,18 @@ def call(name, *args):
 def _call(name, *args):
     lib = load()
     sig = _SIGS[name]
+    # device guard: every tensor of a call lives on ONE GPU and the launch goes to that GPU's current stream, whatever
+    # the caller's current device is (a model on cuda:1 driven from a process whose current device is cuda:0)
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            if dev is None:
+                dev = a.device.index
+            elif a.device.index != dev:
+                raise MliError(f"{name}: tensors on different devices (cuda:{dev} and cuda:{a.device.index})")
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call(name, *args)
     if len(args) == len(sig) - 1:
         args = args + (stream_ptr(),)
     if len(args) != len(sig):

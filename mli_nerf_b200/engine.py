@@ -268,25 +268,8 @@ class RenderEngine:
             j0 += odim
         W["bh"] = [torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for h in self.heads]) for l in range(4)]
         W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
-        if self.tc:  # bf16 TCL copies (tile height = the GEMM's N tile) for the tensor-core layers
-            T = {}
-            # SDF layer 0 as split-bf16 (hi | lo) for the 3-product trunk GEMM; its transpose (encoding columns only)
-            # in plain bf16 for the data-gradient GEMM
-            T["W0s"] = self._tcl(HID, 2 * K0_CH, 256)
-            call("mli_tc_to_tcl_split", W["W0"], K0_PAD, HID, K0_PAD, T["W0s"], 256, 2 * K0_CH, 0, K0_CH, K0_CH)
-            T["W0t_enc"] = self._to_tcl(W["W0t"], HID, 128, HID, self._tcl(128, 32, 128), 128)
-            T["W1"] = self._to_tcl(W["W1"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
-            T["W1t"] = self._to_tcl(W["W1t"], HID, HID, HID, self._tcl(HID, 32, 256), 256)
-            T["Wh0"] = self._to_tcl(W["Wh0"], KH_PAD, nh * HID, KH_PAD, self._tcl(nh * HID, KH_PAD // 8, 256), 256)
-            T["Wh0t_feat"] = self._to_tcl(W["Wh0t"], nh * HID, HID, nh * HID, self._tcl(HID, nh * 32, 256), 256)
-            T["Wh0t_x"] = self._to_tcl(W["Wh0t"][XH_OFF:], nh * HID, KH_PAD - XH_OFF, nh * HID,
-                                       self._tcl(KH_PAD - XH_OFF, nh * 32, KH_PAD - XH_OFF), KH_PAD - XH_OFF)
-            T["Whl"] = [self._to_tcl(W["Whl"][l], HID, nh * HID, HID, self._tcl(nh * HID, 32, 256), 256) for l in range(3)]
-            T["Whlt"] = [self._to_tcl(W["Whlt"][l], HID, nh * HID, HID, self._tcl(nh * HID, 32, 256), 256) for l in range(3)]
-            W["T"] = T
         self.W = W
         return W
-
 
     def _wn_specs(self):
         """(v name, N, K, col_map tensor, row_off) of every weight-normalised matrix, in a fixed order."""

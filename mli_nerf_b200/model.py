@@ -260,6 +260,9 @@ class Model(torch.nn.Module):
     def __getstate__(self):  # engines hold CUDA streams / ctypes structs: rebuilt lazily after unpickling / deepcopy
         state = dict(self.__dict__)
         state["_engine"] = None
+        state.pop("_graph_state", None)   # captured CUDA graphs / their static buffers do not travel
+        state.pop("_graph_last_key", None)
+        state.pop("_last_render", None)
         return state
 
     def __setstate__(self, state):
@@ -298,8 +301,10 @@ class Model(torch.nn.Module):
         R = ray_idx.shape[1] if ray_idx is not None else image_size[0] * image_size[1]
         f = partial(torch.empty, dtype=torch.float32, device=pose.device)
         center, ray_unit, light, norm = f(B * R, 3), f(B * R, 3), f(B * R, 3), f(B * R)
+        if ray_idx is not None:  # the kernel reads int64 indices
+            ray_idx = ray_idx.to(device=pose.device, dtype=torch.int64).contiguous()
         _lib.call("mli_rays_from_pose", pose.contiguous().float(), intr.contiguous().float(),
-                  pose_light.contiguous().float(), ray_idx.contiguous() if ray_idx is not None else None, B, R,
+                  pose_light.contiguous().float(), ray_idx, B, R,
                   int(image_size[1]), center, ray_unit, norm, light)
         return center, ray_unit, light, norm
 
@@ -355,18 +360,28 @@ class Model(torch.nn.Module):
             res["gradient"] = extras[:, 1:4].view(B, R, 3)
             res["_dist"] = extras[:, 4:5].view(B, R, 1)
         if self.flag_light_visibility:  # NeuralLumen/model.py:325-334 (the stage-a export of pseudo shading labels)
-            if self.training:
-                raise NotImplementedError("light_visibility is built for the eval / export path (test_all_light)")
             lv, eng = self.para_light_visibility, self.engine
             with torch.no_grad():
+                if self.training:
+                    # training mode composites the gradient only when visibility is on (NeuralLumen/model.py:369-372);
+                    # the eval extras are not produced there, so the two per-ray blends are formed from the weights
+                    grad_c = (weights.view(B * R, N, 1) * gradients.view(B * R, N, 3)).sum(dim=1)
+                    blend = (weights.view(B * R, N) * dists.view(B * R, N)).sum(dim=1)
+                    res["gradient"] = grad_c.view(B, R, 3)
+                else:
+                    grad_c, blend = extras[:, 1:4].contiguous(), extras[:, 4].contiguous()
                 near, far, _ = eng.bounds(c, r)
                 aabb = None
                 if lv.visibility_bounding_type == "box":
-                    aabb = [float(v) for v in self.visibility_bounding_box_aabb]
+                    # get_dist_bounds_visibility intersects the light rays with the DATA box (`self.bounding_box_aabb`,
+                    # NeuralLumen/model.py:190), not with light_visibility.visibility_bounding_box_aabb
+                    if not hasattr(self, "bounding_box_aabb"):
+                        raise AttributeError("light_visibility.visibility_bounding_type='box' needs data.bounding_type='box' "
+                                             "(the reference reads self.bounding_box_aabb, NeuralLumen/model.py:190)")
+                    aabb = [float(v) for v in self.bounding_box_aabb]
                 vis, nxl, inter_dist, inter_mask = eng.light_visibility(
                     dict(zip(names, params))["neural_sdf.tcnn_encoding.params"], c, r, l, near, far,
-                    extras[:, 4].contiguous(), extras[:, 1:4].contiguous(), lv.camera_ray_type,
-                    getattr(lv, "visibility_sphere_radius", 1.0), aabb)
+                    blend, grad_c, lv.camera_ray_type, getattr(lv, "visibility_sphere_radius", 1.0), aabb)
             res["visibility"] = vis.view(B, R, 1).bool()
             res["normal_x_light"] = nxl.view(B, R, 1)
             res["pseudo_shading"] = res["normal_x_light"] * res["visibility"].float()
@@ -429,7 +444,8 @@ class Model(torch.nn.Module):
         near, far, outside = eng.bounds(c, r)
         dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], c, r, near, far, rands)
         res, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, self.progress)
-        tg = {k: v.reshape(B * R, v.shape[-1]) for k, v in data.items() if k.endswith("_sampled")}
+        tg = {k: v.reshape(B * R, v.shape[-1]).to(device=c.device, dtype=torch.float32).contiguous()
+              for k, v in data.items() if k.endswith("_sampled")}
         losses, d_out, d_grad, d_hess = eng.losses(loss_cfg, res["out"], res["gradients"], res["hessians"], outside, tg)
         need = set()
         for n, q in zip(names, params):
@@ -450,15 +466,26 @@ class Model(torch.nn.Module):
         return losses
 
     def _graphed_train_step(self, data, loss_cfg, after_backward=None):
+        """CUDA-graph replay of the step.  Host-side scalars (anneal ratio, tap epsilon, active levels, loss weights) are
+        baked into the captured launches, so the graph is keyed on them.  ONE graph is kept (the previous one is dropped
+        when the key changes) and a new key is only captured once it has been seen on two consecutive steps: while a
+        schedule moves every iteration (s_var anneal during the first anneal_end*max_iter iterations, the coarse-to-fine
+        warm-up of stage a) the steps run eagerly instead of re-capturing each time; the graph pays off on the static
+        part of training (stage b, and stage a after the anneal)."""
         tensors = {k: v for k, v in data.items() if isinstance(v, torch.Tensor) and v.is_cuda}
         eng = self.engine
         key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())),
                min(self.progress / self.anneal_end, 1.0), float(self.neural_sdf.normal_eps), int(eng.grid.active_levels),
                tuple(p.requires_grad for p in self.parameters()), bytes(loss_cfg), self.path_cfg.precision)
-        if not hasattr(self, "_graphs"):
-            self._graphs = {}
-        st = self._graphs.get(key)
+        st = self.__dict__.get("_graph_state")
+        if st is not None and st[0] != key:
+            st = None
+            self.__dict__["_graph_state"] = None  # frees the old graph and its private memory pool
         if st is None:
+            seen_before = self.__dict__.get("_graph_last_key") == key
+            self.__dict__["_graph_last_key"] = key
+            if not seen_before:  # moving schedule: do not capture yet
+                return self.fused_train_step(data, loss_cfg, after_backward=after_backward)
             static = {k: v.clone() for k, v in tensors.items()}
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -471,9 +498,9 @@ class Model(torch.nn.Module):
             with torch.cuda.graph(graph):
                 losses = self.fused_train_step(static, loss_cfg, after_backward=after_backward)
             grads = {n: p.grad for n, p in self.named_parameters() if p.grad is not None}
-            st = (graph, static, losses, grads)
-            self._graphs[key] = st
-        graph, static, losses, grads = st
+            st = (key, graph, static, losses, grads)
+            self.__dict__["_graph_state"] = st
+        _, graph, static, losses, grads = st
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
         graph.replay()

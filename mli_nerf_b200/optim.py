@@ -16,7 +16,23 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameter")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_scale=grad_scale))
+        # the inert torch.optim.AdamW group keys ride along so that a state_dict saved here loads into torch's AdamW
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False,
+                                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                                      decoupled_weight_decay=True, grad_scale=grad_scale))
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.AdamW checkpoint (the reference's): its param_groups carry no `grad_scale` (kept from
+        this optimizer) and may carry amsgrad / maximize / capturable flags -- the two that would change the update
+        rule are refused instead of being silently ignored."""
+        for g in state_dict["param_groups"]:
+            if g.get("amsgrad", False) or g.get("maximize", False) or not g.get("decoupled_weight_decay", True):
+                raise ValueError("FusedAdamW: checkpoints saved with amsgrad=True, maximize=True or coupled weight decay "
+                                 "are not supported")
+        scales = [g.get("grad_scale", 1.0) for g in self.param_groups]
+        super().load_state_dict(state_dict)
+        for g, s in zip(self.param_groups, scales):
+            g.setdefault("grad_scale", s)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -47,5 +63,5 @@ class FusedAdamW(torch.optim.Optimizer):
                         d.param, d.grad, d.exp_avg, d.exp_avg_sq, d.n = p.data_ptr(), g.data_ptr(), m.data_ptr(), \
                             v.data_ptr(), p.numel()
                     _lib.call("mli_adamw_step_batch", _lib.C.addressof(descs), len(part), group["lr"], b1, b2,
-                              group["eps"], group["weight_decay"], step, group["grad_scale"])
+                              group["eps"], group["weight_decay"], step, group.get("grad_scale", 1.0))
         return loss

@@ -414,9 +414,10 @@ def sphere_tracing_intersection(p, cfg, center, ray_unit, near, far, num_iters=2
 
 
 def light_visibility(p, cfg, center, ray_unit, pts_light, near, far, blend_dist, gradient,
-                     camera_ray_type="blend_z_sphere_tracing", radius=0.95):
-    """Model.get_light_visibility with type 'sphere_tracing' and a sphere visibility bound
-    (projects/NeuralLumen/model.py:133-200).  blend_dist = composite(dists, weights), gradient = composited gradient.
+                     camera_ray_type="blend_z_sphere_tracing", radius=0.95, aabb=None):
+    """Model.get_light_visibility with type 'sphere_tracing' (projects/NeuralLumen/model.py:133-200) and a sphere
+    visibility bound, or -- `aabb` given -- the box bound, which the reference takes from the DATA box
+    `self.bounding_box_aabb` (model.py:188-191).  blend_dist = composite(dists, weights), gradient = composited gradient.
     -> visibility (bool), normal_x_light, inter_dist, inter_mask   (all [B,R,1])"""
     if camera_ray_type == "blend_z_sphere_tracing":
         inter_dist, inter_pts, inter_mask = sphere_tracing_intersection(p, cfg, center, ray_unit, near, far,
@@ -431,13 +432,20 @@ def light_visibility(p, cfg, center, ray_unit, pts_light, near, far, blend_dist,
         raise NotImplementedError
     light_ray = inter_pts - pts_light
     light_ray_unit = F.normalize(light_ray, dim=-1)
-    # get_dist_bounds_visibility, sphere branch (model.py:192-197)
-    ctc = (pts_light * pts_light).sum(dim=-1, keepdim=True)
-    ctv = (pts_light * light_ray_unit).sum(dim=-1, keepdim=True)
-    disc = ctv ** 2 - (ctc - radius ** 2)
-    near_l = (-ctv - disc.sqrt()).relu()
-    far_l = -ctv + disc.sqrt()
-    outside_l = near_l.isnan()
+    if aabb is not None:  # get_dist_bounds_visibility, box branch (model.py:189-191; intersect_aabb, utils.py:86-123)
+        box = torch.tensor(aabb, dtype=torch.float32)
+        t0 = (box[:3] - pts_light) / light_ray_unit
+        t1 = (box[3:] - pts_light) / light_ray_unit
+        near_l = torch.minimum(t0, t1).amax(dim=-1, keepdim=True).clamp(min=0, max=1e10)
+        far_l = torch.maximum(t0, t1).amin(dim=-1, keepdim=True).clamp(min=0, max=1e10)
+        outside_l = far_l <= near_l
+    else:  # sphere branch (model.py:192-197)
+        ctc = (pts_light * pts_light).sum(dim=-1, keepdim=True)
+        ctv = (pts_light * light_ray_unit).sum(dim=-1, keepdim=True)
+        disc = ctv ** 2 - (ctc - radius ** 2)
+        near_l = (-ctv - disc.sqrt()).relu()
+        far_l = -ctv + disc.sqrt()
+        outside_l = near_l.isnan()
     near_l = torch.where(outside_l, torch.ones_like(near_l), near_l)
     far_l = torch.where(outside_l, torch.full_like(far_l, 1.2), far_l)
     far_tracing = light_ray.norm(dim=-1, keepdim=True) - 1e-3

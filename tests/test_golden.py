@@ -118,13 +118,18 @@ def test_port_reproduces_reference_render(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_cuda_reproduces_reference_render(name):
-    """CUDA path (through the C ABI) vs the reference's own outputs, fed the reference's sample distances."""
+def test_cuda_reproduces_reference_render(name, prec):
+    """CUDA path (through the C ABI) vs the reference's own outputs, fed the reference's sample distances.
+    fp32 mode: rtol 1e-3.  bf16 tcgen05 mode (the measured one), stated looser bounds: per-ray colours |err| <= 2e-2
+    (mean <= 3e-3), compositing weights |err| <= 2e-2, numerical gradients relative L2 <= 2e-3, losses 2 %, parameter
+    gradient norms 6 % (SDF-side: see `loose`)."""
     from mli_nerf_b200.engine import RenderEngine
     g, ocfg, p = case_params(name)
     training = bool(g["training"])
-    eng = RenderEngine(product_cfg(ocfg))
+    bf = prec == "bf16"
+    eng = RenderEngine(product_cfg(ocfg, precision=1 if bf else 0))
     pc = {k: v.cuda() for k, v in p.items()}
     eng.pack_weights(pc)
     c, r, l = (torch.from_numpy(g[k][0]).cuda() for k in ("center", "ray_unit", "light"))
@@ -135,30 +140,36 @@ def test_cuda_reproduces_reference_render(name):
     out = res["out"].cpu().numpy()
     R = c.shape[0]
     for k, (a, b) in dict(rgb=(0, 3), o_r=(3, 6), o_s=(6, 7), o_re=(7, 10)).items():
-        assert np.allclose(out[:, a:b], g["out_" + k][0], rtol=1e-3, atol=2e-5), k
-    assert np.allclose(res["weights"].cpu().numpy(), g["out_weights"][0, :, :, 0], rtol=1e-3, atol=2e-5)
+        if bf:
+            err = np.abs(out[:, a:b] - g["out_" + k][0])
+            assert err.max() < 2e-2 and err.mean() < 3e-3, (k, err.max(), err.mean())
+        else:
+            assert np.allclose(out[:, a:b], g["out_" + k][0], rtol=1e-3, atol=2e-5), k
+    assert np.allclose(res["weights"].cpu().numpy(), g["out_weights"][0, :, :, 0], rtol=1e-3, atol=2e-2 if bf else 2e-5)
     inside = ~g["out_outside"][0, :, 0]
     gr = res["gradients"].cpu().numpy().reshape(R, 128, 3)
     assert np.abs(gr[inside] - g["out_gradients"][0][inside]).max() < 2e-3 * np.abs(g["out_gradients"][0][inside]).max()
     if not training:
         ex = res["extras"].cpu().numpy()
-        assert np.allclose(ex[:, 0:1], g["out_opacity"][0], rtol=1e-3, atol=2e-5)
-        assert np.allclose(ex[:, 1:4], g["out_gradient"][0], rtol=2e-3, atol=2e-3)
+        assert np.allclose(ex[:, 0:1], g["out_opacity"][0], rtol=1e-3, atol=2e-2 if bf else 2e-5)
+        assert np.allclose(ex[:, 1:4], g["out_gradient"][0], rtol=2e-3, atol=2e-2 if bf else 2e-3)
         return
     tg = {k: v[0].cuda() for k, v in port.synthetic_targets(R, seed=int(g["seed"]) + 2).items()}
     losses, d_out, d_grad, d_hess = eng.losses(loss_cfg(ocfg), res["out"], res["gradients"], res["hessians"], outside, tg)
     lc = losses.cpu().numpy()
-    assert abs(lc[0] - float(g["loss_total"])) < 2e-3 * abs(float(g["loss_total"]))
+    assert abs(lc[0] - float(g["loss_total"])) < (2e-2 if bf else 2e-3) * abs(float(g["loss_total"]))
     for i, k in ((1, "render"), (2, "eikonal"), (4, "intrinsic"), (5, "regularize_re")):
-        assert abs(lc[i] - float(g["loss_" + k])) < 1e-3 * abs(float(g["loss_" + k])) + 1e-6, k
+        assert abs(lc[i] - float(g["loss_" + k])) < (2e-2 if bf else 1e-3) * abs(float(g["loss_" + k])) + 1e-6, k
     grads = eng.backward(pc, ctx, d_out, d_grad, d_hess, None)
     for k in p:
         gn, ref = float(grads[k].norm()), float(g["gnorm_" + k])
         loose = "neural_sdf" in k or k == "s_var"  # curvature seed = sign(laplacian): fp32-noise sensitive, see parity test
         scalar = grads[k].numel() == 1  # a scalar gradient is a heavily cancelling sum of the noisy per-sample terms
-        assert abs(gn - ref) < ((0.5 if scalar else 1e-1) if loose else 1e-2) * ref + 1e-9, (k, gn, ref)
+        tol_n = ((0.5 if scalar else 1.5e-1 if bf else 1e-1) if loose else 6e-2 if bf else 1e-2)
+        assert abs(gn - ref) < tol_n * ref + 1e-9, (k, gn, ref)
         if grads[k].numel() <= 4096 and not (loose and scalar):
-            assert rel_err(grads[k].cpu().reshape(-1), torch.from_numpy(g["grad_" + k]).reshape(-1)) < (1e-1 if loose else 5e-3), k
+            tol_e = (1.5e-1 if bf else 1e-1) if loose else (6e-2 if bf else 5e-3)
+            assert rel_err(grads[k].cpu().reshape(-1), torch.from_numpy(g["grad_" + k]).reshape(-1)) < tol_e, k
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -311,3 +311,39 @@ def test_dropin_model_builds_from_reference_config(name):
     for attr in ("warm_up_end", "set_active_levels", "set_normal_epsilon", "normal_eps", "growth_rate", "resolutions"):
         assert hasattr(ours.neural_sdf, attr), attr
     assert float(ours.neural_sdf.growth_rate) == float(ref.neural_sdf.growth_rate)
+
+
+def test_light_visibility_box_bound_matches_reference():
+    """visibility_bounding_type 'box': the reference intersects the light rays with the DATA box `bounding_box_aabb`
+    (NeuralLumen/model.py:188-191) -- pins the `aabb` branch of port.light_visibility, and through it the box the
+    drop-in Model hands to the kernels, on the live reference (rene_savannah_b shape, gamma-corrected pseudo shading)."""
+    over = {"model.object.sdf.encoding.hashgrid.dict_size": 14, "model.light_visibility.enabled": True,
+            "model.light_visibility.camera_ray_type": "sphere_tracing",
+            "model.light_visibility.visibility_bounding_type": "box",
+            "model.light_visibility.visibility_bounding_box_aabb": [-0.3, -0.21, -0.18, 0.3, 0.21, 0.18]}
+    cfg_ref = ref_import.load_config("rene_savannah_b", over)
+    aabb = tuple(float(v) for v in cfg_ref.data.bounding_box_aabb)
+    ocfg = port.PathConfig(log2_hashmap_size=14, bounding="box", aabb=aabb, white_background=False)
+    p = port.init_params(ocfg, seed=5, generic=False)
+    # shrink the geometric-init sphere (radius ~0.5 -> ~0.22) so that most of it lies inside the small data box
+    p["neural_sdf.mlp.linear_sdf.bias"] = torch.tensor([-0.3])
+    model = ref_import.build_model(cfg_ref, progress=1.0, training=False)
+    model.load_state_dict(p, strict=True)
+    R = 64
+    center, ray_unit, light = port.synthetic_rays(R, seed=6)
+    center = center * 0.5
+    ray_unit = torch.nn.functional.normalize(-center + 0.05 * torch.randn_like(center), dim=-1)
+    light = light * 0.3
+    with torch.no_grad():
+        ref_out = model.render_rays_lumen(center, ray_unit, light, stratified=False)
+        out = port.render_rays(p, ocfg, center, ray_unit, light, rands=None, training=False, progress=1.0, keep=True)
+        near, far, _ = port.dist_bounds(ocfg, center, ray_unit)
+        blend = port.composite(out["dists"], out["weights"])
+        vis, nxl, idist, imask = port.light_visibility(p, ocfg, center, ray_unit, light, near, far, blend, out["gradient"],
+                                                       "sphere_tracing", aabb=aabb)
+    assert 0 < int(ref_out["inter_mask"].sum()) <= R
+    assert torch.equal(ref_out["inter_mask"].bool(), imask)
+    assert torch.allclose(ref_out["inter_dist"], idist, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ref_out["normal_x_light"], nxl, rtol=1e-3, atol=1e-4)
+    assert float((ref_out["visibility"].bool() == vis).float().mean()) >= 0.97
+    assert 0 < int(vis.sum()) < R  # both outcomes occur
