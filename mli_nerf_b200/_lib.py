@@ -182,9 +182,20 @@ _PROFILE = None
 LAUNCH_COUNT = 0
 
 
-def profile_begin():
-    global _PROFILE
-    _PROFILE = {}
+_WORK_FN = None
+_WORK = None
+
+
+def profile_begin(work_fn=None):
+    """work_fn(name, args) -> (flops, bytes) or None: the caller's accounting of the algorithmic work of one call
+    (bench.py's per-kernel roofline); summed per entry point, read back with profile_work()."""
+    global _PROFILE, _WORK_FN, _WORK
+    _PROFILE, _WORK_FN, _WORK = {}, work_fn, {}
+
+
+def profile_work():
+    """-> {entry point: [flops, bytes]} accumulated since profile_begin(work_fn)."""
+    return dict(_WORK or {})
 
 
 def profile_end():
@@ -225,6 +236,12 @@ def call(name, *args):
         _call(name, *args)
         b.record()
         _PROFILE.setdefault(name, []).append((a, b))
+        if _WORK_FN is not None:
+            w = _WORK_FN(name, args)
+            if w is not None:
+                acc = _WORK.setdefault(name, [0.0, 0.0])
+                acc[0] += w[0]
+                acc[1] += w[1]
     else:
         _call(name, *args)
     LAUNCH_COUNT += _n_launches(name, args)

@@ -1,20 +1,27 @@
 """Ray-sharded multi-GPU training: one process per GPU, every rank renders its own rays against a full replica of the
-hash table + MLPs, and the only exchange per step is the all-reduce(mean) of the parameter gradients -- the DDP
-semantics of the reference (/root/reference/imaginaire/trainers/utils/get_trainer.py:80-88), owned explicitly here
-because the reference toggles requires_grad after the DDP wrap (projects/NeuralLumen/trainer.py:44-54).
+hash table + MLPs, and the only exchange per step is that of the parameter gradients.
 
-torch.distributed (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests) is the plumbing.  The 1.46 GB
-hash-table gradient is exchanged in per-level-group slabs as soon as the scatter kernel of a group has been launched; the
-~3.6 MB of MLP gradients travel as one flat NCCL bucket.
+Two exchanges of the 1.46 GB hash-table gradient (`GradReducer(table_mode=...)`, env MLI_TABLE_EXCHANGE):
 
-Table-gradient exchange (`PeerTableReducer`, default on CUDA): NCCL's all-reduce needs 32 resident CTAs to reach 2.55 ms
-for this payload at N = 2 (16 channels: 4.3 ms) and therefore cannot overlap with the weight-gradient GEMMs that own the
-SMs at that point of the step.  Here every rank maps its peers' gradient buffers (CUDA IPC) and moves the data with the
-copy engines instead: rank r owns shard r of each slab, pulls that shard of every peer's buffer over NVLink, sums
-(`mli_reduce_slots`), and pushes the mean back into every peer's buffer -- zero SMs for the transfers, inbound and outbound
-links busy at the same time.  Cross-rank ordering ("your scatter of this slab has finished", "every push has landed")
-is a one-element NCCL all-reduce enqueued in stream order.  Default for two ranks; with more ranks NCCL (in-switch
-reduction) is faster and stays the default -- `MLI_TABLE_ALLREDUCE=peer|nccl` overrides.
+* ``allreduce`` -- the DDP semantics of the reference (/root/reference/imaginaire/trainers/utils/get_trainer.py:80-88):
+  every rank ends the step with the full mean gradient; any optimizer can follow.  2 (W-1)/W x 1.46 GB per link
+  direction and step.
+* ``reduce_scatter`` (default of `make_reducer`) -- rank r ends the step with the mean gradient of ITS 1/W shard of every
+  level-group slab only ((W-1)/W x 1.46 GB per direction: half the bytes inside the fwd+bwd metric); the optimizer that
+  follows is `ShardedTableAdamW`: AdamW on the owned shard (1/W of the 10 GB optimizer pass, 1/W of the moment
+  memory) and an all-gather of the updated PARAMETERS.  Same arithmetic as all-reduce + dense AdamW: every table entry
+  is updated exactly once, by its owner, from the same mean gradient.
+
+The gradient slabs are exchanged as soon as the scatter kernel of a level group has been launched (engine hook), on a
+side stream, while the weight-gradient GEMMs run; the ~3.6 MB of MLP gradients travel as one flat NCCL bucket.
+torch.distributed (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests) is the plumbing.
+
+Transport (`PeerTableReducer`, default for two ranks): NCCL needs 32 resident CTAs to move this payload at full rate and
+therefore cannot overlap with the weight-gradient GEMMs that own the SMs at that point of the step.  Here every rank
+maps its peers' gradient buffers (CUDA IPC) and moves the data with the copy engines instead: rank r owns shard r of
+each slab, pulls that shard of every peer's buffer over NVLink, sums (`mli_reduce_slots`) -- zero SMs for the
+transfers.  Cross-rank ordering is a one-element NCCL all-reduce enqueued in stream order.  With more ranks NCCL
+(in-switch reduction) is faster and is the default -- `MLI_TABLE_ALLREDUCE=peer|nccl` overrides.
 """
 import os
 import sys
@@ -23,11 +30,28 @@ import torch
 import torch.distributed as dist
 
 
+def make_reducer(model, world, **kw):
+    """The gradient exchange bench.py / a trainer uses: reduce-scatter + rank-owned optimizer shard unless
+    MLI_TABLE_EXCHANGE=allreduce asks for the reference's DDP semantics."""
+    mode = os.environ.get("MLI_TABLE_EXCHANGE", "reduce_scatter")
+    return GradReducer(model, world, comm_sms=int(os.environ.get("MLI_COMM_SMS", "32")), table_mode=mode, **kw)
+
+
+def num_sms():
+    if torch.cuda.is_available():
+        return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return 148
+
+
 class GradReducer:
-    def __init__(self, model, world_size=None, level_slices=None, side_stream=True, comm_sms=32):
+    def __init__(self, model, world_size=None, level_slices=None, side_stream=True, comm_sms=32, table_mode="allreduce"):
+        if table_mode not in ("allreduce", "reduce_scatter"):
+            raise ValueError(f"table_mode {table_mode!r}: expected 'allreduce' or 'reduce_scatter'")
+        self.table_mode = table_mode
         self.comm_sms = comm_sms
         self.model = model
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.level_slices = level_slices  # [(start, end)] element ranges of the hash table per level (optional)
         self.stream = None
         if side_stream and torch.cuda.is_available():
@@ -36,33 +60,47 @@ class GradReducer:
         self.peer = None  # PeerTableReducer (set by attach)
         self._engine = None
         self._limit_sms = False
+        self._limited = False
         self._hooked = None
+        self._transport = "nccl"
+        # reduce_scatter mode: after exchange_grads(), [(elem_begin, elem_end, mean gradient of that owned range)]
+        self.table_grad_shards = []
+        self._shard_buf = None
+        self._shard_off = 0
 
     # -- overlap of the hash-table gradient exchange with the rest of the backward pass ------------------------------
     def attach(self, engine):
         """Have `engine` hand over each level group's slab of the hash-table gradient as soon as its scatter kernel has
-        been launched: the all-reduce of that slab then runs on the side stream (NCCL over NVLink) while the compute
-        stream continues with the next level group and the deferred weight-gradient GEMMs."""
+        been launched: the exchange of that slab then runs on the side stream (NCCL / copy engines over NVLink) while
+        the compute stream continues with the next level group and the deferred weight-gradient GEMMs."""
         engine.table_grad_hook = self._on_table_slab if self.world > 1 else None
         self._engine = engine
         # the table gradient is produced last; holding the weight-gradient GEMMs back until its scatter is launched gives
         # the exchange independent work to overlap with (MLI_WGRAD_LAST=0: single-GPU schedule, for A/B runs)
         engine.wgrad_after_scatter = self.world > 1 and os.environ.get("MLI_WGRAD_LAST", "1") == "1"
+        if self.world > 1 and dist.is_initialized():
+            # every rank must cut the table into the same slabs: the NCCL calls / tokens are matched by order
+            n_slabs = len(engine.level_groups()) if hasattr(engine, "level_groups") else 0
+            seen = [None] * self.world
+            dist.all_gather_object(seen, n_slabs)
+            if any(v != n_slabs for v in seen):
+                raise RuntimeError(f"GradReducer.attach: ranks disagree on the number of table slabs: {seen}")
         if self.world > 1 and torch.cuda.is_available():
             from . import _lib
-            # measured (bench.py, full-grad): N = 2  peer 7.05 ms / NCCL 7.42 ms per step;  N = 8  peer 10.26 ms / NCCL
-            # 9.32 ms (NCCL reduces inside the NVSwitch there; the copy engines reach only 400-460 GB/s inbound with
-            # seven sources) -> the peer exchange is the default for two ranks, NCCL beyond
+            # measured (bench.py, full-grad, all-reduce): N = 2  peer 7.05 ms / NCCL 7.42 ms per step;  N = 8  peer 10.26 ms
+            # / NCCL 9.32 ms (NCCL reduces inside the NVSwitch there; the copy engines reach only 400-460 GB/s inbound
+            # with seven sources) -> the peer transport is the default for two ranks, NCCL beyond
             mode = os.environ.get("MLI_TABLE_ALLREDUCE", "peer" if self.world == 2 else "nccl")
             backend = str(dist.get_backend())
             if dist.get_rank() == 0:
-                print(f"[mli] table-gradient exchange: {mode} (torch.distributed backend {backend})", file=sys.stderr,
-                      flush=True)
+                print(f"[mli] table-gradient exchange: {self.table_mode} over {mode} (torch.distributed backend {backend})",
+                      file=sys.stderr, flush=True)
             if mode == "peer" and "nccl" in backend:
                 try:
                     self.peer = PeerTableReducer(engine.n_table_params(), engine.device,
                                                  max_slabs=len(engine.level_groups()))
                     engine.table_grad_buffer = self.peer.buf  # the scatter writes straight into the IPC-shared buffer
+                    self._transport = "peer"
                 except _lib.MliError as e:  # raised on every rank or on none: all ranks take the NCCL exchange together
                     print(f"[mli] rank {dist.get_rank()}: {e}; using the NCCL exchange", file=sys.stderr, flush=True)
                     self.peer = None
@@ -70,13 +108,41 @@ class GradReducer:
             elif mode in ("peer", "nccl"):
                 # NCCL needs its 32 channels = 32 resident CTAs to move this payload at full rate (16 channels: 4.3 ms
                 # instead of 2.55 ms at N = 2) and a persistent GEMM CTA owns its SM's whole shared memory: from the
-                # first slab on, the persistent kernels of the step are launched on 148 - comm_sms SMs (_on_table_slab)
+                # first slab on, the persistent kernels of the step are launched on n_sms - comm_sms SMs (_on_table_slab)
                 self._limit_sms = True
             else:
                 raise _lib.MliError(f"MLI_TABLE_ALLREDUCE={mode}: expected peer or nccl")
+        if self.table_mode == "reduce_scatter" and self.world > 1 and self.peer is None and hasattr(engine, "n_table_params"):
+            n = engine.n_table_params()
+            dev = engine.device if torch.cuda.is_available() else "cpu"
+            self._shard_buf = torch.empty((n + self.world - 1) // self.world + 64, dtype=torch.float32, device=dev)
+
+    def describe(self):
+        return {"table": self.table_mode, "transport": self._transport, "mlp": "all-reduce (one flat bucket)",
+                "world": self.world}
+
+    def warm_up(self, iters=24):
+        """Communicator start-up, NOT training steps: the first few dozen large NCCL collectives of a process run well below
+        their steady-state rate (measured at N = 8: 13.4 ms per step for steps 4-23, 9.5 ms from step ~40 on).  Runs the
+        exchange's own collective `iters` times on a scratch buffer of one slab's size."""
+        if self.world <= 1 or not torch.cuda.is_available() or self.peer is not None or self._engine is None:
+            return
+        groups = self._engine.level_groups()
+        n = max(e1 - e0 for _, _, e0, e1 in groups)
+        n -= n % self.world
+        x = torch.zeros(n, dtype=torch.float32, device=self._engine.device)
+        y = torch.zeros(n // self.world, dtype=torch.float32, device=self._engine.device)
+        for _ in range(iters):
+            if self.table_mode == "reduce_scatter":
+                dist.reduce_scatter_tensor(y, x, op=dist.ReduceOp.AVG)
+                dist.all_gather_into_tensor(x, y)
+            else:
+                dist.all_reduce(x, op=dist.ReduceOp.AVG)
+        torch.cuda.synchronize()
 
     def close(self):
         """Unmap / free the peer-shared table-gradient buffer (collective: every rank calls it)."""
+        self._restore_sms()
         if self.peer is None:
             return
         for p in self.model.parameters():
@@ -85,8 +151,15 @@ class GradReducer:
         if self._engine is not None:
             self._engine.table_grad_buffer = None
             self._engine.table_grad_hook = None
+        self.table_grad_shards = []
         self.peer.close()
         self.peer = None
+
+    def _restore_sms(self):
+        if self._limited:
+            from . import _lib
+            _lib.set_sm_limit(num_sms())
+            self._limited = False
 
     def _avg(self, t):
         if dist.get_backend() == "nccl":
@@ -95,23 +168,46 @@ class GradReducer:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             t.mul_(1.0 / self.world)
 
+    def _reduce_scatter_avg(self, out, t):
+        """out [n/W] = mean over ranks of t[rank*n/W : (rank+1)*n/W]."""
+        if dist.get_backend() == "nccl":
+            dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.AVG)
+        else:  # gloo (CPU tests) has no reduce-scatter: all-reduce a copy and keep the owned part
+            tmp = t.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+            n = out.numel()
+            out.copy_(tmp[self.rank * n:(self.rank + 1) * n]).mul_(1.0 / self.world)
+
     def _on_table_slab(self, flat, a, b):
+        rs = self.table_mode == "reduce_scatter"
+        if rs and (b - a) % (4 * self.world) != 0:
+            raise RuntimeError(f"reduce_scatter exchange: slab [{a}, {b}) is not divisible into {self.world} 16-byte shards")
+        m0, m1 = shard_bounds(a, b, self.rank, self.world)
         if self.peer is not None:
             if flat.data_ptr() != self.peer.buf.data_ptr():
                 raise RuntimeError("table gradient was not accumulated in the peer-shared buffer")
-            self.peer.reduce_slab(a, b)
-        elif self.stream is None:
-            self._avg(flat[a:b])
+            self.peer.reduce_slab(a, b)  # leaves the mean of the owned shard in place (flat[m0:m1])
+            if rs:
+                self.table_grad_shards.append((m0, m1, flat[m0:m1]))
         else:
-            if self._limit_sms:
-                from . import _lib
-                _lib.set_sm_limit(148 - self.comm_sms)  # until allreduce_grads() has joined
-            ev = torch.cuda.Event()
-            ev.record()  # the slab is final once everything enqueued so far on the compute stream has run
-            self.stream.wait_event(ev)
-            flat.record_stream(self.stream)
-            with torch.cuda.stream(self.stream):
-                self._avg(flat[a:b])
+            out = None
+            if rs:
+                out = self._shard_buf[self._shard_off:self._shard_off + (m1 - m0)]
+                self._shard_off += m1 - m0
+                self.table_grad_shards.append((m0, m1, out))
+            if self.stream is None:
+                self._reduce_scatter_avg(out, flat[a:b]) if rs else self._avg(flat[a:b])
+            else:
+                if self._limit_sms and not self._limited:
+                    from . import _lib
+                    _lib.set_sm_limit(num_sms() - self.comm_sms)  # until exchange_grads() has joined
+                    self._limited = True
+                ev = torch.cuda.Event()
+                ev.record()  # the slab is final once everything enqueued so far on the compute stream has run
+                self.stream.wait_event(ev)
+                flat.record_stream(self.stream)
+                with torch.cuda.stream(self.stream):
+                    self._reduce_scatter_avg(out, flat[a:b]) if rs else self._avg(flat[a:b])
         self._early[flat.data_ptr()] = self._early.get(flat.data_ptr(), 0) + (b - a)
         self._hooked = flat  # the exchange runs in place on this buffer: the parameter's .grad must alias it
 
@@ -135,37 +231,62 @@ class GradReducer:
                                "gradients with set_to_none=True before every backward, or do not attach() the engine")
         return big, small
 
-    def allreduce_grads(self):
-        """all-reduce(mean) of every existing .grad; returns after enqueueing on the current stream (stream-ordered)."""
+    def begin_step(self):
+        """Forget the shard list of the previous step (called by exchange_grads' consumers implicitly: the hook of the
+        next backward appends to a fresh list)."""
+        self.table_grad_shards = []
+        self._shard_off = 0
+
+    def exchange_grads(self):
+        """Complete the gradient exchange of the step; returns after enqueueing on the current stream (stream-ordered).
+        allreduce mode: every existing .grad holds the mean over ranks.  reduce_scatter mode: the MLP / s_var gradients
+        hold the mean; of the table gradient only `table_grad_shards` (this rank's shards) is meaningful."""
         if self.world <= 1:
             return
-        big, small = self._buckets()
-        if self.peer is not None:
-            self.peer.gather()  # ahead of the MLP bucket in the NCCL queue: that one waits for the end of the backward
-        cur = torch.cuda.current_stream() if self.stream is not None else None
-        if self.stream is not None:
-            self.stream.wait_stream(cur)
-        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
-        with ctx:
-            for g in big:
-                flat = g.view(-1)
-                slices = self.level_slices or [(0, flat.numel())]
-                for a, b in slices:
-                    self._avg(flat[a:b])
-            if small:
-                bucket = torch.cat([g.reshape(-1) for g in small])
-                self._avg(bucket)
-                off = 0
-                for g in small:
-                    g.copy_(bucket[off:off + g.numel()].view_as(g))
-                    off += g.numel()
-        if self.stream is not None:
-            cur.wait_stream(self.stream)
-        if self.peer is not None:
-            self.peer.finish()
-        if self._limit_sms:
-            from . import _lib
-            _lib.set_sm_limit(148)
+        try:
+            big, small = self._buckets()
+            rs = self.table_mode == "reduce_scatter"
+            if big and rs:
+                raise RuntimeError("reduce_scatter exchange needs the engine hook (GradReducer.attach): a large gradient "
+                                   "reached exchange_grads() without having been exchanged slab by slab")
+            if self.peer is not None and not rs:
+                self.peer.gather()  # ahead of the MLP bucket in the NCCL queue: that one waits for the end of the backward
+            cur = torch.cuda.current_stream() if self.stream is not None else None
+            if self.stream is not None:
+                self.stream.wait_stream(cur)
+            ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
+            with ctx:
+                for g in big:
+                    flat = g.view(-1)
+                    slices = self.level_slices or [(0, flat.numel())]
+                    for a, b in slices:
+                        self._avg(flat[a:b])
+                if small:
+                    bucket = torch.cat([g.reshape(-1) for g in small])
+                    self._avg(bucket)
+                    off = 0
+                    for g in small:
+                        g.copy_(bucket[off:off + g.numel()].view_as(g))
+                        off += g.numel()
+            if self.stream is not None:
+                cur.wait_stream(self.stream)
+            if self.peer is not None:
+                self.peer.finish(gather=not rs)
+        finally:
+            self._restore_sms()
+        # the shard list stays valid until the next backward starts appending: hand it to the optimizer, then reset
+        self._last_shards, self.table_grad_shards, self._shard_off = self.table_grad_shards, [], 0
+
+    allreduce_grads = exchange_grads  # the all-reduce mode's historical name
+
+    def make_optimizer(self, lr=1e-3, weight_decay=1e-2, betas=(0.9, 0.999), eps=1e-8):
+        """The optimizer that matches the exchange: dense FusedAdamW after an all-reduce, ShardedTableAdamW after a
+        reduce-scatter."""
+        from .optim import FusedAdamW, ShardedTableAdamW
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        if self.table_mode == "reduce_scatter" and self.world > 1:
+            return ShardedTableAdamW(self, params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        return FusedAdamW(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
 
 
 def shard_bounds(a, b, rank, world):
@@ -305,12 +426,15 @@ class PeerTableReducer:
                 self._mark(f"slab {a}: gathered")
         self._slabs = []
 
-    def finish(self):
-        """Current stream waits until the whole buffer holds the mean on every rank and nobody reads this rank's
-        buffer any more (it may be zeroed for the next step)."""
+    def finish(self, gather=True):
+        """Current stream waits until the whole buffer holds the mean on every rank (`gather=False`: only this rank's
+        shards do -- reduce-scatter) and nobody reads this rank's buffer any more (it may be zeroed for the next step)."""
         if not self._pending:
             return
-        self.gather()
+        if gather:
+            self.gather()
+        else:
+            self._slabs = []
         self._mark("finish(): compute stream position")
         ev = torch.cuda.Event()
         with torch.cuda.stream(self.s_copy):

@@ -510,26 +510,52 @@ class Model(torch.nn.Module):
         return losses
 
     @torch.no_grad()
-    def inference(self, data, per_sample=True):
+    def inference(self, data, per_sample=True, shard=None):
         """NeuralLumen/model.py:60-111: full-image render in chunks of rand_rays_val rays, eval outputs + *_map.
         ``per_sample=False`` drops the [B,HW,128,.] debug tensors (dists / weights / gradients) that the reference
-        concatenates but nothing downstream reads."""
+        concatenates but nothing downstream reads.
+        ``shard=(rank, world)``: every rank renders one contiguous range of the frame's rays (dist.shard_rays) and the
+        per-ray outputs are all-gathered (torch.distributed, NCCL over NVLink; the reference gathers whole frames the
+        same way, projects/nerf/utils/misc.py:25-34), so every rank returns the full maps.  ``shard=True`` takes rank
+        and world size from the default process group."""
         self.eval()
         pose = data["pose"]
         B = pose.shape[0]
         H, W = self.image_size_val
-        c, r, l, norm = self._rays(pose, data["intr"], data["pose_light"], self.image_size_val, None)
-        c, r, l, norm = c.view(B, H * W, 3), r.view(B, H * W, 3), l.view(B, H * W, 3), norm.view(B, H * W, 1)
+        rank, world = 0, 1
+        if shard is True:
+            import torch.distributed as dist
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        elif shard:
+            rank, world = int(shard[0]), int(shard[1])
+        if world > 1:
+            from .dist import shard_rays
+            r0, r1 = shard_rays(H * W, rank, world)
+            ray_idx = torch.arange(r0, r1, device=pose.device, dtype=torch.int64)[None].expand(B, -1).contiguous()
+            n_loc = r1 - r0
+        else:
+            ray_idx, n_loc = None, H * W
+        c, r, l, norm = self._rays(pose, data["intr"], data["pose_light"], self.image_size_val, ray_idx)
+        c, r, l, norm = c.view(B, n_loc, 3), r.view(B, n_loc, 3), l.view(B, n_loc, 3), norm.view(B, n_loc, 1)
         chunks = []
-        for s in range(0, H * W, self.rand_rays_val):
-            e = min(H * W, s + self.rand_rays_val)
+        for s in range(0, n_loc, self.rand_rays_val):
+            e = min(n_loc, s + self.rand_rays_val)
             o = self.render_rays_lumen(c[:, s:e], r[:, s:e], l[:, s:e], stratified=False)
             o["depth"] = o.pop("_dist") / norm[:, s:e]
             if not per_sample:
                 for k in ("dists", "weights", "gradients"):
                     o.pop(k, None)
             chunks.append(o)
-        output = {k: torch.cat([ch[k] for ch in chunks], dim=1) for k, v in chunks[0].items() if v is not None}
+        if chunks:
+            output = {k: torch.cat([ch[k] for ch in chunks], dim=1) for k, v in chunks[0].items() if v is not None}
+        else:  # a rank whose range is empty (more ranks than rays): zero-length tensors with the regular keys
+            output = {k: v for k, v in self._empty_render(B, 0, pose.device).items() if v is not None}
+            output["depth"] = output.pop("_dist")
+            if not per_sample:
+                for k in ("dists", "weights", "gradients"):
+                    output.pop(k, None)
+        if world > 1:
+            output = self._gather_rays(output, H * W, world)
         rot = pose[..., :3, :3]
         normal_cam = -output["gradient"] @ rot.transpose(-1, -2)
         to_img = lambda x: x.unflatten(dim=1, sizes=(H, W)).moveaxis(-1, 1)  # misc.py:110-117
@@ -542,3 +568,25 @@ class Model(torch.nn.Module):
             for key in ("visibility", "normal_x_light", "pseudo_shading", "inter_dist", "inter_mask"):
                 output[key + "_map"] = to_img(output[key]).float()
         return output
+
+    @staticmethod
+    def _gather_rays(output, n_rays, world):
+        """all-gather of per-ray outputs [B, n_local, ...] over the ranks' contiguous ray ranges -> [B, n_rays, ...].
+        Ranges are padded to the common shard size so that one all_gather_into_tensor per key does it."""
+        import torch.distributed as dist
+        from .dist import shard_rays
+        per = shard_rays(n_rays, 0, world)[1]
+        full = {}
+        for k in sorted(output):  # same key order on every rank
+            v = output[k]
+            was_bool = v.dtype == torch.bool
+            v = v.to(torch.uint8) if was_bool else v
+            B, n_loc = v.shape[:2]
+            tail = tuple(v.shape[2:])
+            send = v.new_zeros((B, per) + tail)
+            send[:, :n_loc] = v
+            recv = v.new_empty((world, B, per) + tail)
+            dist.all_gather_into_tensor(recv.view(-1), send.view(-1).contiguous())
+            g = recv.transpose(0, 1).reshape((B, world * per) + tail)[:, :n_rays]
+            full[k] = g.bool() if was_bool else g.contiguous()
+        return full

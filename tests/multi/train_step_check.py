@@ -36,23 +36,56 @@ for n, p in model.named_parameters():
     want[n] = g
     p.grad = None
 
+table_mode = os.environ.get("MLI_TABLE_EXCHANGE", "allreduce")
+TAB = "neural_sdf.tcnn_encoding.params"
 for mode in (os.environ.get("MLI_TABLE_ALLREDUCE", "peer"),):
-    reducer = GradReducer(model, world)
+    reducer = GradReducer(model, world, table_mode=table_mode)
     reducer.attach(model.engine)
     for it in range(3):  # the persistent buffer is zeroed and refilled every step
-        model.fused_train_step(data, lcfg, after_backward=reducer.allreduce_grads)
+        model.fused_train_step(data, lcfg, after_backward=reducer.exchange_grads)
     torch.cuda.synchronize()
+    tab = dict(model.named_parameters())[TAB]
     for n, p in model.named_parameters():
+        if n == TAB and table_mode == "reduce_scatter":
+            continue  # only this rank's shards are reduced in this mode (checked below)
         err = float((p.grad - want[n]).norm() / (want[n].norm() + 1e-30))
         assert err < 2e-5, (mode, n, err)
-    tab = dict(model.named_parameters())["neural_sdf.tcnn_encoding.params"]
-    if reducer.peer is not None:
-        assert tab.grad.data_ptr() == reducer.peer.buf.data_ptr()
-    chk = tab.grad.double().sum().reshape(1)
-    allc = [torch.zeros_like(chk) for _ in range(world)]
-    dist.all_gather(allc, chk)
-    assert all(float(c) == float(allc[0]) for c in allc)  # bitwise identical replicas
+    if table_mode == "allreduce":
+        if reducer.peer is not None:
+            assert tab.grad.data_ptr() == reducer.peer.buf.data_ptr()
+        chk = tab.grad.double().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(float(c) == float(allc[0]) for c in allc)  # bitwise identical replicas
+    else:
+        shards = reducer._last_shards
+        assert len(shards) == len(model.engine.level_groups())
+        wt = want[TAB].view(-1)
+        own = 0
+        for a, b, g in shards:
+            err = float((g - wt[a:b]).norm() / (wt[a:b].norm() + 1e-30))
+            assert err < 2e-5, (mode, a, b, err)
+            own += b - a
+        assert own * world == wt.numel()
+        # rank-owned AdamW shard + parameter all-gather == dense AdamW on the mean gradient, identical replicas
+        ref_p = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+        for q, (n, p) in zip(ref_p, model.named_parameters()):
+            q.grad = want[n].clone().view_as(q)
+        ref_opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-2)
+        opt = reducer.make_optimizer(lr=1e-3, weight_decay=1e-2)
+        opt.step()
+        ref_opt.step()
+        torch.cuda.synchronize()
+        for q, (n, p) in zip(ref_p, model.named_parameters()):
+            err = float((p.detach() - q.detach()).abs().max())
+            assert err < 2e-6 * (1.0 + float(q.detach().abs().max())), (n, err)
+        chk = tab.detach().double().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(float(c) == float(allc[0]) for c in allc)  # bitwise identical parameter replicas
+        m, v = opt.gather_state()
+        assert m.shape == tab.shape and float(m.abs().max()) > 0 and float(v.min()) >= 0
     reducer.close()
 if rank == 0:
-    print(f"TRAIN_STEP_ALLREDUCE_OK world={world}", flush=True)
+    print(f"TRAIN_STEP_EXCHANGE_OK world={world} table={table_mode}", flush=True)
 dist.destroy_process_group()

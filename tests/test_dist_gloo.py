@@ -103,3 +103,81 @@ def test_peer_shard_bounds_partition_every_slab():
             assert all((p0 - a) % 4 == 0 for p0, _ in parts)
             slot = ((b - a + world - 1) // world + 3) // 4 * 4
             assert all(0 <= p1 - p0 <= slot for p0, p1 in parts)
+
+
+def _worker_gather(rank, world, port_no, out):
+    """Ray-sharded inference: every rank holds the outputs of its contiguous ray range; Model._gather_rays rebuilds the
+    full per-ray tensors on every rank (ragged last shard, a bool tensor, a rank-4 per-sample tensor)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mli_nerf_b200.model import Model
+    n, B = 1001, 2
+    r0, r1 = shard_rays(n, rank, world)
+    idx = torch.arange(r0, r1, dtype=torch.float32)
+    local = dict(rgb=(idx[None, :, None] * torch.tensor([1.0, 2.0, 3.0])).expand(B, -1, -1).contiguous(),
+                 outside=(idx.long() % 3 == 0)[None, :, None].expand(B, -1, -1).contiguous(),
+                 weights=idx[None, :, None, None].expand(B, -1, 4, 1).contiguous())
+    full = Model._gather_rays(local, n, world)
+    torch.save(full, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_sharded_inference_gather_world3(tmp_path):
+    world, out = 3, str(tmp_path / "i")
+    mp.spawn(_worker_gather, args=(world, 29751, out), nprocs=world, join=True)
+    idx = torch.arange(1001, dtype=torch.float32)
+    for r in range(world):
+        full = torch.load(out + f".{r}")
+        assert full["rgb"].shape == (2, 1001, 3) and torch.equal(full["rgb"][1, :, 2], 3 * idx)
+        assert full["outside"].dtype == torch.bool and torch.equal(full["outside"][0, :, 0], idx.long() % 3 == 0)
+        assert full["weights"].shape == (2, 1001, 4, 1) and torch.equal(full["weights"][0, :, 3, 0], idx)
+
+
+def _worker_rs(rank, world, port_no, out):
+    """reduce_scatter mode: after the exchange every rank holds the mean gradient of ITS shard of every slab (and the
+    all-reduced small gradients); the dense table .grad is left alone."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = torch.nn.ModuleDict(dict(table=torch.nn.Embedding(1 << 19, 8), head=torch.nn.Linear(7, 3)))
+    g = torch.Generator().manual_seed(300 + rank)
+    n = model["table"].weight.numel()
+    tg = torch.randn(n, generator=g)
+    red = GradReducer(model, world, side_stream=False, table_mode="reduce_scatter")
+    slabs = [(0, n // 4), (n // 4, n // 2), (n // 2, n)]
+
+    class Eng:
+        table_grad_hook = None
+        device = "cpu"
+
+        def n_table_params(self):
+            return n
+
+        def level_groups(self):
+            return [(0, 0, a, b) for a, b in slabs]
+    eng = Eng()
+    red.attach(eng)
+    for step in range(2):  # the shard list is rebuilt every step
+        for a, b in slabs:
+            eng.table_grad_hook(tg, a, b)
+        model["table"].weight.grad = tg.view_as(model["table"].weight)
+        model["head"].weight.grad = torch.randn(3, 7, generator=torch.Generator().manual_seed(400 + rank))
+        red.exchange_grads()
+    shards = [(a, b, t.clone()) for a, b, t in red._last_shards]
+    torch.save(dict(shards=shards, head=model["head"].weight.grad, local=tg), out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def test_grad_reduce_scatter_world2(tmp_path):
+    world, out = 2, str(tmp_path / "rs")
+    mp.spawn(_worker_rs, args=(world, 29761, out), nprocs=world, join=True)
+    res = [torch.load(out + f".{r}") for r in range(world)]
+    mean = sum(r["local"] for r in res) / world
+    covered = torch.zeros_like(mean, dtype=torch.bool)
+    for r in range(world):
+        assert len(res[r]["shards"]) == 3
+        for a, b, t in res[r]["shards"]:
+            assert torch.allclose(t, mean[a:b], atol=1e-6)
+            assert not bool(covered[a:b].any())
+            covered[a:b] = True
+        assert torch.equal(res[r]["head"], res[0]["head"])
+    assert bool(covered.all())  # the ranks' shards partition the table

@@ -279,3 +279,57 @@ def test_light_visibility_box_bound_and_training_mode(lib):
         assert out_t[k].shape == (1, R, 1), k
     assert out_t["gradient"].shape == (1, R, 3) and out_t["opacity"] is None and out_t["hessians"] is not None
     assert float((out_t["inter_mask"].cpu() == imask).float().mean()) > 0.97
+
+
+def test_sharded_table_adamw_single_rank_group(lib):
+    """The rank-owned optimizer path of the reduce-scatter exchange on ONE GPU (a world-size-1 NCCL group): slab shards
+    at table offsets through mli_adamw_step_batch + the in-place parameter all-gather == torch.optim.AdamW.  (The
+    N-rank run of the same code is tests/multi/train_step_check.py, which needs >= 2 GPUs.)"""
+    import torch.distributed as dist
+    from mli_nerf_b200.optim import ShardedTableAdamW
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29771", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        torch.manual_seed(0)
+        n = 1 << 22
+        table = torch.nn.Parameter(torch.randn(n, device="cuda") * 0.01)
+        small = torch.nn.Parameter(torch.randn(256, 131, device="cuda"))
+        ref_p = [table.detach().clone().requires_grad_(True), small.detach().clone().requires_grad_(True)]
+        ref = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-2)
+
+        class Red:
+            world, rank = 1, 0
+        red = Red()
+        opt = ShardedTableAdamW(red, [table, small], lr=1e-3, weight_decay=1e-2)
+        cuts = [0, n // 8, n // 2, n]
+        for it in range(3):
+            g = torch.randn(n, device="cuda") * (torch.rand(n, device="cuda") > 0.8)  # mostly-zero gradient, like the table's
+            gs = torch.randn_like(small)
+            table.grad, small.grad = torch.full_like(table, float("nan")), gs.clone()  # the dense .grad must not be read
+            red._last_shards = [(a, b, g[a:b].clone()) for a, b in zip(cuts[:-1], cuts[1:])]
+            ref_p[0].grad, ref_p[1].grad = g.clone(), gs.clone()
+            opt.step()
+            ref.step()
+        assert torch.allclose(table, ref_p[0], rtol=1e-5, atol=1e-7), float((table - ref_p[0]).abs().max())
+        assert torch.allclose(small, ref_p[1], rtol=1e-5, atol=1e-6)
+        m, v = opt.gather_state()
+        assert torch.allclose(m, ref.state[ref_p[0]]["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(v, ref.state[ref_p[0]]["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
+def test_reduce_slots_mean_of_staged_shards(lib):
+    """mli_reduce_slots, the summation step of the copy-engine exchange, emulated on one GPU: own shard + (W-1) staged
+    peer shards -> mean, in place, for ragged sizes."""
+    torch.manual_seed(1)
+    for W, n in ((2, 1000), (4, 8 * 1_000_003 // 4), (8, 4)):
+        slot = (n + 3) // 4 * 4
+        own = torch.randn(n, device="cuda")
+        stage = torch.randn((W - 1) * slot, device="cuda")
+        want = (own + sum(stage[k * slot:k * slot + n] for k in range(W - 1))) / W
+        lib.call("mli_reduce_slots", own, stage, W - 1, slot, n, 1.0 / W)
+        assert torch.allclose(own, want, rtol=1e-6, atol=1e-7)
