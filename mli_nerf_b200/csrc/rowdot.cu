@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int kMaxJ = 8;
+constexpr int kMaxJ = 12;  // r_s_re: 3 heads x 3 channels = 9 narrow outputs
 
 struct RowdotArgs {
   int32_t col_off[kMaxJ];
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) adamw_batch_kernel(const __grid_constant_
 }
 
 int make_args(RowdotArgs* a, const int32_t* col_off, int32_t J, int32_t K) {
-  MLI_REQUIRE(J >= 1 && J <= kMaxJ, "rowdot: J must be in 1..8");
+  MLI_REQUIRE(J >= 1 && J <= kMaxJ, "rowdot: J must be in 1..12");
   MLI_REQUIRE(K >= 128 && K % 128 == 0 && K <= 1024, "rowdot: K must be a multiple of 128 (<= 1024)");
   a->J = J; a->K = K;
   for (int j = 0; j < kMaxJ; ++j) {
@@ -428,7 +428,8 @@ extern "C" int mli_rowdot_bwd(const float* dS, int64_t lds, const float* A, int6
 #define LAUNCH_W(JJ) rowdot_bwd_weight_kernel<JJ><<<blocks, K, 0, (cudaStream_t)stream>>>(dS, lds, A, lda, M, a, rows, (float*)ws)
     switch (J) {
       case 1: LAUNCH_W(1); break; case 2: LAUNCH_W(2); break; case 3: LAUNCH_W(3); break; case 4: LAUNCH_W(4); break;
-      case 5: LAUNCH_W(5); break; case 6: LAUNCH_W(6); break; case 7: LAUNCH_W(7); break; default: LAUNCH_W(8); break;
+      case 5: LAUNCH_W(5); break; case 6: LAUNCH_W(6); break; case 7: LAUNCH_W(7); break; case 8: LAUNCH_W(8); break;
+      case 9: LAUNCH_W(9); break; case 10: LAUNCH_W(10); break; case 11: LAUNCH_W(11); break; default: LAUNCH_W(12); break;
     }
 #undef LAUNCH_W
     MLI_LAUNCH_OK();

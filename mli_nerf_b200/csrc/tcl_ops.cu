@@ -10,7 +10,7 @@
 
 namespace {
 
-constexpr int kMaxJ = 8;
+constexpr int kMaxJ = 12;  // r_s_re: 3 heads x 3 channels = 9 narrow outputs
 constexpr int kTile = 128;
 
 struct RdArgs {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTile) rowdot_tcl_bwd_kernel(const float* __re
 }
 
 int make_args(RdArgs* a, const int32_t* col_off, int32_t J, int32_t K) {
-  MLI_REQUIRE(J >= 1 && J <= kMaxJ, "rowdot_tcl: J must be in 1..8");
+  MLI_REQUIRE(J >= 1 && J <= kMaxJ, "rowdot_tcl: J must be in 1..12");
   MLI_REQUIRE(K >= 8 && K % 8 == 0 && K <= 1024, "rowdot_tcl: K must be a multiple of 8 (<= 1024)");
   a->J = J; a->K = K;
   for (int j = 0; j < kMaxJ; ++j) {

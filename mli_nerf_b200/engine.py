@@ -119,6 +119,7 @@ class RenderEngine:
                 self.act_mask |= (1 << j) if h[3] else 0
                 j += 1
         self.n_out = {0: 3, 1: 10, 2: 9, 3: 9, 4: 12}[self.mode]
+        self.lds = 8 if self.J <= 8 else 12  # row length of the per-sample head outputs S / their gradients
         i32 = dict(dtype=torch.int32, device=self.device)
         self.map_sdf0 = torch.tensor([128, 129, 130] + list(range(128)), **i32)
         self.map_head = [torch.tensor(_col_map(h[1]), **i32) for h in self.heads]
@@ -522,7 +523,7 @@ class RenderEngine:
                  S0, H0c, DZ, sdf)
         gradients = self._f(M, 3)
         hessians = self._f(M, 3) if training else None
-        S = self._f(M, 8)
+        S = self._f(M, self.lds)
         if not self.tc:
             XH = self._f(M, KH_PAD)
             call("mli_linear_fwd", H0, HID, 0, W["W1"], HID, 0, W["b1"], 0, XH, KH_PAD, 0, M, HID, HID, ACT_SOFTPLUS100, 1,
@@ -536,7 +537,7 @@ class RenderEngine:
                 call("mli_linear_fwd", A[l], nh * HID, HID, W["Whl"][l], HID, HID * HID, W["bh"][l + 1], HID, A[l + 1],
                      nh * HID, HID, M, HID, HID, ACT_RELU, nh, prec)
             call("mli_rowdot_fwd", A[3], nh * HID, M, W["Wout"], W["bout"], self.col_off, self.J, HID, ACT_SIGMOID,
-                 self.act_mask, S, 8)
+                 self.act_mask, S, self.lds)
             H0c = None
         else:
             # layer 1 + all head layers on the tensor cores; activations in bf16 TCL (never leave that layout)
@@ -562,13 +563,13 @@ class RenderEngine:
                 njs.append(h[2])
                 j += h[2]
             call("mli_tc_linear_dot", A[2], nh * 32, 0, 32, T["Whl"][2], HID * HID, HID, W["bh"][3], HID, A[3], nh * 32, 0,
-                 32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, 8, Am[3],
+                 32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, self.lds, Am[3],
                  Am[3].shape[1] if Am[3] is not None else 0, 0, 8)
         ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
                                  min(progress / cfg.anneal_end, 1.0))
         weights, out = self._f(R, N), self._f(R, self.n_out)
         extras = self._f(R, 5) if not training else None
-        call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, 8, R, None, weights, out,
+        call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, self.lds, R, None, weights, out,
              extras)
         ctx = dict(R=R, M=M, P=P, X0=X0, H0=H0, H0c=H0c, Xd=Xd, S0=S0, DZ=DZ, Am=Am if self.tc else None, sdf=sdf, XH=XH, gradients=gradients, A=A, S=S, weights=weights,
                    ccfg=ccfg, center=center, ray_unit=ray_unit, dists=dists, far=far, outside=outside)
@@ -585,10 +586,10 @@ class RenderEngine:
         need_sdf = ("sdf" in need) or ("table" in need)
         grads = {}
         d_grad = d_gradients.contiguous().clone() if d_gradients is not None else self._z(M, 3)
-        dS, d_sdf_c = self._f(M, 8), self._f(M)
+        dS, d_sdf_c = self._f(M, self.lds), self._f(M)
         d_svar = self._z(1) if "s_var" in need else None
         call("mli_composite_bwd", ctx["ccfg"], p["s_var"], ctx["sdf"], ctx["gradients"], ctx["ray_unit"], ctx["dists"], N,
-             ctx["far"], ctx["S"], 8, R, ctx["weights"], d_out, d_weights, self.act_mask, dS, d_sdf_c, d_grad, d_svar, 0,
+             ctx["far"], ctx["S"], self.lds, R, ctx["weights"], d_out, d_weights, self.act_mask, dS, d_sdf_c, d_grad, d_svar, 0,
              self._f(R) if d_svar is not None else None)
         if d_svar is not None:
             grads["s_var"] = d_svar.view(())
@@ -610,7 +611,7 @@ class RenderEngine:
             # ---- heads, fp32 CUDA-core path -------------------------------------------------------------------------
             dZ = self._f(M, nh * HID)
             ws = torch.empty(_lib.load().mli_rowdot_bwd_ws_bytes(M, self.J, HID), dtype=torch.uint8, device=self.device)
-            call("mli_rowdot_bwd", dS, 8, A[3], nh * HID, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, nh * HID,
+            call("mli_rowdot_bwd", dS, self.lds, A[3], nh * HID, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, nh * HID,
                  nh * HID, 0, dWout if need_heads else None, dbout, ws)
             for l in (2, 1, 0):
                 if need_heads:
@@ -649,14 +650,14 @@ class RenderEngine:
             T, XH = W["T"], ctx["XH"]
             dZ = self._tcl(M, nh * 32)
             Am = ctx["Am"] if ctx["Am"][0] is not None else [None] * 4
-            call("mli_tc_rowdot_bwd_data", dS, 8, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, Am[3])
+            call("mli_tc_rowdot_bwd_data", dS, self.lds, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, Am[3])
             if need_heads:
                 def _out_layer():
-                    dSt = self._to_tcl(dS, 8, M, 8, self._tcl(M, 2), 128, 0, 2)
+                    dSt = self._to_tcl(dS, self.lds, M, self.lds, self._tcl(M, 2), 128, 0, 2)
                     outT = self._f(nh, 16, HID)  # [head][j][k] = sum_m dS[m, j] A4[m, head*256 + k]
                     self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1)
                     dWout.copy_(torch.stack([outT[self.col_off[j] // HID, j] for j in range(self.J)]))
-                    dbout.copy_(self._tc_colsum(dSt, 0, 1, M)[:self.J])
+                    dbout.copy_(self._tc_colsum(dSt, 0, 2, M)[:self.J])
                 later.append(_out_layer)
             for l in (2, 1, 0):
                 if need_heads:
