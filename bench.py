@@ -185,6 +185,9 @@ def kernel_work(name, a):
         M, nh, kh, store = a[1], a[2], a[3], a[4]
         return 2.0 * M * nh * 256 * (kh + 3 * 256) + 2.0 * M * 256 * 7, \
             float(M * kh * 2 + (M * nh * 256 * 2 * 4 if store else 0) + M * 8 * f32)
+    if name == "mli_tc_heads_bwd":
+        M, nh = a[2], a[3]
+        return 2.0 * M * nh * 256 * 3 * 256 + 2.0 * M * 256 * 7, float(M * 8 * f32 + M * nh * 256 // 8 * 4 + M * nh * 256 * 2 * 4)
     if name == "mli_tc_wgrad":
         M, rows, cols, batch = a[8], a[9], a[10], a[11]
         return 2.0 * M * rows * cols * batch, float(M * batch * (rows + cols) * 2)

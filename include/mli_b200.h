@@ -211,6 +211,34 @@ int mli_tc_sdf_trunk_bwd(const float* g, int64_t M, int32_t taps, const float* s
                          const void* h0, const float* w_sdf, void* Ed, float* dw_sdf, float* db_sdf, void* ws,
                          void* stream);
 
+/* Fused forward of the WHOLE head stack (LumenRGB.forward, NeuralLumen/utils/modules.py:106-174: per head the five
+ * layers of MLPwithSkipConnection.forward, nerf_util.py:186-196) in one persistent tcgen05 kernel (csrc/heads_fused.cu):
+ * the [256 x 256] hidden activations of a tile pair stay in shared memory between layers, weights stream from L2.
+ * XH: TCL-128 input of head layer 0 (xh_chunks chunks per tile row, the first K0/8 are used); W0 / W1..W3: the
+ * weight_norm-ed weights of all nh heads in TCL with 128-row tiles, [nh][2][K/8][128][8] (mli_weightnorm_pack_batch,
+ * tcl2); bias0..3 [nh*256]; w_out [J,256] / b_out [J] fp32, head h owning outputs [host_j0[h], +host_nj[h]) (<= 4
+ * each), act_out applied where bit j of act_mask is set.  store_activations != 0 (a backward pass follows): A0..A3
+ * (bf16 TCL-128, nh*32 chunks per tile row) and the relu sign bits mask0..3 ([tiles][nh*8][128] uint32, may be NULL)
+ * are written; otherwise nothing but S [M, lds] leaves the SM.  M % 128 == 0. */
+int mli_tc_heads_fwd(const void* XH, int64_t M, int32_t nh, int32_t K0, int32_t store_activations, int32_t xh_chunks,
+                     const void* W0, const void* W1, const void* W2, const void* W3, const float* bias0,
+                     const float* bias1, const float* bias2, const float* bias3, const float* w_out, const float* b_out,
+                     const int32_t* host_j0, const int32_t* host_nj, int32_t act_out, uint32_t act_mask, void* A0,
+                     void* A1, void* A2, void* A3, void* mask0, void* mask1, void* mask2, void* mask3, float* S,
+                     int64_t lds, void* stream);
+
+/* Fused data-gradient chain of the head stack (backward of the same layers, csrc/heads_fused.cu): from dS [M, lds]
+ * (gradient w.r.t. the PRE-activation head outputs, mli_composite_bwd) and the relu sign bits mask0..3 written by
+ * mli_tc_heads_fwd to the pre-activation gradients of the four hidden layers,
+ *     dZ3 = (dS W_out) * relu'(A3),   dZ_{l-1} = (dZ_l W_l) * relu'(A_{l-1})   (l = 3, 2, 1),
+ * each written ONCE as bf16 TCL-128 (nh*32 chunks per tile row) -- the operands of the weight-gradient GEMMs and of the
+ * layer-0 data gradient.  W3t, W2t, W1t: TRANSPOSED hidden-layer weights, TCL with 128-row tiles [nh][2][32][128][8]
+ * (rows = input unit; mli_weightnorm_pack_batch, tclt).  M % 128 == 0. */
+int mli_tc_heads_bwd(const float* dS, int64_t lds, int64_t M, int32_t nh, const void* W3t, const void* W2t,
+                     const void* W1t, const float* w_out, const int32_t* host_j0, const int32_t* host_nj,
+                     const void* mask0, const void* mask1, const void* mask2, const void* mask3, void* dZ0, void* dZ1,
+                     void* dZ2, void* dZ3, void* stream);
+
 /* Weight-gradient GEMM: out[b][r, c] = sum_m L[m, 8*(l_chunk0 + b*l_batch_chunks) + r] * R[m, 8*(r_chunk0 +
  * b*r_batch_chunks) + c]; r < rows_out (multiple of 128), c < cols_out (multiple of 16; < 256 or a multiple of 256).
  * L, R: TCL-128 (the same bytes serve as MN-major operands).  Split over row tiles, deterministic reduction.
@@ -265,6 +293,7 @@ int mli_weightnorm_unpack_grad(const float* v, const float* g, const float* dWp,
  *   Wp    fp32 row-major (ldw)                                                       (may be NULL)
  *   tcl   bf16 TCL with tcl_tile-row tiles and tcl_chunks chunks per tile row; tcl_lo >= 0 also writes the split-bf16
  *         remainder bf16(w - bf16(w)) tcl_lo chunks further                           (may be NULL)
+ *   tcl2  a second bf16 TCL copy (tcl2_tile-row tiles, tcl2_chunks chunks per tile row)  (may be NULL)
  *   tclt  up to two bf16 TCL copies of column ranges [c0, c1) of the TRANSPOSE: element
  *         (tclt_row_off + c - c0, tclt_col_off + n)                                   (may be NULL)
  * Target buffers must be zero where no element is scattered (K padding).  The same descriptors drive the backward:
@@ -280,6 +309,7 @@ typedef struct {
   int32_t tcl_tile, tcl_chunks, tcl_lo;
   int32_t tclt_c0[2], tclt_c1[2], tclt_tile[2], tclt_chunks[2], tclt_row_off[2], tclt_col_off[2];
   int32_t row_begin;  /* filled by the library */
+  void* tcl2; int32_t tcl2_tile, tcl2_chunks;  /* a second bf16 TCL copy with its own tile height (fused head kernel) */
 } mli_wn_desc_t;
 int mli_weightnorm_pack_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream);
 int mli_weightnorm_unpack_grad_batch(const mli_wn_desc_t* descs_on_host, int32_t n_descs, void* stream);

@@ -54,7 +54,8 @@ class WnDesc(C.Structure):
                 ("tcl_tile", C.c_int32), ("tcl_chunks", C.c_int32), ("tcl_lo", C.c_int32),
                 ("tclt_c0", C.c_int32 * 2), ("tclt_c1", C.c_int32 * 2), ("tclt_tile", C.c_int32 * 2),
                 ("tclt_chunks", C.c_int32 * 2), ("tclt_row_off", C.c_int32 * 2), ("tclt_col_off", C.c_int32 * 2),
-                ("row_begin", C.c_int32)]
+                ("row_begin", C.c_int32),
+                ("tcl2", C.c_void_p), ("tcl2_tile", C.c_int32), ("tcl2_chunks", C.c_int32)]
 
 
 ADAMW_MAX_TENSORS = 64

@@ -13,7 +13,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libmli_b200.so")
-SOURCES = ["capi.cu", "hashgrid.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "sdf_trunk.cu", "tcl_ops.cu", "rowdot.cu", "rays_sampling.cu",
+SOURCES = ["capi.cu", "hashgrid.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "heads_fused.cu", "sdf_trunk.cu", "tcl_ops.cu", "rowdot.cu", "rays_sampling.cu",
            "geometry.cu", "composite.cu", "losses.cu", "visibility.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xcudafe", "--diag_suppress=177"]

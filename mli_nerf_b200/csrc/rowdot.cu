@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(128) weightnorm_pack_batch_kernel(const __grid
       t[tcl_index(R, c, d.tcl_tile, d.tcl_chunks)] = hi;
       if (d.tcl_lo >= 0) t[tcl_index(R, c + 8 * d.tcl_lo, d.tcl_tile, d.tcl_chunks)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
     }
+    if (d.tcl2) reinterpret_cast<__nv_bfloat16*>(d.tcl2)[tcl_index(R, c, d.tcl2_tile, d.tcl2_chunks)] = hi;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       if (d.tclt[q] && c >= d.tclt_c0[q] && c < d.tclt_c1[q])

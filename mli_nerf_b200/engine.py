@@ -26,6 +26,7 @@ kept for the backward pass, Am[l] are the relu sign bits of the head activations
 (main stream), weight-gradient GEMMs deferred to a second stream, table gradient scattered per level group.
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -138,6 +139,8 @@ class RenderEngine:
         self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
+        # bf16 mode: the head stack as ONE on-chip kernel (csrc/heads_fused.cu); MLI_FUSE_HEADS=0 = layer-by-layer GEMMs
+        self.fuse_heads = os.environ.get("MLI_FUSE_HEADS", "0") == "1"
         # persistent buffer the table gradient is accumulated in (multi-GPU: the IPC-shared buffer of PeerTableReducer);
         # None: a fresh zero-filled buffer per step
         self.table_grad_buffer = None
@@ -296,6 +299,11 @@ class RenderEngine:
         for l in range(3):
             sizes[f"Whl{l}"] = nh * HID * HID
             sizes[f"Whlt{l}"] = nh * HID * HID
+        if self.fuse_heads:  # the same forward weights in 128-row tiles: [head][N-half][K/8][128][8] (csrc/heads_fused.cu)
+            sizes["Wh0_128"] = nh * HID * KH_PAD
+            for l in range(3):
+                sizes[f"Whl128_{l}"] = nh * HID * HID
+                sizes[f"Whlt128_{l}"] = nh * HID * HID
         flat = torch.zeros(sum(sizes.values()), dtype=bf, device=self.device)
         off, buf = 0, {}
         for k, n in sizes.items():
@@ -309,6 +317,10 @@ class RenderEngine:
         T["Wh0t_x"] = buf["Wh0t_x"].view(1, nh * 32, KH_PAD - XH_OFF, 8)
         T["Whl"] = [buf[f"Whl{l}"].view(nh, 32, 256, 8) for l in range(3)]
         T["Whlt"] = [buf[f"Whlt{l}"].view(nh, 32, 256, 8) for l in range(3)]
+        if self.fuse_heads:
+            T["Wh0_128"] = buf["Wh0_128"].view(nh * 2, KH_PAD // 8, 128, 8)
+            T["Whl128"] = [buf[f"Whl128_{l}"].view(nh * 2, 32, 128, 8) for l in range(3)]
+            T["Whlt128"] = [buf[f"Whlt128_{l}"].view(nh * 2, 32, 128, 8) for l in range(3)]  # rows = input unit
         W["Wout"] = self._f(self.J, HID)
         descs = (_lib.WnDesc * 24)()
         specs = self._wn_specs()
@@ -334,19 +346,30 @@ class RenderEngine:
                 d.tclt[1] = T["Wh0t_x"].data_ptr()
                 d.tclt_c0[1], d.tclt_c1[1], d.tclt_tile[1], d.tclt_chunks[1] = XH_OFF, KH_PAD, KH_PAD - XH_OFF, nh * 32
                 d.tclt_col_off[1] = hi * HID
+                if self.fuse_heads:
+                    d.tcl2, d.tcl2_tile, d.tcl2_chunks = T["Wh0_128"].data_ptr(), 128, KH_PAD // 8
             elif tag[0] == "hl":
                 _, l, hi = tag
                 d.tcl, d.tcl_tile, d.tcl_chunks = T["Whl"][l].data_ptr(), 256, 32
                 d.tclt[0] = T["Whlt"][l].data_ptr()
                 d.tclt_c0[0], d.tclt_c1[0], d.tclt_tile[0], d.tclt_chunks[0] = 0, HID, 256, 32
                 d.tclt_row_off[0] = hi * HID
+                if self.fuse_heads:
+                    d.tcl2, d.tcl2_tile, d.tcl2_chunks = T["Whl128"][l].data_ptr(), 128, 32
+                    d.tclt[1] = T["Whlt128"][l].data_ptr()
+                    d.tclt_c0[1], d.tclt_c1[1], d.tclt_tile[1], d.tclt_chunks[1] = 0, HID, 128, 32
+                    d.tclt_row_off[1] = hi * HID
             else:  # output layer: fp32 rows of W_out
                 d.Wp, d.ldw = W["Wout"].data_ptr(), HID
         call("mli_weightnorm_pack_batch", _lib.C.addressof(descs), len(specs))
         W["b0"], W["b1"] = p["neural_sdf.mlp.linears.0.bias"], p["neural_sdf.mlp.linears.1.bias"]
         W["w_sdf"], W["b_sdf"] = p["neural_sdf.mlp.linear_sdf.weight"], p["neural_sdf.mlp.linear_sdf.bias"]
-        W["bh"] = [torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for h in self.heads]) for l in range(4)]
-        W["bout"] = torch.cat([p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
+        # every head bias of the step in ONE concatenation (layer-major, heads side by side; output-layer biases last)
+        nb = nh * HID
+        bflat = torch.cat([p[f"neural_rgb.{h[0]}.linears.{l}.bias"] for l in range(4) for h in self.heads] +
+                          [p[f"neural_rgb.{h[0]}.linears.4.bias"] for h in self.heads])
+        W["bh"] = [bflat[l * nb:(l + 1) * nb] for l in range(4)]
+        W["bout"] = bflat[4 * nb:]
         W["T"], W["_keep"] = T, flat
         self.W = W
         return W
@@ -547,21 +570,29 @@ class RenderEngine:
             # gradients / Hessians + the non-feature head inputs, written straight into XH's last 6 TCL chunks
             call("mli_geometry_fwd", sdf, M, N, cfg.taps, self.tap_eps, outside, cfg.outside_val, center, ray_unit,
                  pts_light, dists, N, gradients, hessians, None, 0, 0, 1, XH, KH_PAD // 8, XH_OFF // 8)
-            A = [self._tcl(M, nh * 32) for _ in range(4)]
+            j0s, njs, j = [], [], 0
+            for h in self.heads:
+                j0s.append(j)
+                njs.append(h[2])
+                j += h[2]
+            fused = self.fuse_heads and "Wh0_128" in T
+            # hidden activations: kept (bf16 TCL) only when a backward pass follows -- the fused kernel needs no HBM copy
+            A = [self._tcl(M, nh * 32) if (keep_dz or not fused) else None for _ in range(4)]
             # relu sign bits of every hidden activation (only when a backward pass follows): the data-gradient
             # epilogues read these 4 bytes per 32 columns instead of the 64-byte bf16 activations
             Am = [self._mask(M, nh * HID) if keep_dz else None for _ in range(4)]
+        if self.tc and fused:
+            # the whole head stack (layer 0 .. output layers) in ONE persistent kernel: activations stay in shared memory
+            call("mli_tc_heads_fwd", XH, M, nh, KH_PAD, int(keep_dz), KH_PAD // 8, T["Wh0_128"], T["Whl128"][0],
+                 T["Whl128"][1], T["Whl128"][2], W["bh"][0], W["bh"][1], W["bh"][2], W["bh"][3], W["Wout"], W["bout"], j0s,
+                 njs, ACT_SIGMOID, self.act_mask, A[0], A[1], A[2], A[3], Am[0], Am[1], Am[2], Am[3], S, self.lds)
+        elif self.tc:
             self._tc_linear(XH, 0, 0, T["Wh0"], 0, KH_PAD, nh * HID, 256, W["bh"][0], 0, None, 0, 0, ACT_RELU, A[0], False,
                             0, 0, 0, M, 1, 0, mask=Am[0])
             for l in range(2):
                 self._tc_linear(A[l], 0, 32, T["Whl"][l], HID * HID, HID, HID, 256, W["bh"][l + 1], HID, None, 0, 0,
                                 ACT_RELU, A[l + 1], False, 0, 32, 0, M, nh, 0, mask=Am[l + 1], mask_bchunks=8)
             # last hidden layer with the 256 -> 3/3/1 output layers + sigmoid fused into its epilogue
-            j0s, njs, j = [], [], 0
-            for h in self.heads:
-                j0s.append(j)
-                njs.append(h[2])
-                j += h[2]
             call("mli_tc_linear_dot", A[2], nh * 32, 0, 32, T["Whl"][2], HID * HID, HID, W["bh"][3], HID, A[3], nh * 32, 0,
                  32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, self.lds, Am[3],
                  Am[3].shape[1] if Am[3] is not None else 0, 0, 8)
@@ -648,9 +679,24 @@ class RenderEngine:
             # a multi-GPU step has to all-reduce -- only depends on the former, so it is launched as early as possible
             # and its exchange overlaps the weight-gradient GEMMs.
             T, XH = W["T"], ctx["XH"]
-            dZ = self._tcl(M, nh * 32)
             Am = ctx["Am"] if ctx["Am"][0] is not None else [None] * 4
-            call("mli_tc_rowdot_bwd_data", dS, self.lds, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID, ACT_RELU, dZ, Am[3])
+            fused_bwd = self.fuse_heads and "Whlt128" in T and Am[0] is not None
+            if fused_bwd:
+                # the whole data-gradient chain (output layers + three hidden layers) in ONE on-chip kernel: every
+                # pre-activation gradient is written once, for the weight-gradient GEMMs and the layer-0 data gradient
+                dZs = [self._tcl(M, nh * 32) for _ in range(4)]
+                j0s, njs, j = [], [], 0
+                for h in self.heads:
+                    j0s.append(j)
+                    njs.append(h[2])
+                    j += h[2]
+                call("mli_tc_heads_bwd", dS, self.lds, M, nh, T["Whlt128"][2], T["Whlt128"][1], T["Whlt128"][0], W["Wout"],
+                     j0s, njs, Am[0], Am[1], Am[2], Am[3], dZs[0], dZs[1], dZs[2], dZs[3])
+                dZ = dZs[3]
+            else:
+                dZ = self._tcl(M, nh * 32)
+                call("mli_tc_rowdot_bwd_data", dS, self.lds, A[3], nh * 32, M, W["Wout"], self.col_off, self.J, HID,
+                     ACT_RELU, dZ, Am[3])
             if need_heads:
                 def _out_layer():
                     dSt = self._to_tcl(dS, self.lds, M, self.lds, self._tcl(M, 2), 128, 0, 2)
@@ -664,6 +710,9 @@ class RenderEngine:
                     dWh[l], dbh[l + 1] = self._f(nh, HID, HID), self._f(nh * HID)
                     later.append(lambda dZ=dZ, l=l: self._tc_wgrad(dZ, 0, 32, A[l], 0, 32, M, HID, HID, nh, dWh[l], HID,
                                                                    HID * HID, db=dbh[l + 1]))
+                if fused_bwd:
+                    dZ = dZs[l]
+                    continue
                 dZp = self._tcl(M, nh * 32)
                 self._tc_linear(dZ, 0, 32, T["Whlt"][l], HID * HID, HID, HID, 256, None, 0,
                                 A[l] if Am[l] is None else None, 0, 32, ACT_RELU, dZp, False, 0, 32, 0, M, nh, 1,

@@ -100,8 +100,17 @@ def test_t22_forward_backward_vs_oracle(lib, t22_case, prec):
     print(f"T=22 [{prec}] table gradient rel-L2 error: dense levels 0-5 {e_dense:.2e}, hashed levels 6-15 {e_hash:.2e}")
     assert float(tg_ref[:split].abs().max()) > 0 and float(tg_ref[split:].abs().max()) > 0
     assert e_dense < tol_t and e_hash < tol_t, (e_dense, e_hash)
-    # the zero pattern must agree too: entries no sample touches stay exactly zero
-    assert int(((tg_got != 0) & (tg_ref == 0)).sum()) == 0
+    # the zero pattern must agree too: entries no sample touches stay zero (an entry whose oracle contributions cancel
+    # to exactly 0.0 may hold rounding noise).  NOTE: no tensor comparison inside an `assert` -- pytest's failure report
+    # would iterate over the 365 M-element operands.
+    extra = (tg_got != 0) & (tg_ref == 0)
+    n_extra = int(extra.sum())
+    max_extra = float(tg_got[extra].abs().max()) if n_extra else 0.0
+    ref_max = float(tg_ref.abs().max())
+    n_ref = int((tg_ref != 0).sum())
+    print(f"T=22 [{prec}] entries non-zero only in the product: {n_extra} of {n_ref} touched, max |g| {max_extra:.2e} "
+          f"(max |g_ref| {ref_max:.2e})")
+    assert n_extra <= 1e-3 * n_ref and max_extra <= 1e-4 * ref_max, (n_extra, n_ref, max_extra, ref_max)
     worst = {}
     for k, v in g_ref.items():
         if k == "neural_sdf.tcnn_encoding.params":

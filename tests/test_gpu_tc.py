@@ -381,3 +381,64 @@ def test_relu_sign_mask_roundtrip(lib):
              o2, 0, batch * K // 8, 0, K // 8, 0, 0, 0, M, batch, 1, mask, batch * N // 32, 0, N // 32)
     d = (from_tcl_host(o1.cpu(), M) != from_tcl_host(o2.cpu(), M)).float().mean()
     assert float(d) < 1e-3, float(d)
+
+
+@pytest.mark.parametrize("mode,R", [("rgb_r_s", 256), ("rgb", 130), ("r_s_re", 64)])
+def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
+    """csrc/heads_fused.cu (the whole head stack in one on-chip tcgen05 kernel, two 128-sample tiles per CTA) against the
+    layer-by-layer tensor-core path on the same inputs: same bf16 roundings, same accumulation order -> the stored
+    activations, relu sign bits and per-sample outputs agree to the last bit almost everywhere.  R = 130 / 64 give an ODD
+    number of 128-sample tiles (the last tile pair is half empty) resp. fewer pairs than SMs; rgb = one head, r_s_re = nine
+    narrow outputs, one of them without sigmoid."""
+    from mli_nerf_b200.engine import RenderEngine
+    from oracle import port
+    from tests.util import make_case, product_cfg
+    case = make_case(R=R, mode=mode, progress=0.5)
+    res = {}
+    for fused in (False, True):
+        eng = RenderEngine(product_cfg(case["ocfg"], precision=1))
+        eng.fuse_heads = fused
+        p = {k: v.contiguous().cuda() for k, v in case["params"].items()}
+        eng.pack_weights(p)
+        c, r, l = (case[k][0].contiguous().cuda() for k in ("center", "ray_unit", "light"))
+        near, far, outside = eng.bounds(c, r)
+        with torch.no_grad():
+            ref = port.render_rays(case["params"], case["ocfg"], case["center"], case["ray_unit"], case["light"],
+                                   rands=case["rands"], training=True, progress=0.5)
+        dists = ref["dists"][0, :, :, 0].contiguous().cuda()
+        out, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, 0.5)
+        torch.cuda.synchronize()
+        res[fused] = (out, ctx)
+        # forward-only call (no backward follows): nothing but S leaves the SM, same S
+        out2, ctx2 = eng.forward(p, c, r, l, dists, near, far, outside, False, 0.5, keep_dz=False)
+        assert torch.equal(out2["S"], out["S"])
+        if fused:
+            assert ctx2["A"][0] is None
+    (o0, c0), (o1, c1) = res[False], res[True]
+    J = sum(h[2] for h in __import__("mli_nerf_b200.engine", fromlist=["head_layout"]).head_layout(mode if mode != "rgb" else None))
+    assert float((o0["S"][:, :J] - o1["S"][:, :J]).abs().max()) < 1e-5
+    assert float((o0["out"] - o1["out"]).abs().max()) < 1e-5
+    for l in range(4):
+        a0, a1 = c0["A"][l].float(), c1["A"][l].float()
+        frac_a = float(a0.ne(a1).float().mean())
+        err_a, max_a = float((a0 - a1).abs().max()), float(a0.abs().max())
+        frac_m = float(c0["Am"][l].ne(c1["Am"][l]).float().mean())
+        assert frac_a < 1e-3, (l, frac_a)            # a rare 1-ulp bf16 flip is tolerated ...
+        assert err_a < 1e-2 * max_a, (l, err_a)      # ... a wrong value is not
+        assert frac_m < 1e-3, (l, frac_m)
+    # the fused data-gradient chain (mli_tc_heads_bwd) against the layer-by-layer chain: every parameter gradient
+    torch.manual_seed(5)
+    d_out = torch.randn_like(o0["out"]) * 1e-2
+    d_grad = torch.randn_like(o0["gradients"]) * 1e-4
+    grads = {}
+    for fused in (False, True):
+        eng = RenderEngine(product_cfg(case["ocfg"], precision=1))
+        eng.fuse_heads = fused
+        p = {k: v.contiguous().cuda() for k, v in case["params"].items()}
+        eng.pack_weights(p)
+        grads[fused] = eng.backward(p, res[fused][1], d_out, d_grad, None, None)
+        torch.cuda.synchronize()
+    for k, g0 in grads[False].items():
+        g1 = grads[True][k]
+        err = float((g0 - g1).norm() / (g0.norm() + 1e-30))
+        assert err < 2e-3, (k, err)
