@@ -488,16 +488,16 @@ def main():
         opt_step(i)
     ms_opt, _ = timed(opt_step, args.steps, barrier)
 
-    extras = {}
-    if not args.no_extras:
-        extras = run_extras(args, world, rank, model, cfg, lcfg, dev, barrier, build, step)
-
-    if reducer is not None:
+    if reducer is not None:  # the extra sections below run without a gradient exchange
         torch.cuda.synchronize()
         exchange = reducer.describe()
         reducer.close()
+        del opt
     else:
         exchange = None
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, world, rank, model, cfg, lcfg, dev, barrier, build, step)
     if world > 1:
         t = torch.tensor([ms, ms_e2e, ms_opt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

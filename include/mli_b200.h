@@ -337,6 +337,11 @@ int mli_sample_fine(const float* dists, const float* sdfs, int64_t ld, int64_t R
 /* inverse-CDF binning alone, from given weights [R, ld_w] (n_w used): bit-exact KAT entry. */
 int mli_pdf_bins(const float* weights, int64_t ld_w, int64_t R, int32_t n_w, int32_t n_fine, int32_t* idx,
                  int32_t* low, int32_t* high, float* cdf, void* stream);
+/* mli_sample_merge(fine_in, sdf_fine) immediately followed by mli_sample_fine(inv_s_next) on the merged n + n_fine
+ * samples, in one launch (the hierarchy loop of sample_dists_all, neuralangelo/model.py:455-465): dists/sdfs are merged
+ * in place, fine_out [R, n_fine] receives the next round's samples.  Same results, bit for bit, as the two calls. */
+int mli_sample_merge_fine(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n, const float* fine_in,
+                          const float* sdf_fine, int32_t n_fine, float inv_s_next, float* fine_out, void* stream);
 /* cat + sort(dim=2) (+ gather of sdfs): merges n sorted + n_fine new samples, stable. sdf pointers may be NULL. */
 int mli_sample_merge(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n, const float* fine,
                      const float* sdf_fine, int32_t n_fine, void* stream);

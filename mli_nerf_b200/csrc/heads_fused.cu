@@ -46,17 +46,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol error must surface as a device-side trap with the wait site, not as a hung GPU (a kernel that
+// never returns costs the whole box).  try_wait suspends the thread for a hardware time slice per poll; 2^24 polls are
+// several seconds, orders of magnitude beyond any legitimate wait in this kernel.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "HF_WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra HF_WAIT_DONE;\n\t"
-      "bra HF_WAIT_LOOP;\n\t"
-      "HF_WAIT_DONE:\n\t"
-      "}\n" ::"r"(bar), "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout(int site, uint32_t parity) {
+  printf("tc_heads_kernel: wait timed out at site %d (parity %u) block %d thread %d\n", site, parity, (int)blockIdx.x,
+         (int)threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site) {
+  for (uint32_t spin = 0; !mbar_try(bar, parity); ++spin)
+    if (spin > (1u << 24)) mbar_timeout(site, parity);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
       uint32_t cnt = 0;
       auto put = [&](const void* src, uint32_t bytes) {
         const uint32_t s = cnt % kSlots;
-        if (cnt >= kSlots) mbar_wait(empty0 + 8 * s, ((cnt / kSlots) - 1) & 1);
+        if (cnt >= kSlots) mbar_wait(empty0 + 8 * s, ((cnt / kSlots) - 1) & 1, 1);
         mbar_expect_tx(full0 + 8 * s, bytes);
         bulk_g2s(sRing + s * kSlotBytes, src, bytes, full0 + 8 * s);
         ++cnt;
@@ -225,13 +238,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128);
       uint32_t cnt = 0, stage = 0;  // ring items consumed / stages passed so far (`ready` flips once per stage)
-      auto wait_full = [&](uint32_t c) { mbar_wait(full0 + 8 * (c % kSlots), (c / kSlots) & 1); };
+      auto wait_full = [&](uint32_t c) { mbar_wait(full0 + 8 * (c % kSlots), (c / kSlots) & 1, 2); };
       for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
         for (int h = 0; h < nh; ++h) {
           if (!BWD) {
             // ---- layer 0: both operands from the ring, k-major (all four accumulators finish together) ----
             if (stage > 0)
-              for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1);
+              for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
             tc_fence_after();
             for (int ks = 0; ks < k0_steps; ++ks) {
               const int nch = min(4, p.k0_chunks - ks * 4);
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                     // first write of accumulator (t, nf) in this stage: its previous contents have been drained, and
                     // activation column half nf of tile t (= K-half nf of this stage's A operand; K-half 0 is needed
                     // from quarter (0,0) on, K-half 1 from quarter (1,0) on, i.e. after the wait of quarter (0,1))
-                    mbar_wait(ready0 + 8 * (t * 2 + nf), (stage - 1) & 1);
+                    mbar_wait(ready0 + 8 * (t * 2 + nf), (stage - 1) & 1, 4);
                     tc_fence_after();
                   }
                   const uint32_t sa = sAct + t * 65536 + (kh * 16 + it * 4) * 2048;
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
               group_bar(g);
             }
             if (has_acc) {
-              mbar_wait(acc_full0 + 8 * (t * 2 + g), n_acc & 1);
+              mbar_wait(acc_full0 + 8 * (t * 2 + g), n_acc & 1, 5);
               tc_fence_after();
             }
             float dj[4] = {0.f, 0.f, 0.f, 0.f};

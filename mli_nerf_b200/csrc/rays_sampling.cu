@@ -173,7 +173,57 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_merge_kernel(
   }
 }
 
+// merge (cat + stable sort + gather of sdfs) of round h fused with the importance sampling of round h + 1: the merged
+// ray stays in shared memory between the two (saves a launch and the re-read on the latency-bound sampling path).  Same
+// arithmetic, in the same order, as sample_merge_kernel followed by sample_fine_kernel.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_merge_fine_kernel(
+    float* __restrict__ dists, float* __restrict__ sdfs, int64_t ld, int64_t R, int n, const float* __restrict__ fine_in,
+    const float* __restrict__ sdf_fine, int n_fine, float inv_s_next, float* __restrict__ fine_out) {
+  __shared__ FineSmem smem[kWarpsPerBlock];
+  __shared__ float sd[kWarpsPerBlock][kMaxN], ss[kWarpsPerBlock][kMaxN];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= R) return;
+  FineSmem& sm = smem[warp];
+  const int tot = n + n_fine;
+  for (int i = lane; i < tot; i += 32) {
+    sd[warp][i] = i < n ? dists[r * ld + i] : fine_in[r * n_fine + (i - n)];
+    ss[warp][i] = i < n ? sdfs[r * ld + i] : sdf_fine[r * n_fine + (i - n)];
+  }
+  __syncwarp();
+  for (int i = lane; i < tot; i += 32) {
+    const float v = sd[warp][i];
+    int rank = 0;
+    for (int j = 0; j < tot; ++j) {
+      const float o = sd[warp][j];
+      rank += (o < v) || (o == v && j < i) || (v != v && o == o) || (v != v && o != o && j < i);  // NaN last
+    }
+    sm.d[rank] = v;
+    sm.s[rank] = ss[warp][i];
+  }
+  __syncwarp();
+  for (int i = lane; i < tot; i += 32) { dists[r * ld + i] = sm.d[i]; sdfs[r * ld + i] = sm.s[i]; }
+  for (int i = lane; i < tot - 1; i += 32) sm.w[i] = mli_hier_alpha(sm.d, sm.s, i, inv_s_next);
+  __syncwarp();
+  if (lane == 0) mli_alphas_to_weights(sm.w, tot - 1);
+  __syncwarp();
+  bins_from_weights(sm, tot - 1, tot, n_fine, lane, fine_out + r * n_fine, nullptr, nullptr, nullptr, nullptr);
+}
+
 }  // namespace
+
+extern "C" int mli_sample_merge_fine(float* dists, float* sdfs, int64_t ld, int64_t R, int32_t n, const float* fine_in,
+                                     const float* sdf_fine, int32_t n_fine, float inv_s_next, float* fine_out,
+                                     void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(R >= 0 && n >= 1 && n_fine >= 1 && n + n_fine <= kMaxN && ld >= n + n_fine, "sample_merge_fine: bad shape");
+  MLI_REQUIRE(dists && sdfs && fine_in && sdf_fine && fine_out && fine_out != fine_in, "sample_merge_fine: NULL / aliased argument");
+  if (R == 0) return MLI_OK;
+  sample_merge_fine_kernel<<<mli_cdiv(R, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, (cudaStream_t)stream>>>(
+      dists, sdfs, ld, R, n, fine_in, sdf_fine, n_fine, inv_s_next, fine_out);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
 
 extern "C" int mli_rays_from_pose(const float* pose, const float* intr, const float* pose_light,
                                   const int64_t* ray_idx, int64_t B, int64_t R, int32_t W, float* center,

@@ -143,6 +143,10 @@ class GradReducer:
     def close(self):
         """Unmap / free the peer-shared table-gradient buffer (collective: every rank calls it)."""
         self._restore_sms()
+        if self._engine is not None:  # detach: the engine goes back to the single-GPU schedule
+            self._engine.table_grad_hook = None
+            self._engine.wgrad_after_scatter = False
+        self.table_grad_shards, self._last_shards = [], []
         if self.peer is None:
             return
         for p in self.model.parameters():
@@ -150,8 +154,6 @@ class GradReducer:
                 p.grad = None
         if self._engine is not None:
             self._engine.table_grad_buffer = None
-            self._engine.table_grad_hook = None
-        self.table_grad_shards = []
         self.peer.close()
         self.peer = None
 

@@ -469,12 +469,16 @@ class RenderEngine:
         if cfg.hierarchy > 0:
             s = self.sdf_query(table, center, ray_unit, dists, N, n)
             sdfs[:, :n] = s.view(R, n)
-        fine = self._f(R, cfg.fine)
+        # round h: importance-sample n_fine distances from (dists, sdfs), query their SDFs, merge.  The merge of round h
+        # and the sampling of round h + 1 run as ONE launch (mli_sample_merge_fine); the last merge needs no SDFs.
+        fine, fine_next = self._f(R, cfg.fine), self._f(R, cfg.fine)
         for h in range(cfg.hierarchy):
-            call("mli_sample_fine", dists, sdfs, N, R, n, cfg.fine, float(64 * 2 ** h), fine, None, None, None, None)
+            if h == 0:
+                call("mli_sample_fine", dists, sdfs, N, R, n, cfg.fine, float(64 * 2 ** h), fine, None, None, None, None)
             if h != cfg.hierarchy - 1:
                 sf = self.sdf_query(table, center, ray_unit, fine, cfg.fine, cfg.fine)
-                call("mli_sample_merge", dists, sdfs, N, R, n, fine, sf, cfg.fine)
+                call("mli_sample_merge_fine", dists, sdfs, N, R, n, fine, sf, cfg.fine, float(64 * 2 ** (h + 1)), fine_next)
+                fine, fine_next = fine_next, fine
             else:
                 call("mli_sample_merge", dists, None, N, R, n, fine, None, cfg.fine)
             n += cfg.fine

@@ -889,3 +889,26 @@ def test_model_stage_a_partial_coarse_to_fine(lib, prec):
         assert int(inside.sum()) > R // 8
         g_got, g_ref = out["gradients"].cpu()[0][inside], ref["gradients"][0][inside]
         assert float((g_got - g_ref).norm() / g_ref.norm()) < 2e-3
+
+
+def test_sample_merge_fine_fused_equals_two_calls(lib):
+    """mli_sample_merge_fine (merge of round h + importance sampling of round h+1 in one launch) is bit-identical to
+    mli_sample_merge followed by mli_sample_fine, including ties, NaN distances and flat (all-zero weight) rays."""
+    torch.manual_seed(7)
+    R, n, nf, ld = 777, 80, 16, 128
+    d = torch.sort(torch.rand(R, n) * 3.0 + 0.5, dim=1).values
+    s = torch.randn(R, n) * 0.05
+    s[:50] = 1.0                      # no surface crossing: weights ~ 0 -> flat cdf
+    fine = torch.rand(R, nf) * 3.0 + 0.5
+    fine[100:120, :4] = d[100:120, 10:14]   # exact ties between old and new samples
+    fine[130, 3] = float("nan")
+    sf = torch.randn(R, nf) * 0.05
+    D0, S0 = torch.zeros(R, ld), torch.zeros(R, ld)
+    D0[:, :n], S0[:, :n] = d, s
+    Da, Sa, Db, Sb = cu(D0), cu(S0), cu(D0), cu(S0)
+    fa, fb = torch.empty(R, nf, device="cuda"), torch.empty(R, nf, device="cuda")
+    lib.call("mli_sample_merge", Da, Sa, ld, R, n, cu(fine), cu(sf), nf)
+    lib.call("mli_sample_fine", Da, Sa, ld, R, n + nf, nf, 256.0, fa, None, None, None, None)
+    lib.call("mli_sample_merge_fine", Db, Sb, ld, R, n, cu(fine), cu(sf), nf, 256.0, fb)
+    same = lambda a, b: bool(((a == b) | (a.isnan() & b.isnan())).all())  # noqa: E731
+    assert same(Da, Db) and same(Sa, Sb) and same(fa, fb)

@@ -393,7 +393,9 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
     from mli_nerf_b200.engine import RenderEngine
     from oracle import port
     from tests.util import make_case, product_cfg
+    from mli_nerf_b200.engine import head_layout
     case = make_case(R=R, mode=mode, progress=0.5)
+    J = sum(h[2] for h in head_layout(mode if mode != "rgb" else None))
     res = {}
     for fused in (False, True):
         eng = RenderEngine(product_cfg(case["ocfg"], precision=1))
@@ -411,11 +413,10 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
         res[fused] = (out, ctx)
         # forward-only call (no backward follows): nothing but S leaves the SM, same S
         out2, ctx2 = eng.forward(p, c, r, l, dists, near, far, outside, False, 0.5, keep_dz=False)
-        assert torch.equal(out2["S"], out["S"])
+        assert torch.equal(out2["S"][:, :J], out["S"][:, :J])  # columns >= J of S are padding (never written)
         if fused:
             assert ctx2["A"][0] is None
     (o0, c0), (o1, c1) = res[False], res[True]
-    J = sum(h[2] for h in __import__("mli_nerf_b200.engine", fromlist=["head_layout"]).head_layout(mode if mode != "rgb" else None))
     assert float((o0["S"][:, :J] - o1["S"][:, :J]).abs().max()) < 1e-5
     assert float((o0["out"] - o1["out"]).abs().max()) < 1e-5
     for l in range(4):
