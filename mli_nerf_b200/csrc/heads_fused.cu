@@ -241,11 +241,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
       auto wait_full = [&](uint32_t c) { mbar_wait(full0 + 8 * (c % kSlots), (c / kSlots) & 1, 2); };
       for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
         for (int h = 0; h < nh; ++h) {
+          // Head boundary: the last stage of the previous head must have been drained (all four accumulators) and
+          // its `ready` phase must be COMPLETE before anything of this head is waited for: an mbarrier parity wait is
+          // only meaningful for the current or the immediately preceding phase, and the backward prologue stage has no
+          // MMAs -- without this wait the issuer would test the prologue's phase while the previous one is still
+          // open and pass through at once.
+          if (stage > 0)
+            for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
+          tc_fence_after();
           if (!BWD) {
             // ---- layer 0: both operands from the ring, k-major (all four accumulators finish together) ----
-            if (stage > 0)
-              for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
-            tc_fence_after();
             for (int ks = 0; ks < k0_steps; ++ks) {
               const int nch = min(4, p.k0_chunks - ks * 4);
               for (int i = 0; i < 4; ++i) wait_full(cnt + i);

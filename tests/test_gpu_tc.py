@@ -383,15 +383,14 @@ def test_relu_sign_mask_roundtrip(lib):
     assert float(d) < 1e-3, float(d)
 
 
-@pytest.mark.parametrize("mode,R", [("rgb_r_s", 256), ("rgb", 130), ("r_s_re", 64)])
+@pytest.mark.parametrize("mode,R", [("rgb_r_s", 256), ("rgb", 130), ("r_s_re", 64), ("rgb_r_s", 2401)])
 def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
     """csrc/heads_fused.cu (the whole head stack in one on-chip tcgen05 kernel, two 128-sample tiles per CTA) against the
     layer-by-layer tensor-core path on the same inputs: same bf16 roundings, same accumulation order -> the stored
     activations, relu sign bits and per-sample outputs agree to the last bit almost everywhere.  R = 130 / 64 give an ODD
-    number of 128-sample tiles (the last tile pair is half empty) resp. fewer pairs than SMs; rgb = one head, r_s_re = nine
-    narrow outputs, one of them without sigmoid."""
+    number of 128-sample tiles (the last tile pair is half empty) resp. fewer pairs than SMs; R = 2401 gives 1201 tile pairs
+    = 8 or 9 per persistent CTA (barrier phases carried across pairs); rgb = one head, r_s_re = nine narrow outputs."""
     from mli_nerf_b200.engine import RenderEngine
-    from oracle import port
     from tests.util import make_case, product_cfg
     from mli_nerf_b200.engine import head_layout
     case = make_case(R=R, mode=mode, progress=0.5)
@@ -404,10 +403,9 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
         eng.pack_weights(p)
         c, r, l = (case[k][0].contiguous().cuda() for k in ("center", "ray_unit", "light"))
         near, far, outside = eng.bounds(c, r)
-        with torch.no_grad():
-            ref = port.render_rays(case["params"], case["ocfg"], case["center"], case["ray_unit"], case["light"],
-                                   rands=case["rands"], training=True, progress=0.5)
-        dists = ref["dists"][0, :, :, 0].contiguous().cuda()
+        if "dists" not in res:  # the product's own sampling (bit-reproducible): the same distances for both runs
+            res["dists"] = eng.sample(p["neural_sdf.tcnn_encoding.params"], c, r, near, far, case["rands"].view(R, -1).cuda())
+        dists = res["dists"]
         out, ctx = eng.forward(p, c, r, l, dists, near, far, outside, True, 0.5)
         torch.cuda.synchronize()
         res[fused] = (out, ctx)
