@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLI_ABI_VERSION 2
+#define MLI_ABI_VERSION 3
 
 enum {
   MLI_OK = 0,

@@ -1025,6 +1025,10 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_tn_kernel(TcTN p) {
     }
     if constexpr (COLSUM) {
       if (do_cs) {  // all loads and MMAs have completed: the stage buffers are free -> [128 rows][129] fp32 transpose
+        // ... once EVERY column-sum warp has finished reading the last stage: `red` overlays stage 0, which is the last
+        // one read when this CTA's tile count is odd (a fast warp used to overwrite rows a slower warp was still summing:
+        // nondeterministic bias gradients for, e.g., 2401 row tiles)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         float* red = reinterpret_cast<float*>(smem);
 #pragma unroll
         for (int k = 0; k < 128; ++k) red[t * 129 + k] = n_t > 0 ? cs[k] : 0.0f;

@@ -383,11 +383,11 @@ def test_relu_sign_mask_roundtrip(lib):
     assert float(d) < 1e-3, float(d)
 
 
-@pytest.mark.parametrize("mode,R", [("rgb_r_s", 256), ("rgb", 130), ("r_s_re", 64), ("rgb_r_s", 2401)])
+@pytest.mark.parametrize("mode,R", [("rgb_r_s", 256), ("rgb", 131), ("r_s_re", 64), ("rgb_r_s", 2400), ("rgb_r_s", 2401)])
 def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
     """csrc/heads_fused.cu (the whole head stack in one on-chip tcgen05 kernel, two 128-sample tiles per CTA) against the
     layer-by-layer tensor-core path on the same inputs: same bf16 roundings, same accumulation order -> the stored
-    activations, relu sign bits and per-sample outputs agree to the last bit almost everywhere.  R = 130 / 64 give an ODD
+    activations, relu sign bits and per-sample outputs agree to the last bit almost everywhere.  R = 131 / 2401 give an ODD
     number of 128-sample tiles (the last tile pair is half empty) resp. fewer pairs than SMs; R = 2401 gives 1201 tile pairs
     = 8 or 9 per persistent CTA (barrier phases carried across pairs); rgb = one head, r_s_re = nine narrow outputs."""
     from mli_nerf_b200.engine import RenderEngine
@@ -437,7 +437,7 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
         eng.pack_weights(p)
         grads[fused] = eng.backward(p, res[fused][1], d_out, d_grad, None, None)
         torch.cuda.synchronize()
-    for k, g0 in grads[False].items():
-        g1 = grads[True][k]
-        err = float((g0 - g1).norm() / (g0.norm() + 1e-30))
-        assert err < 2e-3, (k, err)
+    errs = {k: float((g0 - grads[True][k]).norm() / (g0.norm() + 1e-30)) for k, g0 in grads[False].items()}
+    bad = {k: (e, bool(torch.isfinite(grads[False][k]).all()), bool(torch.isfinite(grads[True][k]).all()))
+           for k, e in errs.items() if not e < 2e-3}
+    assert not bad, bad  # (relative error, layer-by-layer finite, fused finite)
