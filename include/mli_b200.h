@@ -214,9 +214,9 @@ int mli_tc_sdf_trunk_bwd(const float* g, int64_t M, int32_t taps, const float* s
 /* Fused forward of the WHOLE head stack (LumenRGB.forward, NeuralLumen/utils/modules.py:106-174: per head the five
  * layers of MLPwithSkipConnection.forward, nerf_util.py:186-196) in one persistent tcgen05 kernel (csrc/heads_fused.cu):
  * the [256 x 256] hidden activations of a tile pair stay in shared memory between layers, weights stream from L2.
- * XH: TCL-128 input of head layer 0 (xh_chunks chunks per tile row, the first K0/8 are used); W0 / W1..W3: the
- * weight_norm-ed weights of all nh heads in TCL with 128-row tiles, [nh][2][K/8][128][8] (mli_weightnorm_pack_batch,
- * tcl2); bias0..3 [nh*256]; w_out [J,256] / b_out [J] fp32, head h owning outputs [host_j0[h], +host_nj[h]) (<= 4
+ * XH: TCL-128 input of head layer 0 (xh_chunks chunks per tile row, the first K0/8 are used); W0: layer-0 weights of
+ * all nh heads in TCL with 256-row tiles, [nh][K0/8][256][8]; W1..W3: hidden-layer weights in TCL with 128-row tiles,
+ * [nh][2][32][128][8] (mli_weightnorm_pack_batch, tcl / tcl2); bias0..3 [nh*256]; w_out [J,256] / b_out [J] fp32, head h owning outputs [host_j0[h], +host_nj[h]) (<= 4
  * each), act_out applied where bit j of act_mask is set.  store_activations != 0 (a backward pass follows): A0..A3
  * (bf16 TCL-128, nh*32 chunks per tile row) and the relu sign bits mask0..3 ([tiles][nh*8][128] uint32, may be NULL)
  * are written; otherwise nothing but S [M, lds] leaves the SM.  M % 128 == 0. */

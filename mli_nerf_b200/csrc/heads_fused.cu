@@ -12,15 +12,21 @@
 //     out: S[:, j] = act(w_out[j] . A3 + b_out[j])    row dot fused into L3's epilogue
 // Shared memory: two 64 KB activation tiles (rows 0..127 / 128..255 of the pair; UMMA K-major core-matrix layout =
 // byte-identical to one TCL tile, so a finished layer leaves the SM as ONE 32 KB TMA bulk store per column half, and only
-// when a backward pass will need it), a 9 x 8 KB ring (weights: [128 x 32] bf16 = one N-half x K32 slice), biases and
-// output-layer rows.  TMEM: four 128-column fp32 accumulators (tile x N-half).
+// when a backward pass will need it), an 8 x 8 KB ring (hidden-layer weights: [128 x 32] bf16 = one N-half x K32 slice;
+// layer 0: [256 x 16] weight slices and [128 x 32] XH slices), biases and output-layer rows.  TMEM: four 128-column fp32
+// accumulators (tile x N-half).
 // Why two tiles per CTA: every 8 KB weight slice read from L2 feeds 4 MMAs (2 tiles x 2 k-steps) = 256 tensor cycles, i.e.
 // 32 B/clk/SM of L2 traffic -- half of what one tile per CTA would need and under the ~42 B/clk/SM the L2 sustains with all
 // 148 SMs pulling.  The MMA order inside a hidden layer is (K-half 0: N0, N1), (K-half 1: N0, N1), each for both tiles:
 // the epilogue of column half N0 (which OVERWRITES activation columns 0..127 = K-half 0 of the next layer's operand)
 // starts while the K-half-1 MMAs of N1 still run, and the next layer's K-half-0 MMAs start before N1's epilogue ends.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue of column half 0, 6..9 = column half 1
-// (a warp may only touch TMEM lane quarter warp % 4).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..17 = four epilogue groups of four warps, one per
+// (tile, column half) accumulator (a warp may only touch TMEM lane quarter warp % 4).
+// Measured lesson (profiles/r02_heads_fused.md): the first version issued its MMAs from inside an `if (lane == 0)` region
+// with modulo-9 ring arithmetic; ncu showed the tensor pipe 23 % active with the eight epilogue warps parked on the
+// accumulator barrier and the issuing warp busy 100 % of the time (R2UR broadcast loops around every tcgen05 instruction).
+// The issuer now runs warp-uniform code (operands stay in uniform registers, only the tcgen05 instructions themselves are
+// predicated on lane 0), layer 0 uses N = 256 MMAs, and ring positions are carried incrementally.
 #include <cuda_bf16.h>
 #include <string.h>
 
@@ -31,8 +37,9 @@ namespace {
 constexpr int kRows = 128;            // rows of one activation tile (UMMA M)
 constexpr int kHid = 256;
 constexpr int kSlotBytes = 8192;      // [128 x 32] bf16
-constexpr int kSlots = 9;
-constexpr int kThreads = 320;         // 10 warps
+constexpr int kSlots = 8;             // power of two: ring positions advance with a mask
+constexpr int kEpiGroups = 4;         // (tile, column half)
+constexpr int kThreads = 64 + 128 * kEpiGroups;   // 18 warps
 constexpr int kMaxHeads = 3;
 constexpr int kMaxJ = 12;
 
@@ -87,10 +94,12 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void group_bar(int g) {  // the 128 threads of one epilogue group (named barriers 1, 2)
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+__device__ __forceinline__ void group_bar(int eg) {  // the 128 threads of one epilogue group (named barriers 1..4)
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
 }
-__device__ __forceinline__ void both_groups_bar() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+__device__ __forceinline__ void tile_bar(int t) {    // both column-half groups of one tile (named barriers 5, 6)
+  asm volatile("bar.sync %0, 256;" ::"r"(5 + t) : "memory");
+}
 
 // un-swizzled K-major shared-memory matrix descriptor (sm_100 version bits): LBO = bytes between 8-column chunks, SBO =
 // bytes between 8-row groups
@@ -101,6 +110,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   return d;
+}
+// the same descriptor with the start address left out: desc = desc_base(lbo, sbo) + (smem byte address >> 4)
+__device__ __forceinline__ uint64_t desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M = 128, N = n, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
@@ -143,7 +156,7 @@ struct HeadsArgs {
   // ---- forward ----
   const __nv_bfloat16* XH; int xh_chunks;         // TCL-128 [tiles][xh_chunks][128][8], K0 = 8 * k0_chunks columns used
   int k0_chunks;
-  const __nv_bfloat16* W0;                        // [nh][2 N-halves][k0_chunks][128][8]
+  const __nv_bfloat16* W0;                        // [nh][k0_chunks][256][8] (TCL with 256-row tiles: N = 256 MMAs)
   const float* bias[4];                           // [nh * 256] per layer
   const float* bout;                              // [J]
   int act_out; uint32_t act_mask;
@@ -161,14 +174,14 @@ struct HeadsArgs {
 };
 
 // Ring items the producer streams per head and tile pair (the MMA warp consumes them in the same order):
-//   forward L0, per K32 step: XH slice of tile 0, XH slice of tile 1, W0 slice of N-half 0, W0 slice of N-half 1
-//   every 256x256 layer, per quarter (K-half, N-half) in the order (0,0) (0,1) (1,0) (1,1): four K32 weight slices
+//   forward L0, per K32 step: XH slice of tile 0, XH slice of tile 1 ([128 x 32]), then one [256 x 16] W0 slice per K16 step
+//   every 256x256 layer, per quarter (K-half, N-half) in the order (0,0) (0,1) (1,0) (1,1): four [128 x 32] weight slices
 // Stages per head: forward  L0, L1, L2, L3 (+ output dot);  backward  P (dZ3 from dS, CUDA cores), L3', L2', L1'.
 // `ready[tile][half]` is arrived once per stage, `acc_full[tile][half]` once per stage that has MMAs.
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 * kSlots + 12];
+  __shared__ __align__(8) uint64_t bars[2 * kSlots + 8];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nh = p.nh;
@@ -205,24 +218,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer ------------------------------------
     if (lane == 0) {
-      uint32_t cnt = 0;
+      uint32_t slot = 0, par = 1;  // waiting for parity 1 on a fresh barrier passes at once: the first round finds the ring empty
       auto put = [&](const void* src, uint32_t bytes) {
-        const uint32_t s = cnt % kSlots;
-        if (cnt >= kSlots) mbar_wait(empty0 + 8 * s, ((cnt / kSlots) - 1) & 1, 1);
-        mbar_expect_tx(full0 + 8 * s, bytes);
-        bulk_g2s(sRing + s * kSlotBytes, src, bytes, full0 + 8 * s);
-        ++cnt;
+        mbar_wait(empty0 + 8 * slot, par, 1);
+        mbar_expect_tx(full0 + 8 * slot, bytes);
+        bulk_g2s(sRing + slot * kSlotBytes, src, bytes, full0 + 8 * slot);
+        slot = (slot + 1) & (kSlots - 1);
+        par ^= (slot == 0);
       };
       for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
         const int64_t t0 = 2 * (int64_t)pr, t1 = (t0 + 1 < p.n_tiles) ? t0 + 1 : t0;  // odd tile count: tile 0 twice
         for (int h = 0; h < nh; ++h) {
           for (int ks = 0; ks < k0_steps; ++ks) {
             const int nch = min(4, p.k0_chunks - ks * 4);
-            const uint32_t bytes = nch * 2048;
-            put(p.XH + (t0 * p.xh_chunks + ks * 4) * 1024, bytes);
-            put(p.XH + (t1 * p.xh_chunks + ks * 4) * 1024, bytes);
-            put(p.W0 + ((int64_t)(h * 2 + 0) * p.k0_chunks + ks * 4) * 1024, bytes);
-            put(p.W0 + ((int64_t)(h * 2 + 1) * p.k0_chunks + ks * 4) * 1024, bytes);
+            put(p.XH + (t0 * p.xh_chunks + ks * 4) * 1024, nch * 2048);
+            put(p.XH + (t1 * p.xh_chunks + ks * 4) * 1024, nch * 2048);
+            for (int kk = 0; kk < nch / 2; ++kk)  // [256 rows x 16 columns] = 2 chunks of the 256-row-tile layout
+              put(p.W0 + ((int64_t)h * p.k0_chunks + ks * 4 + kk * 2) * 2048, 8192);
           }
           for (int l = 0; l < 3; ++l)
             for (int q = 0; q < 4; ++q) {
@@ -235,191 +247,204 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer --------------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128);
-      uint32_t cnt = 0, stage = 0;  // ring items consumed / stages passed so far (`ready` flips once per stage)
-      auto wait_full = [&](uint32_t c) { mbar_wait(full0 + 8 * (c % kSlots), (c / kSlots) & 1, 2); };
-      for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-        for (int h = 0; h < nh; ++h) {
-          // Head boundary: the last stage of the previous head must have been drained (all four accumulators) and
-          // its `ready` phase must be COMPLETE before anything of this head is waited for: an mbarrier parity wait is
-          // only meaningful for the current or the immediately preceding phase, and the backward prologue stage has no
-          // MMAs -- without this wait the issuer would test the prologue's phase while the previous one is still
-          // open and pass through at once.
-          if (stage > 0)
-            for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
-          tc_fence_after();
-          if (!BWD) {
-            // ---- layer 0: both operands from the ring, k-major (all four accumulators finish together) ----
-            for (int ks = 0; ks < k0_steps; ++ks) {
-              const int nch = min(4, p.k0_chunks - ks * 4);
-              for (int i = 0; i < 4; ++i) wait_full(cnt + i);
+    // Warp-uniform control flow: all 32 lanes run the loops (every operand stays in uniform registers), lane 0 alone
+    // executes the tcgen05 instructions (tcgen05.commit tracks the MMAs of the thread that issues it).
+    // elect.sync names the same leader for the same member mask every time, and tells the compiler that exactly one lane
+    // runs the guarded instructions while their operands were computed warp-uniformly
+    auto elected = []() {
+      uint32_t pred;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+      return pred != 0;
+    };
+    const uint32_t idesc128 = make_idesc(128), idesc256 = make_idesc(256);
+    const uint64_t dA = desc_base(2048, 128);      // [128 rows][16 B] chunks, 2048 B apart (activation tiles, 128-row slots)
+    const uint64_t dB256 = desc_base(4096, 128);   // [256 rows][16 B] chunks, 4096 B apart (layer-0 weight slices)
+    uint32_t slot = 0, par = 0, stage = 0;         // ring position / stages passed so far (`ready` flips once per stage)
+    auto advance = [&]() { slot = (slot + 1) & (kSlots - 1); par ^= (slot == 0); };
+    for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+      for (int h = 0; h < nh; ++h) {
+        // Head boundary: the last stage of the previous head must have been drained (all four accumulators) and its
+        // `ready` phase must be COMPLETE before anything of this head is waited for: an mbarrier parity wait is only
+        // meaningful for the current or the immediately preceding phase, and the backward prologue stage has no MMAs.
+        if (stage > 0)
+          for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
+        tc_fence_after();
+        if (!BWD) {
+          // ---- layer 0: both operands from the ring, k-major, N = 256 (all four accumulators finish together) ----
+          for (int ks = 0; ks < k0_steps; ++ks) {
+            const int nk = min(4, p.k0_chunks - ks * 4) / 2;  // K16 steps in this K32 step
+            const uint32_t sa0 = sRing + slot * kSlotBytes, s0 = slot, p0 = par;
+            mbar_wait(full0 + 8 * slot, par, 2); advance();
+            const uint32_t sa1 = sRing + slot * kSlotBytes, s1 = slot;
+            mbar_wait(full0 + 8 * slot, par, 2); advance();
+            (void)p0;
+            for (int kk = 0; kk < nk; ++kk) {
+              const uint32_t sb = sRing + slot * kSlotBytes, sbs = slot;
+              mbar_wait(full0 + 8 * slot, par, 2); advance();
               tc_fence_after();
-              const uint32_t sa[2] = {sRing + ((cnt + 0) % kSlots) * kSlotBytes, sRing + ((cnt + 1) % kSlots) * kSlotBytes};
-              const uint32_t sb[2] = {sRing + ((cnt + 2) % kSlots) * kSlotBytes, sRing + ((cnt + 3) % kSlots) * kSlotBytes};
-              for (int t = 0; t < 2; ++t)
-                for (int nf = 0; nf < 2; ++nf)
-                  for (int kk = 0; kk < nch / 2; ++kk)
-                    umma(tmem_base + (t * 2 + nf) * 128, make_desc(sa[t] + kk * 4096, 2048, 128),
-                         make_desc(sb[nf] + kk * 4096, 2048, 128), idesc, (ks | kk) != 0);
-              for (int i = 0; i < 4; ++i) umma_commit(empty0 + 8 * ((cnt + i) % kSlots));
-              cnt += 4;
-            }
-            for (int i = 0; i < 4; ++i) umma_commit(acc_full0 + 8 * i);
-          }
-          ++stage;  // forward: L0 issued; backward: the prologue stage has no MMAs
-          // ---- three 256x256 layers: A operand = the activation tiles in shared memory ----
-          for (int l = 0; l < 3; ++l) {
-            for (int q = 0; q < 4; ++q) {
-              const int kh = q >> 1, nf = q & 1;
-              for (int it = 0; it < 4; ++it, ++cnt) {
-                wait_full(cnt);
-                tc_fence_after();
-                const uint32_t sb = sRing + (cnt % kSlots) * kSlotBytes;
-                for (int t = 0; t < 2; ++t) {
-                  if (kh == 0 && it == 0) {
-                    // first write of accumulator (t, nf) in this stage: its previous contents have been drained, and
-                    // activation column half nf of tile t (= K-half nf of this stage's A operand; K-half 0 is needed
-                    // from quarter (0,0) on, K-half 1 from quarter (1,0) on, i.e. after the wait of quarter (0,1))
-                    mbar_wait(ready0 + 8 * (t * 2 + nf), (stage - 1) & 1, 4);
-                    tc_fence_after();
-                  }
-                  const uint32_t sa = sAct + t * 65536 + (kh * 16 + it * 4) * 2048;
-                  for (int kk = 0; kk < 2; ++kk)
-                    umma(tmem_base + (t * 2 + nf) * 128, make_desc(sa + kk * 4096, 2048, 128),
-                         make_desc(sb + kk * 4096, 2048, 128), idesc, (kh | it | kk) != 0);
-                  if (kh == 1 && it == 3) umma_commit(acc_full0 + 8 * (t * 2 + nf));
-                }
-                umma_commit(empty0 + 8 * (cnt % kSlots));
+              if (elected()) {
+                umma(tmem_base, dA + ((sa0 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, (ks | kk) != 0);
+                umma(tmem_base + 256, dA + ((sa1 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, (ks | kk) != 0);
+                umma_commit(empty0 + 8 * sbs);
               }
             }
-            ++stage;
+            if (elected()) { umma_commit(empty0 + 8 * s0); umma_commit(empty0 + 8 * s1); }
           }
+          if (elected())
+            for (int i = 0; i < 4; ++i) umma_commit(acc_full0 + 8 * i);
+        }
+        ++stage;  // forward: L0 issued; backward: the prologue stage has no MMAs
+        // ---- three 256x256 layers: A operand = the activation tiles in shared memory ----
+        for (int l = 0; l < 3; ++l) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kh = q >> 1, nf = q & 1;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const uint32_t sb = sRing + slot * kSlotBytes, sbs = slot;
+              mbar_wait(full0 + 8 * slot, par, 2); advance();
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                if (kh == 0 && it == 0) {
+                  // first write of accumulator (t, nf) in this stage: its previous contents have been drained, and
+                  // activation column half nf of tile t (= K-half nf of this stage's A operand; K-half 0 is needed
+                  // from quarter (0,0) on, K-half 1 from quarter (1,0) on, i.e. after the wait of quarter (0,1))
+                  mbar_wait(ready0 + 8 * (t * 2 + nf), (stage - 1) & 1, 4);
+                }
+                tc_fence_after();
+                if (elected()) {
+                  const uint32_t sa = sAct + t * 65536 + (kh * 16 + it * 4) * 2048;
+                  umma(tmem_base + (t * 2 + nf) * 128, dA + (sa >> 4), dA + (sb >> 4), idesc128, (kh | it) != 0);
+                  umma(tmem_base + (t * 2 + nf) * 128, dA + ((sa + 4096) >> 4), dA + ((sb + 4096) >> 4), idesc128, 1u);
+                  if (kh == 1 && it == 3) umma_commit(acc_full0 + 8 * (t * 2 + nf));
+                }
+              }
+              if (elected()) umma_commit(empty0 + 8 * sbs);
+            }
+          }
+          ++stage;
         }
       }
     }
   } else {
     // ---------------------------------------------------------------- epilogue ----------------------------------------
-    const int g = (warp - 2) >> 2;            // column half this group owns
+    const int eg = (warp - 2) >> 2;           // epilogue group = accumulator it owns
+    const int t = eg >> 1, g = eg & 1;        // tile of the pair, column half
     const int q = warp & 3;                   // TMEM lane quarter
     const int r_local = q * 32 + lane;
-    const bool leader = (threadIdx.x == 64 + g * 128);
+    const bool leader = (threadIdx.x == 64 + eg * 128);
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool store = BWD || p.A[0] != nullptr;
+    uint8_t* act = smem + t * 65536 + (size_t)(g * 16) * 2048 + r_local * 16;
     uint32_t n_acc = 0;  // stages with MMAs passed so far (`acc_full` flips once per such stage)
     for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-      const bool pair_full = 2 * pr + 1 < p.n_tiles;
+      const int64_t tile = 2 * (int64_t)pr + t;
+      const bool live = tile < p.n_tiles;
+      const int64_t row = tile * kRows + r_local;
       for (int h = 0; h < nh; ++h) {
+        const float* wd = s_wout + p.j0[h] * kHid + g * 128;
+        const int njh = p.nj[h];
+        const int64_t mrow = (tile * (nh * 8) + h * 8 + g * 4) * kRows + r_local;  // + c * kRows per 32-column chunk
         for (int l = 0; l < 4; ++l) {
           const bool has_acc = !(BWD && l == 0);
           const float* bias = s_bias + (l * nh + h) * kHid + g * 128;
-          const float* wd = s_wout + p.j0[h] * kHid + g * 128;
-          const int njh = p.nj[h];
           // relu sign bits this stage reads (backward: of the activation whose pre-activation gradient it produces)
           const uint32_t* mask_in = BWD ? p.mask[3 - l] : nullptr;
           uint32_t* mask_out = BWD ? nullptr : p.mask[l];
-          for (int t = 0; t < 2; ++t) {
-            const int64_t tile = 2 * (int64_t)pr + t;
-            const bool live = tile < p.n_tiles;
-            const int64_t row = tile * kRows + r_local;
-            const int64_t mrow = (tile * (nh * 8) + h * 8 + g * 4) * kRows + r_local;  // + c * kRows per 32-column chunk
-            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
-            float ds[4] = {0.f, 0.f, 0.f, 0.f};
-            if (BWD && live) {
+          uint32_t mb0 = 0u, mb1 = 0u, mb2 = 0u, mb3 = 0u;
+          float ds[4] = {0.f, 0.f, 0.f, 0.f};
+          if (BWD && live) {
+            mb0 = __ldg(mask_in + mrow); mb1 = __ldg(mask_in + mrow + kRows);
+            mb2 = __ldg(mask_in + mrow + 2 * kRows); mb3 = __ldg(mask_in + mrow + 3 * kRows);
+            if (l == 0) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) mbits[c] = __ldg(mask_in + mrow + c * kRows);
-              if (l == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < njh && row < p.M) ds[j] = __ldg(p.dS + row * p.lds + p.j0[h] + j);
-              }
+              for (int j = 0; j < 4; ++j)
+                if (j < njh && row < p.M) ds[j] = __ldg(p.dS + row * p.lds + p.j0[h] + j);
             }
-            if (store) {
-              // the bulk store that read this activation half (previous stage, same tile) must be done reading before
-              // the half is rewritten; the store of the OTHER tile, issued after it, may still be in flight
-              if (leader) { if (pair_full) bulk_wait_read1(); else bulk_wait_read0(); }
-              group_bar(g);
-            }
-            if (has_acc) {
-              mbar_wait(acc_full0 + 8 * (t * 2 + g), n_acc & 1, 5);
-              tc_fence_after();
-            }
-            float dj[4] = {0.f, 0.f, 0.f, 0.f};
-            uint8_t* act = smem + t * 65536 + (size_t)(g * 16) * 2048 + r_local * 16;
+          }
+          if (store) {
+            // the bulk store that read this activation half (previous stage) must be done reading before it is rewritten
+            if (leader) bulk_wait_read0();
+            group_bar(eg);
+          }
+          if (has_acc) {
+            mbar_wait(acc_full0 + 8 * eg, n_acc & 1, 5);
+            tc_fence_after();
+            ++n_acc;
+          }
+          float dj[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              float v[32];
-              if (has_acc) tmem_ld32(tmem_base + lane_addr + (t * 2 + g) * 128 + c * 32, v);
-              if (!BWD) {
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            if (has_acc) tmem_ld32(tmem_base + lane_addr + eg * 128 + c * 32, v);
+            if (!BWD) {
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i4 * 4);
-                  v[i4 * 4 + 0] = fmaxf(v[i4 * 4 + 0] + b4.x, 0.0f); v[i4 * 4 + 1] = fmaxf(v[i4 * 4 + 1] + b4.y, 0.0f);
-                  v[i4 * 4 + 2] = fmaxf(v[i4 * 4 + 2] + b4.z, 0.0f); v[i4 * 4 + 3] = fmaxf(v[i4 * 4 + 3] + b4.w, 0.0f);
-                }
-                if (mask_out != nullptr && live) {
-                  // v >= +0 after relu: v > 0 <=> bits(v) + 0x7fffffff carries into the sign bit; funnel shift collects it
-                  uint32_t bits = 0;
-#pragma unroll
-                  for (int i = 31; i >= 0; --i) bits = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, bits, 1);
-                  mask_out[mrow + c * kRows] = bits;
-                }
-                if (l == 3) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (j < njh) {
-#pragma unroll
-                      for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], wd[j * kHid + c * 32 + i], dj[j]);
-                    }
-                }
-              } else {
-                if (l == 0) {  // prologue: dA3 = dS . W_out (the narrow output layers' data gradient)
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (j < njh) {
-#pragma unroll
-                      for (int i = 0; i < 32; ++i) v[i] = fmaf(ds[j], wd[j * kHid + c * 32 + i], v[i]);
-                    }
-                }
-                const uint32_t mb = mbits[c];  // relu'(activation) from its sign bits
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] : 0.0f;
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i4 * 4);
+                v[i4 * 4 + 0] = fmaxf(v[i4 * 4 + 0] + b4.x, 0.0f); v[i4 * 4 + 1] = fmaxf(v[i4 * 4 + 1] + b4.y, 0.0f);
+                v[i4 * 4 + 2] = fmaxf(v[i4 * 4 + 2] + b4.z, 0.0f); v[i4 * 4 + 3] = fmaxf(v[i4 * 4 + 3] + b4.w, 0.0f);
               }
+              if (mask_out != nullptr && live) {
+                // v >= +0 after relu: v > 0 <=> bits(v) + 0x7fffffff carries into the sign bit; funnel shift collects it
+                uint32_t bits = 0;
 #pragma unroll
-              for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = pack8(v + gq * 8);
-            }
-            if (has_acc) tc_fence_before();
-            fence_async_smem();   // generic-proxy writes of the activation half -> visible to UMMA / the bulk store
-            if (!BWD && l == 3) {  // output layer: column half 1 hands its partial row dots to column half 0
-              float* dp = s_dotp + (size_t)t * 4 * kRows + r_local;
-              if (g == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dp[j * kRows] = dj[j];
+                for (int i = 31; i >= 0; --i) bits = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, bits, 1);
+                mask_out[mrow + c * kRows] = bits;
               }
-              both_groups_bar();
-              if (g == 0 && live && row < p.M) {
+              if (l == 3) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   if (j < njh) {
-                    const int jo = p.j0[h] + j;
-                    const float r = dj[j] + dp[j * kRows] + s_bout[jo];
-                    p.S[row * p.lds + jo] = ((p.act_mask >> jo) & 1u) ? mli_act(r, p.act_out) : r;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], wd[j * kHid + c * 32 + i], dj[j]);
                   }
               }
-              both_groups_bar();  // s_dotp[t] is free again (next head) once every reader is past this point
-            }
-            group_bar(g);
-            if (leader) {
-              mbar_arrive(ready0 + 8 * (t * 2 + g));
-              if (store && live) {
-                bulk_s2g(p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024, sAct + t * 65536 + g * 32768, 32768);
-                bulk_commit();
+            } else {
+              if (l == 0) {  // prologue: dA3 = dS . W_out (the narrow output layers' data gradient)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < njh) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(ds[j], wd[j * kHid + c * 32 + i], v[i]);
+                  }
               }
+              const uint32_t mb = c == 0 ? mb0 : c == 1 ? mb1 : c == 2 ? mb2 : mb3;  // relu'(activation) from its sign bits
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] : 0.0f;
+            }
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = pack8(v + gq * 8);
+          }
+          if (has_acc) tc_fence_before();
+          fence_async_smem();   // generic-proxy writes of the activation half -> visible to UMMA / the bulk store
+          if (!BWD && l == 3) {  // output layer: column half 1 hands its partial row dots to column half 0
+            float* dp = s_dotp + (size_t)t * 4 * kRows + r_local;
+            if (g == 1) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dp[j * kRows] = dj[j];
+            }
+            tile_bar(t);
+            if (g == 0 && live && row < p.M) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < njh) {
+                  const int jo = p.j0[h] + j;
+                  const float r = dj[j] + dp[j * kRows] + s_bout[jo];
+                  p.S[row * p.lds + jo] = ((p.act_mask >> jo) & 1u) ? mli_act(r, p.act_out) : r;
+                }
+            }
+            tile_bar(t);  // s_dotp[t] is free again (next head) once every reader is past this point
+          }
+          group_bar(eg);
+          if (leader) {
+            mbar_arrive(ready0 + 8 * eg);
+            if (store && live) {
+              bulk_s2g(p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024, sAct + t * 65536 + g * 32768, 32768);
+              bulk_commit();
             }
           }
-          if (has_acc) ++n_acc;
         }
       }
     }
@@ -469,8 +494,8 @@ int fill_heads(HeadsArgs* p, int32_t nh, const int32_t* host_j0, const int32_t* 
 }  // namespace
 
 // Fused forward of the whole head stack (see the header of this file).  XH: TCL-128 input of head layer 0 (K0 = 8 *
-// k0_chunks <= 8 * xh_chunks columns); W0 / W1..W3: weight_norm-ed weights in TCL with 128-row tiles ([nh][2][chunks][128][8],
-// written by mli_weightnorm_pack_batch); bias0..3 [nh * 256]; w_out [J, 256] / b_out [J] fp32 with head h owning outputs
+// k0_chunks <= 8 * xh_chunks columns); W0: TCL with 256-row tiles [nh][K0/8][256][8]; W1..W3: TCL with 128-row tiles
+// [nh][2][32][128][8] (both written by mli_weightnorm_pack_batch); bias0..3 [nh * 256]; w_out [J, 256] / b_out [J] fp32 with head h owning outputs
 // [host_j0[h], host_j0[h] + host_nj[h]); A0..A3 (bf16 TCL-128, nh * 32 chunks) and mask0..3 (relu sign bits) are written
 // only when store_activations != 0 (a backward pass follows); S [M, lds] fp32 = act_j(w_out[j] . A3 + b_out[j]).
 extern "C" int mli_tc_heads_fwd(const void* XH, int64_t M, int32_t nh, int32_t K0, int32_t store_activations,

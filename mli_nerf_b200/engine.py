@@ -299,8 +299,7 @@ class RenderEngine:
         for l in range(3):
             sizes[f"Whl{l}"] = nh * HID * HID
             sizes[f"Whlt{l}"] = nh * HID * HID
-        if self.fuse_heads:  # the same forward weights in 128-row tiles: [head][N-half][K/8][128][8] (csrc/heads_fused.cu)
-            sizes["Wh0_128"] = nh * HID * KH_PAD
+        if self.fuse_heads:  # hidden-layer weights (and transposes) in 128-row tiles: [head][N-half][32][128][8]
             for l in range(3):
                 sizes[f"Whl128_{l}"] = nh * HID * HID
                 sizes[f"Whlt128_{l}"] = nh * HID * HID
@@ -318,7 +317,6 @@ class RenderEngine:
         T["Whl"] = [buf[f"Whl{l}"].view(nh, 32, 256, 8) for l in range(3)]
         T["Whlt"] = [buf[f"Whlt{l}"].view(nh, 32, 256, 8) for l in range(3)]
         if self.fuse_heads:
-            T["Wh0_128"] = buf["Wh0_128"].view(nh * 2, KH_PAD // 8, 128, 8)
             T["Whl128"] = [buf[f"Whl128_{l}"].view(nh * 2, 32, 128, 8) for l in range(3)]
             T["Whlt128"] = [buf[f"Whlt128_{l}"].view(nh * 2, 32, 128, 8) for l in range(3)]  # rows = input unit
         W["Wout"] = self._f(self.J, HID)
@@ -346,8 +344,6 @@ class RenderEngine:
                 d.tclt[1] = T["Wh0t_x"].data_ptr()
                 d.tclt_c0[1], d.tclt_c1[1], d.tclt_tile[1], d.tclt_chunks[1] = XH_OFF, KH_PAD, KH_PAD - XH_OFF, nh * 32
                 d.tclt_col_off[1] = hi * HID
-                if self.fuse_heads:
-                    d.tcl2, d.tcl2_tile, d.tcl2_chunks = T["Wh0_128"].data_ptr(), 128, KH_PAD // 8
             elif tag[0] == "hl":
                 _, l, hi = tag
                 d.tcl, d.tcl_tile, d.tcl_chunks = T["Whl"][l].data_ptr(), 256, 32
@@ -579,7 +575,7 @@ class RenderEngine:
                 j0s.append(j)
                 njs.append(h[2])
                 j += h[2]
-            fused = self.fuse_heads and "Wh0_128" in T
+            fused = self.fuse_heads and "Whl128" in T
             # hidden activations: kept (bf16 TCL) only when a backward pass follows -- the fused kernel needs no HBM copy
             A = [self._tcl(M, nh * 32) if (keep_dz or not fused) else None for _ in range(4)]
             # relu sign bits of every hidden activation (only when a backward pass follows): the data-gradient
@@ -587,7 +583,7 @@ class RenderEngine:
             Am = [self._mask(M, nh * HID) if keep_dz else None for _ in range(4)]
         if self.tc and fused:
             # the whole head stack (layer 0 .. output layers) in ONE persistent kernel: activations stay in shared memory
-            call("mli_tc_heads_fwd", XH, M, nh, KH_PAD, int(keep_dz), KH_PAD // 8, T["Wh0_128"], T["Whl128"][0],
+            call("mli_tc_heads_fwd", XH, M, nh, KH_PAD, int(keep_dz), KH_PAD // 8, T["Wh0"], T["Whl128"][0],
                  T["Whl128"][1], T["Whl128"][2], W["bh"][0], W["bh"][1], W["bh"][2], W["bh"][3], W["Wout"], W["bout"], j0s,
                  njs, ACT_SIGMOID, self.act_mask, A[0], A[1], A[2], A[3], Am[0], Am[1], Am[2], Am[3], S, self.lds)
         elif self.tc:

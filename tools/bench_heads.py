@@ -48,7 +48,7 @@ def main():
         j += h[2]
 
     def fwd(store):
-        call("mli_tc_heads_fwd", XH, M, nh, KH_PAD, int(store), KH_PAD // 8, T["Wh0_128"], T["Whl128"][0], T["Whl128"][1],
+        call("mli_tc_heads_fwd", XH, M, nh, KH_PAD, int(store), KH_PAD // 8, T["Wh0"], T["Whl128"][0], T["Whl128"][1],
              T["Whl128"][2], W["bh"][0], W["bh"][1], W["bh"][2], W["bh"][3], W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID,
              eng.act_mask, A[0] if store else None, A[1] if store else None, A[2] if store else None,
              A[3] if store else None, Am[0] if store else None, Am[1] if store else None, Am[2] if store else None,
