@@ -143,6 +143,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// relu on a packed pair of bf16 (the pack rounds first: max(round(x), 0) == round(max(x, 0)) for round-to-nearest)
+__device__ __forceinline__ uint32_t relu_pack2(float a, float b) {
+  __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(a, b), __floats2bfloat162_rn(0.0f, 0.0f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
   __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
@@ -177,7 +194,15 @@ struct HeadsArgs {
 //   forward L0, per K32 step: XH slice of tile 0, XH slice of tile 1 ([128 x 32]), then one [256 x 16] W0 slice per K16 step
 //   every 256x256 layer, per quarter (K-half, N-half) in the order (0,0) (0,1) (1,0) (1,1): four [128 x 32] weight slices
 // Stages per head: forward  L0, L1, L2, L3 (+ output dot);  backward  P (dZ3 from dS, CUDA cores), L3', L2', L1'.
-// `ready[tile][half]` is arrived once per stage, `acc_full[tile][half]` once per stage that has MMAs.
+// `acc_full[tile][half]` completes once per stage that has MMAs.  `ready[tile][half]` ("accumulator drained, activation
+// half written, next stage's bias stored") is arrived by the owning epilogue group
+//   forward:  once before the first stage of the kernel (bias of L0 stored into the accumulator) and after every stage;
+//   backward: after P, L3', L2' -- NOT after L1': the prologue of the next head needs nothing from the MMA warp, so an
+//             arrival after L1' could be followed by the prologue's arrival before the MMA warp has looked at the
+//             barrier, and a parity wait cannot tell a phase that completed twice from one that has not completed.
+// The MMA warp waits for exactly one new arrival per (tile, half) before the first MMA of every stage.
+// Forward bias: the accumulators are pre-loaded with the NEXT stage's bias by the epilogue (tcgen05.st) and every MMA
+// accumulates -- 32 FADDs per 32-column chunk and row leave the epilogue, which is what limits this kernel.
 template <bool BWD>
 __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_constant__ HeadsArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -259,32 +284,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     const uint32_t idesc128 = make_idesc(128), idesc256 = make_idesc(256);
     const uint64_t dA = desc_base(2048, 128);      // [128 rows][16 B] chunks, 2048 B apart (activation tiles, 128-row slots)
     const uint64_t dB256 = desc_base(4096, 128);   // [256 rows][16 B] chunks, 4096 B apart (layer-0 weight slices)
-    uint32_t slot = 0, par = 0, stage = 0;         // ring position / stages passed so far (`ready` flips once per stage)
+    uint32_t slot = 0, par = 0, na = 0;            // ring position / `ready` arrivals consumed so far (per barrier)
     auto advance = [&]() { slot = (slot + 1) & (kSlots - 1); par ^= (slot == 0); };
     for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
       for (int h = 0; h < nh; ++h) {
-        // Head boundary: the last stage of the previous head must have been drained (all four accumulators) and its
-        // `ready` phase must be COMPLETE before anything of this head is waited for: an mbarrier parity wait is only
-        // meaningful for the current or the immediately preceding phase, and the backward prologue stage has no MMAs.
-        if (stage > 0)
-          for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, (stage - 1) & 1, 3);
-        tc_fence_after();
         if (!BWD) {
-          // ---- layer 0: both operands from the ring, k-major, N = 256 (all four accumulators finish together) ----
+          // ---- layer 0: both operands from the ring, k-major, N = 256 (all four accumulators finish together);
+          //      accumulators hold the bias already ----
+          for (int i = 0; i < 4; ++i) mbar_wait(ready0 + 8 * i, na & 1, 3);
+          ++na;
+          tc_fence_after();
           for (int ks = 0; ks < k0_steps; ++ks) {
             const int nk = min(4, p.k0_chunks - ks * 4) / 2;  // K16 steps in this K32 step
-            const uint32_t sa0 = sRing + slot * kSlotBytes, s0 = slot, p0 = par;
+            const uint32_t sa0 = sRing + slot * kSlotBytes, s0 = slot;
             mbar_wait(full0 + 8 * slot, par, 2); advance();
             const uint32_t sa1 = sRing + slot * kSlotBytes, s1 = slot;
             mbar_wait(full0 + 8 * slot, par, 2); advance();
-            (void)p0;
             for (int kk = 0; kk < nk; ++kk) {
               const uint32_t sb = sRing + slot * kSlotBytes, sbs = slot;
               mbar_wait(full0 + 8 * slot, par, 2); advance();
               tc_fence_after();
               if (elected()) {
-                umma(tmem_base, dA + ((sa0 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, (ks | kk) != 0);
-                umma(tmem_base + 256, dA + ((sa1 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, (ks | kk) != 0);
+                umma(tmem_base, dA + ((sa0 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, 1u);
+                umma(tmem_base + 256, dA + ((sa1 + kk * 4096) >> 4), dB256 + (sb >> 4), idesc256, 1u);
                 umma_commit(empty0 + 8 * sbs);
               }
             }
@@ -293,7 +315,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
           if (elected())
             for (int i = 0; i < 4; ++i) umma_commit(acc_full0 + 8 * i);
         }
-        ++stage;  // forward: L0 issued; backward: the prologue stage has no MMAs
         // ---- three 256x256 layers: A operand = the activation tiles in shared memory ----
         for (int l = 0; l < 3; ++l) {
 #pragma unroll
@@ -306,15 +327,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
 #pragma unroll
               for (int t = 0; t < 2; ++t) {
                 if (kh == 0 && it == 0) {
-                  // first write of accumulator (t, nf) in this stage: its previous contents have been drained, and
-                  // activation column half nf of tile t (= K-half nf of this stage's A operand; K-half 0 is needed
-                  // from quarter (0,0) on, K-half 1 from quarter (1,0) on, i.e. after the wait of quarter (0,1))
-                  mbar_wait(ready0 + 8 * (t * 2 + nf), (stage - 1) & 1, 4);
+                  // first write of accumulator (t, nf) in this stage: its previous contents have been drained (forward:
+                  // and replaced by this stage's bias), and activation column half nf of tile t (= K-half nf of this
+                  // stage's A operand; K-half 0 is needed from quarter (0,0) on, K-half 1 from quarter (1,0) on, i.e.
+                  // after the wait of quarter (0,1)) has been written
+                  mbar_wait(ready0 + 8 * (t * 2 + nf), na & 1, 4);
                 }
                 tc_fence_after();
                 if (elected()) {
                   const uint32_t sa = sAct + t * 65536 + (kh * 16 + it * 4) * 2048;
-                  umma(tmem_base + (t * 2 + nf) * 128, dA + (sa >> 4), dA + (sb >> 4), idesc128, (kh | it) != 0);
+                  umma(tmem_base + (t * 2 + nf) * 128, dA + (sa >> 4), dA + (sb >> 4), idesc128, BWD ? (uint32_t)((kh | it) != 0) : 1u);
                   umma(tmem_base + (t * 2 + nf) * 128, dA + ((sa + 4096) >> 4), dA + ((sb + 4096) >> 4), idesc128, 1u);
                   if (kh == 1 && it == 3) umma_commit(acc_full0 + 8 * (t * 2 + nf));
                 }
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
               if (elected()) umma_commit(empty0 + 8 * sbs);
             }
           }
-          ++stage;
+          ++na;
         }
       }
     }
@@ -337,6 +359,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
     const bool store = BWD || p.A[0] != nullptr;
     uint8_t* act = smem + t * 65536 + (size_t)(g * 16) * 2048 + r_local * 16;
     uint32_t n_acc = 0;  // stages with MMAs passed so far (`acc_full` flips once per such stage)
+    // bias of the stage that comes after (h, l) in this CTA's stage sequence (forward); NULL after the very last one
+    auto next_bias = [&](int pr, int h, int l) -> const float* {
+      if (l < 3) return s_bias + ((l + 1) * nh + h) * kHid + g * 128;
+      if (h + 1 < nh) return s_bias + (h + 1) * kHid + g * 128;
+      return (pr + (int)gridDim.x < n_pairs) ? s_bias + g * 128 : nullptr;
+    };
+    auto store_bias = [&](const float* b) {  // accumulator (t, g) <- b broadcast over the rows
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(b + c * 32 + i4 * 4);
+          v[i4 * 4 + 0] = b4.x; v[i4 * 4 + 1] = b4.y; v[i4 * 4 + 2] = b4.z; v[i4 * 4 + 3] = b4.w;
+        }
+        tmem_st32(tmem_base + lane_addr + eg * 128 + c * 32, v);
+      }
+      tmem_st_wait();
+    };
+    if (!BWD && (int)blockIdx.x < n_pairs) {  // forward stage "-1": layer-0 bias of the first head into the accumulators
+      store_bias(s_bias + g * 128);
+      tc_fence_before();
+      group_bar(eg);
+      if (leader) mbar_arrive(ready0 + 8 * eg);
+    }
     for (int pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
       const int64_t tile = 2 * (int64_t)pr + t;
       const bool live = tile < p.n_tiles;
@@ -347,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
         const int64_t mrow = (tile * (nh * 8) + h * 8 + g * 4) * kRows + r_local;  // + c * kRows per 32-column chunk
         for (int l = 0; l < 4; ++l) {
           const bool has_acc = !(BWD && l == 0);
-          const float* bias = s_bias + (l * nh + h) * kHid + g * 128;
+          const float* nbias = BWD ? nullptr : next_bias(pr, h, l);
           // relu sign bits this stage reads (backward: of the activation whose pre-activation gradient it produces)
           const uint32_t* mask_in = BWD ? p.mask[3 - l] : nullptr;
           uint32_t* mask_out = BWD ? nullptr : p.mask[l];
@@ -378,20 +425,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             float v[32];
             if (has_acc) tmem_ld32(tmem_base + lane_addr + eg * 128 + c * 32, v);
             if (!BWD) {
+              // v = pre-activation (the bias was in the accumulator).  The chunk has been read: hand it the next stage's bias.
+              if (nbias != nullptr) {
+                float nb[32];
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i4 * 4);
-                v[i4 * 4 + 0] = fmaxf(v[i4 * 4 + 0] + b4.x, 0.0f); v[i4 * 4 + 1] = fmaxf(v[i4 * 4 + 1] + b4.y, 0.0f);
-                v[i4 * 4 + 2] = fmaxf(v[i4 * 4 + 2] + b4.z, 0.0f); v[i4 * 4 + 3] = fmaxf(v[i4 * 4 + 3] + b4.w, 0.0f);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(nbias + c * 32 + i4 * 4);
+                  nb[i4 * 4 + 0] = b4.x; nb[i4 * 4 + 1] = b4.y; nb[i4 * 4 + 2] = b4.z; nb[i4 * 4 + 3] = b4.w;
+                }
+                tmem_st32(tmem_base + lane_addr + eg * 128 + c * 32, nb);
               }
               if (mask_out != nullptr && live) {
-                // v >= +0 after relu: v > 0 <=> bits(v) + 0x7fffffff carries into the sign bit; funnel shift collects it
-                uint32_t bits = 0;
+                // relu'(x) as the complement of the sign bit: one funnel shift per element collects the signs (x >= +0 is
+                // kept; the layer-by-layer kernels test x > 0 -- they differ for an exact +0.0 only, where the activation
+                // itself is 0)
+                uint32_t neg = 0;
 #pragma unroll
-                for (int i = 31; i >= 0; --i) bits = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, bits, 1);
-                mask_out[mrow + c * kRows] = bits;
+                for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(v[i]), neg, 1);
+                mask_out[mrow + c * kRows] = ~neg;
               }
               if (l == 3) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   if (j < njh) {
@@ -399,6 +454,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                     for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], wd[j * kHid + c * 32 + i], dj[j]);
                   }
               }
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                uint4 o;
+                o.x = relu_pack2(v[gq * 8 + 0], v[gq * 8 + 1]); o.y = relu_pack2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                o.z = relu_pack2(v[gq * 8 + 4], v[gq * 8 + 5]); o.w = relu_pack2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = o;
+              }
+              continue;
             } else {
               if (l == 0) {  // prologue: dA3 = dS . W_out (the narrow output layers' data gradient)
 #pragma unroll
@@ -417,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = pack8(v + gq * 8);
           }
+          if (!BWD) tmem_st_wait();  // the next stage's bias is in the accumulator before `ready` is signalled
           if (has_acc) tc_fence_before();
           fence_async_smem();   // generic-proxy writes of the activation half -> visible to UMMA / the bulk store
           if (!BWD && l == 3) {  // output layer: column half 1 hands its partial row dots to column half 0
@@ -439,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
           }
           group_bar(eg);
           if (leader) {
-            mbar_arrive(ready0 + 8 * eg);
+            if (!(BWD && l == 3)) mbar_arrive(ready0 + 8 * eg);
             if (store && live) {
               bulk_s2g(p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024, sAct + t * 65536 + g * 32768, 32768);
               bulk_commit();
