@@ -155,32 +155,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// 16-column variants.  tmem_ld16_async leaves the load in flight; tmem_ld16_wait() completes it and -- by naming the
-// destination registers as read-write operands -- keeps every use of them behind the wait.
-__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16_wait(float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 // relu on a packed pair of bf16 (the pack rounds first: max(round(x), 0) == round(max(x, 0)) for round-to-nearest)
 __device__ __forceinline__ uint32_t relu_pack2(float a, float b) {
   __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(a, b), __floats2bfloat162_rn(0.0f, 0.0f));
@@ -424,16 +398,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
           // relu sign bits this stage reads (backward: of the activation whose pre-activation gradient it produces)
           const uint32_t* mask_in = BWD ? p.mask[3 - l] : nullptr;
           uint32_t* mask_out = BWD ? nullptr : p.mask[l];
-          uint32_t mb[4] = {0u, 0u, 0u, 0u};
+          uint32_t mb0 = 0u, mb1 = 0u, mb2 = 0u, mb3 = 0u;
           float ds[4] = {0.f, 0.f, 0.f, 0.f};
           if (BWD && live) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) mb[c] = __ldg(mask_in + mrow + c * kRows);
+            mb0 = __ldg(mask_in + mrow); mb1 = __ldg(mask_in + mrow + kRows);
+            mb2 = __ldg(mask_in + mrow + 2 * kRows); mb3 = __ldg(mask_in + mrow + 3 * kRows);
             if (l == 0) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (j < njh && row < p.M) ds[j] = __ldg(p.dS + row * p.lds + p.j0[h] + j);
             }
+          }
+          if (store) {
+            // the bulk store that read this activation half (previous stage) must be done reading before it is rewritten
+            if (leader) bulk_wait_read0();
+            group_bar(eg);
           }
           if (has_acc) {
             mbar_wait(acc_full0 + 8 * eg, n_acc & 1, 5);
@@ -441,78 +420,65 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             ++n_acc;
           }
           float dj[4] = {0.f, 0.f, 0.f, 0.f};
-          // global copy of this activation half (bf16 TCL, the same bytes as the shared-memory tile): 16 B per thread and
-          // 8-column chunk straight from the registers, 512 contiguous bytes per warp -- a TMA bulk store of the finished
-          // half had the next stage's epilogue waiting for the store engine to finish READING the tile
-          __nv_bfloat16* gdst = (store && live) ? p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024 + r_local * 8 : nullptr;
-          // 8 sub-chunks of 16 columns; the TMEM load of sub-chunk s + 1 is in flight while s is processed
-          float v[2][16];
-          const uint32_t tacc = tmem_base + lane_addr + eg * 128;
-          if (has_acc) { tmem_ld16_async(tacc, v[0]); tmem_ld16_wait(v[0]); }
-          uint32_t mword = 0;
-#pragma unroll
-          for (int sc = 0; sc < 8; ++sc) {
-            float* x = v[sc & 1];
-            if (has_acc && sc + 1 < 8) tmem_ld16_async(tacc + (sc + 1) * 16, v[(sc + 1) & 1]);
-            uint4 o0, o1;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            if (has_acc) tmem_ld32(tmem_base + lane_addr + eg * 128 + c * 32, v);
             if (!BWD) {
-              // x = pre-activation (the bias was in the accumulator).  The sub-chunk has been read: hand it the next stage's bias.
+              // v = pre-activation (the bias was in the accumulator).  The chunk has been read: hand it the next stage's bias.
               if (nbias != nullptr) {
-                float nb[16];
+                float nb[32];
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(nbias + sc * 16 + i4 * 4);
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(nbias + c * 32 + i4 * 4);
                   nb[i4 * 4 + 0] = b4.x; nb[i4 * 4 + 1] = b4.y; nb[i4 * 4 + 2] = b4.z; nb[i4 * 4 + 3] = b4.w;
                 }
-                tmem_st16(tacc + sc * 16, nb);
+                tmem_st32(tmem_base + lane_addr + eg * 128 + c * 32, nb);
               }
-              if (mask_out != nullptr) {
+              if (mask_out != nullptr && live) {
                 // relu'(x) as the complement of the sign bit: one funnel shift per element collects the signs (x >= +0 is
                 // kept; the layer-by-layer kernels test x > 0 -- they differ for an exact +0.0 only, where the activation
                 // itself is 0)
+                uint32_t neg = 0;
 #pragma unroll
-                for (int i = 15; i >= 0; --i) mword = __funnelshift_l(__float_as_uint(x[i]), mword, 1);
-                if (sc & 1) {  // two 16-bit halves (the second one sits in the low half now): one word per 32 columns
-                  if (live) mask_out[mrow + (sc >> 1) * kRows] = ~((mword << 16) | (mword >> 16));
-                  mword = 0;
-                }
+                for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(v[i]), neg, 1);
+                mask_out[mrow + c * kRows] = ~neg;
               }
               if (l == 3) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.0f);
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   if (j < njh) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) dj[j] = fmaf(x[i], wd[j * kHid + sc * 16 + i], dj[j]);
+                    for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], wd[j * kHid + c * 32 + i], dj[j]);
                   }
               }
-              o0.x = relu_pack2(x[0], x[1]); o0.y = relu_pack2(x[2], x[3]); o0.z = relu_pack2(x[4], x[5]); o0.w = relu_pack2(x[6], x[7]);
-              o1.x = relu_pack2(x[8], x[9]); o1.y = relu_pack2(x[10], x[11]); o1.z = relu_pack2(x[12], x[13]); o1.w = relu_pack2(x[14], x[15]);
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                uint4 o;
+                o.x = relu_pack2(v[gq * 8 + 0], v[gq * 8 + 1]); o.y = relu_pack2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                o.z = relu_pack2(v[gq * 8 + 4], v[gq * 8 + 5]); o.w = relu_pack2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = o;
+              }
+              continue;
             } else {
               if (l == 0) {  // prologue: dA3 = dS . W_out (the narrow output layers' data gradient)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = 0.0f;
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   if (j < njh) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) x[i] = fmaf(ds[j], wd[j * kHid + sc * 16 + i], x[i]);
+                    for (int i = 0; i < 32; ++i) v[i] = fmaf(ds[j], wd[j * kHid + c * 32 + i], v[i]);
                   }
               }
-              const uint32_t m16 = mb[sc >> 1] >> ((sc & 1) * 16);  // relu'(activation) from its sign bits
+              const uint32_t mb = c == 0 ? mb0 : c == 1 ? mb1 : c == 2 ? mb2 : mb3;  // relu'(activation) from its sign bits
 #pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = ((m16 >> i) & 1u) ? x[i] : 0.0f;
-              o0 = pack8(x);
-              o1 = pack8(x + 8);
+              for (int i = 0; i < 32; ++i) v[i] = ((mb >> i) & 1u) ? v[i] : 0.0f;
             }
-            *reinterpret_cast<uint4*>(act + (size_t)(sc * 2) * 2048) = o0;
-            *reinterpret_cast<uint4*>(act + (size_t)(sc * 2 + 1) * 2048) = o1;
-            if (gdst != nullptr) {
-              *reinterpret_cast<uint4*>(gdst + (size_t)(sc * 2) * 1024) = o0;
-              *reinterpret_cast<uint4*>(gdst + (size_t)(sc * 2 + 1) * 1024) = o1;
-            }
-            if (has_acc && sc + 1 < 8) tmem_ld16_wait(v[(sc + 1) & 1]);
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) *reinterpret_cast<uint4*>(act + (size_t)(c * 4 + gq) * 2048) = pack8(v + gq * 8);
           }
           if (!BWD) tmem_st_wait();  // the next stage's bias is in the accumulator before `ready` is signalled
           if (has_acc) tc_fence_before();
@@ -536,10 +502,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
             tile_bar(t);  // s_dotp[t] is free again (next head) once every reader is past this point
           }
           group_bar(eg);
-          if (leader && !(BWD && l == 3)) mbar_arrive(ready0 + 8 * eg);
+          if (leader) {
+            if (!(BWD && l == 3)) mbar_arrive(ready0 + 8 * eg);
+            if (store && live) {
+              bulk_s2g(p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024, sAct + t * 65536 + g * 32768, 32768);
+              bulk_commit();
+            }
+          }
         }
       }
     }
+    if (leader) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();

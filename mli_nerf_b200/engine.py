@@ -139,8 +139,13 @@ class RenderEngine:
         self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
-        # bf16 mode: the head stack as ONE on-chip kernel (csrc/heads_fused.cu); MLI_FUSE_HEADS=0 = layer-by-layer GEMMs
-        self.fuse_heads = os.environ.get("MLI_FUSE_HEADS", "0") == "1"
+        # bf16 mode: the head stack as ONE on-chip kernel per direction (csrc/heads_fused.cu).  Measured at the bench shape
+        # (tools/bench_heads.py, profiles/r02_heads_fused.md): data-gradient chain 435 us fused vs 564 us layer by layer;
+        # forward WITHOUT stored activations (inference / no-grad) 493 us vs 579 us; forward that also has to write the
+        # four activation matrices + relu masks for the backward pass 685 us vs 579 us -- so a training forward keeps the
+        # layer-by-layer GEMMs (MLI_FUSE_HEADS_TRAIN_FWD=1 forces the fused kernel, MLI_FUSE_HEADS=0 disables all of it)
+        self.fuse_heads = os.environ.get("MLI_FUSE_HEADS", "1") == "1"
+        self.fuse_heads_train_fwd = os.environ.get("MLI_FUSE_HEADS_TRAIN_FWD", "0") == "1"
         # persistent buffer the table gradient is accumulated in (multi-GPU: the IPC-shared buffer of PeerTableReducer);
         # None: a fresh zero-filled buffer per step
         self.table_grad_buffer = None
@@ -575,7 +580,7 @@ class RenderEngine:
                 j0s.append(j)
                 njs.append(h[2])
                 j += h[2]
-            fused = self.fuse_heads and "Whl128" in T
+            fused = self.fuse_heads and "Whl128" in T and (not keep_dz or self.fuse_heads_train_fwd)
             # hidden activations: kept (bf16 TCL) only when a backward pass follows -- the fused kernel needs no HBM copy
             A = [self._tcl(M, nh * 32) if (keep_dz or not fused) else None for _ in range(4)]
             # relu sign bits of every hidden activation (only when a backward pass follows): the data-gradient

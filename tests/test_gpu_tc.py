@@ -398,7 +398,7 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
     res = {}
     for fused in (False, True):
         eng = RenderEngine(product_cfg(case["ocfg"], precision=1))
-        eng.fuse_heads = fused
+        eng.fuse_heads = eng.fuse_heads_train_fwd = fused  # also the (default-off) fused training forward
         p = {k: v.contiguous().cuda() for k, v in case["params"].items()}
         eng.pack_weights(p)
         c, r, l = (case[k][0].contiguous().cuda() for k in ("center", "ray_unit", "light"))
