@@ -449,9 +449,11 @@ int mli_light_rays(const float* center, const float* ray_unit, const float* inte
 int mli_light_finish(const uint8_t* mask_light, const uint8_t* inside_bounding, const float* gradient,
                      const float* light_unit, int64_t R, uint8_t* visibility, float* normal_x_light, void* stream);
 
-/* dense AdamW step (torch.optim.AdamW semantics, get_trainer.py:106-150) fused with gradient scaling (1/world). */
-int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+/* dense AdamW step (torch.optim.AdamW semantics, get_trainer.py:106-150) fused with gradient scaling (1/world).
+ * Hyper-parameters arrive as doubles: 1 - beta, 1 - lr*wd and the bias corrections are formed in double and rounded once,
+ * as torch forms them from the Python floats. */
+int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int32_t step, double grad_scale,
                    void* stream);
 
 /* The same update for every tensor of an optimizer group in ONE launch (descriptors in HOST memory, at most
@@ -460,8 +462,8 @@ int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
 typedef struct {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t n;
 } mli_adamw_desc_t;
-int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, float lr, float beta1, float beta2,
-                         float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int32_t step, double grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Multi-GPU exchange of the hash-table gradient over NVLink peer memory (mli_nerf_b200/dist.py): replaces the DDP
@@ -479,6 +481,14 @@ int mli_peer_free(void* ptr);
 int mli_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
 int mli_reduce_slots(float* dst, const float* slots, int32_t n_slots, int64_t slot_stride, int64_t n, float scale,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * L2 residency of the dense hash-grid levels (tcnn keeps no such control; north star (a)): access-policy window on
+ * `stream` over [ptr, ptr+bytes) -- persisting with probability hit_ratio, everything else streaming; bytes == 0
+ * removes it.  mli_l2_info reports the device's L2 size, maximum persisting carve-out and maximum window size.
+ * ---------------------------------------------------------------------------------------------------- */
+int mli_set_l2_window(const void* ptr, int64_t bytes, float hit_ratio, void* stream);
+int mli_l2_info(int32_t* host_out_l2_bytes, int32_t* host_out_max_persist_bytes, int32_t* host_out_max_window_bytes);
 
 #ifdef __cplusplus
 }

@@ -101,7 +101,7 @@ def _parse_header(path=HEADER_PATH):
 
 
 _SIGS = {k: v for k, v in _parse_header().items() if k not in ("mli_abi_version", "mli_device_ok", "mli_grid_init",
-                                                                "mli_set_sm_limit", "mli_peer_alloc", "mli_peer_open")}
+                                                                "mli_set_sm_limit", "mli_peer_alloc", "mli_peer_open", "mli_l2_info")}
 HOST_ONLY = {"mli_enable_peer_access", "mli_peer_close", "mli_peer_free"}  # management calls: no stream argument
 _CTYPE = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "d": C.c_double, "u": C.c_uint32,
           "s": C.c_void_p, "h": C.c_void_p, "H": C.c_void_p}
@@ -221,7 +221,7 @@ def _n_launches(name, args):
         return 1 + (1 if args[18] is not None else 0)
     if name in ("mli_weightnorm_pack_batch", "mli_weightnorm_unpack_grad_batch"):
         return 1
-    if name in ("mli_copy_async", "mli_enable_peer_access"):
+    if name in ("mli_copy_async", "mli_enable_peer_access", "mli_set_l2_window"):
         return 0  # copy-engine transfer / host call: no kernel
     if name == "mli_losses_fwd_bwd":
         return 3 + (1 if args[0].has_intrinsic else 0)
@@ -333,6 +333,15 @@ def peer_open(handle, device):
     if code != 0:
         _raise(code, "mli_peer_open")
     return ptr.value
+
+
+def l2_info():
+    """-> (L2 bytes, maximum persisting carve-out, maximum access-policy window) of the current device."""
+    out = (C.c_int32 * 3)()
+    code = load().mli_l2_info(C.byref(out, 0), C.byref(out, 4), C.byref(out, 8))
+    if code != 0:
+        _raise(code, "mli_l2_info")
+    return int(out[0]), int(out[1]), int(out[2])
 
 
 def set_sm_limit(n_sms):

@@ -83,3 +83,45 @@ extern "C" int mli_grid_init(mli_grid_t* grid, uint32_t n_levels, uint32_t feat,
   grid->n_entries = (uint32_t)offset;
   return MLI_OK;
 }
+
+// L2 residency control for the dense levels of the hash table (north star (a): "L2-resident tables"): an access-policy
+// window on `stream` marks [ptr, ptr + bytes) as persisting in L2 with probability hit_ratio (the rest of the stream's
+// traffic -- the 1.3 GB of hashed levels, activations -- is unaffected); bytes == 0 removes the window.  The persisting
+// carve-out of L2 is raised to what the window needs (capped by the device limit).  Kernels captured into a CUDA graph
+// from this stream inherit the window.
+extern "C" int mli_set_l2_window(const void* ptr, int64_t bytes, float hit_ratio, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(bytes >= 0 && hit_ratio >= 0.0f && hit_ratio <= 1.0f, "l2_window: bad bytes / hit_ratio");
+  int dev = 0;
+  MLI_CUDA_OK(cudaGetDevice(&dev));
+  int max_win = 0, max_persist = 0;
+  MLI_CUDA_OK(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  MLI_CUDA_OK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (bytes > 0 && ptr != nullptr) {
+    size_t win = (size_t)bytes < (size_t)max_win ? (size_t)bytes : (size_t)max_win;
+    size_t carve = (size_t)((double)win * hit_ratio);
+    if (carve > (size_t)max_persist) carve = (size_t)max_persist;
+    MLI_CUDA_OK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = hit_ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;
+  }
+  MLI_CUDA_OK(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  return MLI_OK;
+}
+
+extern "C" int mli_l2_info(int32_t* host_out_l2_bytes, int32_t* host_out_max_persist_bytes, int32_t* host_out_max_window_bytes) {
+  MLI_ENTRY();
+  int dev = 0, v = 0;
+  MLI_CUDA_OK(cudaGetDevice(&dev));
+  if (host_out_l2_bytes) { MLI_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev)); *host_out_l2_bytes = v; }
+  if (host_out_max_persist_bytes) { MLI_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev)); *host_out_max_persist_bytes = v; }
+  if (host_out_max_window_bytes) { MLI_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev)); *host_out_max_window_bytes = v; }
+  return MLI_OK;
+}

@@ -274,8 +274,20 @@ static int make_wn_batch(WnBatch* b, const mli_wn_desc_t* descs, int32_t n, int*
 // AdamW (torch.optim.AdamW single-tensor semantics), gradient pre-scaled by grad_scale (1/world_size)
 // ---------------------------------------------------------------------------------------------------------
 struct AdamHyper {
-  float lr, b1, b2, eps, wd, step_size, inv_bc2_sqrt, gs;  // step_size = lr / (1 - b1^t), inv_bc2_sqrt = 1 / sqrt(1 - b2^t)
+  // every derived constant is formed in double on the host, as torch forms them from the Python floats, and rounded once:
+  // omb1 = 1 - beta1, omb2 = 1 - beta2 (NOT 1 - float(beta2): 4.7e-5 relative apart for 0.999), decay = 1 - lr * wd,
+  // step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t)
+  float b2, omb1, omb2, eps, decay, step_size, inv_bc2_sqrt, gs;
 };
+
+static AdamHyper make_adam_hyper(double lr, double b1, double b2, double eps, double wd, int step, double gs) {
+  AdamHyper h;
+  h.b2 = (float)b2; h.omb1 = (float)(1.0 - b1); h.omb2 = (float)(1.0 - b2); h.eps = (float)eps;
+  h.decay = (float)(1.0 - lr * wd); h.gs = (float)gs;
+  h.step_size = (float)(lr / (1.0 - pow(b1, (double)step)));
+  h.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(b2, (double)step)));
+  return h;
+}
 
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;
@@ -285,9 +297,9 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 
 __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, const AdamHyper& h) {
   const float gr = g * h.gs;
-  p *= 1.0f - h.lr * h.wd;
-  m = m + (gr - m) * (1.0f - h.b1);  // lerp form used by torch
-  v = v * h.b2 + (1.0f - h.b2) * gr * gr;
+  p *= h.decay;
+  m = m + (gr - m) * h.omb1;  // lerp form used by torch
+  v = v * h.b2 + h.omb2 * gr * gr;
   // 84 % of the hash-table entries see a zero gradient in a step and 38 % still have v == 0: the IEEE sqrtf / division
   // take their special-case slow paths for those (measured: 2.75 ms instead of 1.5 ms for the table), so both use the
   // branch-free MUFU forms (<= 2 ulp each; denom >= eps is always in __fdividef's range)
@@ -461,17 +473,14 @@ extern "C" int mli_weightnorm_unpack_grad(const float* v, const float* g, const 
 }
 
 extern "C" int mli_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                              float grad_scale, void* stream) {
+                              double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                              double grad_scale, void* stream) {
   MLI_ENTRY();
   MLI_REQUIRE(n >= 0 && step >= 1, "adamw: bad n/step");
   MLI_REQUIRE(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
               "adamw: buffers must be 16-byte aligned");
   if (n == 0) return MLI_OK;
-  AdamHyper h;
-  h.lr = lr; h.b1 = beta1; h.b2 = beta2; h.eps = eps; h.wd = weight_decay; h.gs = grad_scale;
-  h.step_size = lr / (1.0f - powf(beta1, (float)step));
-  h.inv_bc2_sqrt = 1.0f / sqrtf(1.0f - powf(beta2, (float)step));
+  const AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > 16 * MLI_NUM_SMS) blocks = 16 * MLI_NUM_SMS;
@@ -481,8 +490,8 @@ extern "C" int mli_adamw_step(float* param, const float* grad, float* exp_avg, f
   return MLI_OK;
 }
 
-extern "C" int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, float lr, float beta1,
-                                    float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+extern "C" int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32_t n_descs, double lr, double beta1,
+                                    double beta2, double eps, double weight_decay, int32_t step, double grad_scale,
                                     void* stream) {
   MLI_ENTRY();
   MLI_REQUIRE(descs_on_host != nullptr && n_descs >= 0 && n_descs <= MLI_ADAMW_MAX_TENSORS, "adamw batch: bad descriptors");
@@ -503,10 +512,7 @@ extern "C" int mli_adamw_step_batch(const mli_adamw_desc_t* descs_on_host, int32
   if (b.n == 0) return MLI_OK;
   MLI_REQUIRE(blocks < (1ull << 31), "adamw batch: too many elements for one launch");
   b.first_block[b.n] = (uint32_t)blocks;
-  AdamHyper h;
-  h.lr = lr; h.b1 = beta1; h.b2 = beta2; h.eps = eps; h.wd = weight_decay; h.gs = grad_scale;
-  h.step_size = lr / (1.0f - powf(beta1, (float)step));
-  h.inv_bc2_sqrt = 1.0f / sqrtf(1.0f - powf(beta2, (float)step));
+  const AdamHyper h = make_adam_hyper(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
   adamw_batch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(b, h);
   MLI_LAUNCH_OK();
   return MLI_OK;

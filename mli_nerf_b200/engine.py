@@ -144,6 +144,11 @@ class RenderEngine:
         # forward WITHOUT stored activations (inference / no-grad) 493 us vs 579 us; forward that also has to write the
         # four activation matrices + relu masks for the backward pass 685 us vs 579 us -- so a training forward keeps the
         # layer-by-layer GEMMs (MLI_FUSE_HEADS_TRAIN_FWD=1 forces the fused kernel, MLI_FUSE_HEADS=0 disables all of it)
+        # L2 persisting window over the DENSE levels of the table (levels whose grid fits the table: 0-5 at T = 2^22, 119 MB
+        # fp32) on the stream the encode kernels run on: MLI_L2_PERSIST=<hit ratio in (0,1]>, 0 = off (default; measured
+        # A/B in profiles/r02_summary.md)
+        self.l2_persist = float(os.environ.get("MLI_L2_PERSIST", "0"))
+        self._l2_key = None
         self.fuse_heads = os.environ.get("MLI_FUSE_HEADS", "1") == "1"
         self.fuse_heads_train_fwd = os.environ.get("MLI_FUSE_HEADS_TRAIN_FWD", "0") == "1"
         # persistent buffer the table gradient is accumulated in (multi-GPU: the IPC-shared buffer of PeerTableReducer);
@@ -461,9 +466,26 @@ class RenderEngine:
         call("mli_rowdot_fwd", H, HID, R * n, W["w_sdf"], W["b_sdf"], [0], 1, HID, ACT_NONE, 0, sdf, 1)
         return sdf
 
+    def dense_table_bytes(self):
+        """Bytes of the leading, densely indexed levels of the table (the part worth keeping in L2)."""
+        lv, n = self.grid.level, self.cfg.n_levels
+        first_hashed = next((l for l in range(n) if lv[l].hashed), n)
+        end = int(lv[first_hashed].offset) if first_hashed < n else int(self.grid.n_entries)
+        return end * self.cfg.feat_per_level * 4
+
+    def apply_l2_window(self, table):
+        """(Re)install the access-policy window when the table pointer / stream changes; no-op when MLI_L2_PERSIST is 0."""
+        if self.l2_persist <= 0.0:
+            return
+        key = (table.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if key != self._l2_key:
+            call("mli_set_l2_window", table, self.dense_table_bytes(), self.l2_persist)
+            self._l2_key = key
+
     def sample(self, table, center, ray_unit, near, far, rands=None):
         """Model.sample_dists_all (neuralangelo/model.py:449-465): coarse + hierarchical importance sampling."""
         cfg, R, N = self.cfg, center.shape[0], self.cfg.n_samples
+        self.apply_l2_window(table)
         dists, sdfs = self._f(R, N), self._f(R, N)
         call("mli_sample_coarse", near, far, rands, R, cfg.coarse, dists, N)
         n = cfg.coarse
