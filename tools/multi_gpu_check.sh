@@ -17,7 +17,8 @@ run $TR --master-port 29735 tests/multi/inference_shard_check.py
 grep -E "_OK|rc=" $OUT.log
 for table in reduce_scatter allreduce; do
   echo "== bench --gpus $N exchange=$table" | tee -a $OUT.log
-  MLI_TABLE_EXCHANGE=$table timeout 400 $TR --master-port 29740 bench.py --gpus $N --steps 30 --warmup 5 --no-cpu-baseline \
+  EXTRA=""; [ "$table" = "allreduce" ] && EXTRA="--no-extras"
+  MLI_TABLE_EXCHANGE=$table timeout 400 $TR --master-port 29740 bench.py --gpus $N --steps 30 --warmup 5 --no-cpu-baseline $EXTRA \
       > ${OUT}_bench_$table.json 2>> $OUT.log
   echo "rc=$?" | tee -a $OUT.log
   python - <<PY
