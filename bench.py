@@ -590,17 +590,18 @@ def run_extras(args, world, rank, model, cfg, lcfg, dev, barrier, build, step):
         return ms
 
     # ---- the true drop-in path: model(data) -> torch-side losses -> backward() (autograd node = our kernels) --------
+    # (single-GPU figure: at N > 1 the reference wraps this path in DDP, which is not what this section measures)
     def dropin(i):
         for p in model.parameters():
             p.grad = None
         o = model(dev[i % len(dev)])
         trainer_losses_torch(cfg.trainer, o, dev[i % len(dev)]).backward()
-    for i in range(3):
-        dropin(i)
-    ms, _ = timed(dropin, k, barrier)
-    ms = agg(ms)
-    out["autograd_dropin"] = {"value": world * RAYS * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k,
-                              "note": "model(data) -> torch losses -> backward(), eager, no gradient exchange"}
+    if world == 1:
+        for i in range(3):
+            dropin(i)
+        ms, _ = timed(dropin, k, barrier)
+        out["autograd_dropin"] = {"value": RAYS * k / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / k,
+                                  "note": "model(data) -> torch losses -> backward(), eager launches"}
 
     # ---- render: 800x800 view, chunks of 20 000 rays, frame's rays partitioned over the ranks ----------------------
     H = W = 800

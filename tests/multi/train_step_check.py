@@ -78,13 +78,20 @@ for mode in (os.environ.get("MLI_TABLE_ALLREDUCE", "peer"),):
         torch.cuda.synchronize()
         for q, (n, p) in zip(ref_p, model.named_parameters()):
             err = float((p.detach() - q.detach()).abs().max())
-            assert err < 2e-6 * (1.0 + float(q.detach().abs().max())), (n, err)
+            # first AdamW step: the update is lr * g / (|g| + eps), so where |g| ~ eps = 1e-8 a 1e-12 difference between two
+            # exact-looking means moves the parameter by a fraction of lr = 1e-3: bound = 2 % of lr
+            assert err < 2e-5, (n, err)
         chk = tab.detach().double().sum().reshape(1)
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         assert all(float(c) == float(allc[0]) for c in allc)  # bitwise identical parameter replicas
         m, v = opt.gather_state()
-        assert m.shape == tab.shape and float(m.abs().max()) > 0 and float(v.min()) >= 0
+        stats = (tuple(m.shape), tuple(tab.shape), float(m.abs().max()), float(v.min()), float(v.max()),
+                 int(torch.isnan(m).sum()), int(torch.isnan(v).sum()))
+        assert m.shape == tab.shape and stats[2] > 0 and stats[3] >= 0 and stats[5] == 0 and stats[6] == 0, stats
+        # dense moments == torch's after the same single step: exp_avg = 0.1 g, exp_avg_sq = 0.001 g^2
+        gm = want[TAB].view(-1)
+        assert float((m.view(-1) - 0.1 * gm).abs().max()) <= 1e-6 * float(gm.abs().max()) + 1e-12, "gathered exp_avg"
     reducer.close()
 if rank == 0:
     print(f"TRAIN_STEP_EXCHANGE_OK world={world} table={table_mode}", flush=True)
