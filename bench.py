@@ -124,37 +124,72 @@ def workload_cfg(name, precision):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons of THIS rank's GPU during the timed region (B200_PROFILING.md recipe), read in-process
+    through NVML (nvidia_ml_py).  Round 2 lesson: the nvidia-smi subprocess this used to spawn five times a second on
+    every rank takes driver-wide locks while it enumerates all GPUs -- at N = 8 forty of them per second stalled every
+    rank's kernel launches (host enqueue 9.4 ms per step during the sampled loop, 4 ms without the sampler).  Falls
+    back to one nvidia-smi query per second when NVML cannot be imported."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
-        self.sm_max = None
+        self.sm_max, self.source = None, "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml, self.source = None, "nvidia-smi"
 
-    def run(self):
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [v.strip() for v in out.split(",")]
+        self.samples.append(float(f[0]))
+        self.sm_max = float(f[1])
+        for (name, _), v in zip(self.REASONS, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [v.strip() for v in out.split(",")]
-                self.samples.append(float(f[0]))
-                self.sm_max = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                self._sample_nvml() if self._nvml is not None else self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02 if self._nvml is not None else 1.0)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.source}
 
 
 def peaks():
@@ -446,7 +481,11 @@ def main():
     def step(batch, graph=use_graph):
         return model.fused_train_step(batch, lcfg, use_graph=graph, after_backward=hook)
 
-    for i in range(args.warmup):
+    # N > 1: the first few dozen steps of a process group run well below the steady state (lazy NCCL connections per
+    # message size and protocol, allocator pools of eight processes still growing: 13.4 -> 9.5 ms per step over the first
+    # 40 steps in round 1), so at least 40 untimed steps are run there; the line reports the warm-up actually done.
+    n_warm = args.warmup if world == 1 else max(args.warmup, 40)
+    for i in range(n_warm):
         step(dev[i % n_batches])
     barrier()
 
@@ -533,12 +572,13 @@ def main():
         if t.get("precision") == args.precision and t.get("grad") == args.grad and args.workload == "syn_hotdog_b":
             traffic = t.get("dense_layers_dram_bytes_per_step")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms / args.steps, "host_enqueue_ms_per_step": host_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][4], "grad": args.grad, "precision": args.precision,
                    "rays_per_gpu": RAYS, "samples_per_ray": n_s, "cuda_graph": use_graph, "exchange": exchange,
+                   "warmup_requested": args.warmup,
                    "l2": "inputs larger than L2: 1.46 GB hash table + 1.46 GB gradient "
                    "buffer streamed every step (L2 = 126 MB), 8 rotating ray batches"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0]},

@@ -248,48 +248,57 @@ def call(name, *args):
     LAUNCH_COUNT += _n_launches(name, args)
 
 
+_FN = {}  # entry point name -> (ctypes function, signature string): resolved once, the call path is hot in eager mode
+
+
 def _call(name, *args):
-    lib = load()
-    sig = _SIGS[name]
-    # device guard: every tensor of a call lives on ONE GPU and the launch goes to that GPU's current stream, whatever
-    # the caller's current device is (a model on cuda:1 driven from a process whose current device is cuda:0)
-    dev = None
-    for a in args:
-        if isinstance(a, torch.Tensor) and a.is_cuda:
-            if dev is None:
-                dev = a.device.index
-            elif a.device.index != dev:
-                raise MliError(f"{name}: tensors on different devices (cuda:{dev} and cuda:{a.device.index})")
-    if dev is not None and dev != torch.cuda.current_device():
-        with torch.cuda.device(dev):
-            return _call(name, *args)
-    if len(args) == len(sig) - 1:
-        args = args + (stream_ptr(),)
-    if len(args) != len(sig):
-        raise TypeError(f"{name}: expected {len(sig)} arguments, got {len(args)}")
-    conv, keep = [], []
-    for c, a in zip(sig, args):
-        if c in "ps":
-            conv.append(_ptr(a))
-        elif c == "h":
+    ent = _FN.get(name)
+    if ent is None:
+        ent = _FN[name] = (getattr(load(), name), _SIGS[name])
+    fn, sig = ent
+    n = len(sig)
+    if len(args) == n - 1 and sig[-1] == "s":
+        args = args + (None,)  # stream slot, filled below once the device is known
+    elif len(args) != n:
+        raise TypeError(f"{name}: expected {n} arguments, got {len(args)}")
+    # One pass: convert, and check that every tensor of the call lives on ONE GPU -- the launch goes to that GPU's current
+    # stream whatever the caller's current device is (a model on cuda:1 driven while the current device is cuda:0).
+    conv, keep, dev = [None] * n, None, -1
+    for k in range(n):
+        c, a = sig[k], args[k]
+        if c == "p":
             if a is None:
-                conv.append(None)
+                continue
+            if isinstance(a, torch.Tensor):
+                d = a.device
+                if d.type != "cuda":
+                    raise MliError("libmli_b200 takes CUDA tensors only (no CPU fallback)")
+                if dev != d.index:
+                    if dev >= 0:
+                        raise MliError(f"{name}: tensors on different devices (cuda:{dev} and cuda:{d.index})")
+                    dev = d.index
+                conv[k] = a.data_ptr()
+            elif isinstance(a, C.Structure):
+                conv[k] = C.addressof(a)
             else:
-                arr = (C.c_int32 * len(a))(*[int(v) for v in a])
-                keep.append(arr)
-                conv.append(C.addressof(arr))
-        elif c == "H":
-            if a is None:
-                conv.append(None)
-            else:
-                arr = (C.c_float * len(a))(*[float(v) for v in a])
-                keep.append(arr)
-                conv.append(C.addressof(arr))
-        elif c in "f" "d":
-            conv.append(float(a))
+                conv[k] = int(a)
+        elif c == "s":
+            conv[k] = a  # resolved below
+        elif c == "h" or c == "H":
+            if a is not None:
+                arr = ((C.c_int32 if c == "h" else C.c_float) * len(a))(*a)
+                keep = (keep or []) + [arr]
+                conv[k] = C.addressof(arr)
+        elif c == "f" or c == "d":
+            conv[k] = float(a)
         else:
-            conv.append(int(a))
-    code = getattr(lib, name)(*conv)
+            conv[k] = int(a)
+    if dev >= 0 and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call(name, *args[:-1]) if args[-1] is None and sig[-1] == "s" else _call(name, *args)
+    if sig[-1] == "s" and conv[-1] is None:
+        conv[-1] = stream_ptr()
+    code = fn(*conv)
     if code != 0:
         _raise(code, name)
 

@@ -85,7 +85,10 @@ for mode in (os.environ.get("MLI_TABLE_ALLREDUCE", "peer"),):
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         assert all(float(c) == float(allc[0]) for c in allc)  # bitwise identical parameter replicas
+        pre = [(k, float(st[0].abs().max()), float(st[1].max())) for k, st in sorted(opt.state.items())]
         m, v = opt.gather_state()
+        if rank == 0:
+            print("moments per owned shard (range, max |m|, max v):", pre, flush=True)
         stats = (tuple(m.shape), tuple(tab.shape), float(m.abs().max()), float(v.min()), float(v.max()),
                  int(torch.isnan(m).sum()), int(torch.isnan(v).sum()))
         assert m.shape == tab.shape and stats[2] > 0 and stats[3] >= 0 and stats[5] == 0 and stats[6] == 0, stats
