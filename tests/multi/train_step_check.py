@@ -25,6 +25,16 @@ cfg.model.render.stratified = False
 torch.manual_seed(0)  # same weights on every rank
 model = Model(cfg.model, cfg.data).cuda().train()
 model.progress = 0.5
+# The reference's geometric init zeroes the hash-encoding columns of SDF layer 0 (mlp.py:71-84): the table gradient would
+# be exactly zero and every check of its exchange vacuous.  Give those columns (and the table) some weight, identically on
+# every rank.
+with torch.no_grad():
+    g0 = torch.Generator(device="cuda").manual_seed(1234)
+    w0 = model.neural_sdf.mlp.linears[0].weight_v
+    w0[:, 3:] = torch.randn(w0[:, 3:].shape, device="cuda", generator=g0) * 0.3
+    model.neural_sdf.mlp.linears[0].weight_g.copy_(w0.norm(dim=1, keepdim=True))
+    tab0 = model.neural_sdf.tcnn_encoding.params
+    tab0.copy_((torch.rand(tab0.shape, device="cuda", generator=g0) * 2 - 1) * 5e-3)
 lcfg = loss_cfg_from_trainer(cfg.trainer)
 data = {k: v.cuda() for k, v in bench.synthetic_batch(R, 100 + rank).items()}  # different rays per rank
 
@@ -35,6 +45,7 @@ for n, p in model.named_parameters():
     dist.all_reduce(g, op=dist.ReduceOp.AVG)
     want[n] = g
     p.grad = None
+assert float(want["neural_sdf.tcnn_encoding.params"].abs().max()) > 0, "table gradient is zero: the exchange checks would be vacuous"
 
 table_mode = os.environ.get("MLI_TABLE_EXCHANGE", "allreduce")
 TAB = "neural_sdf.tcnn_encoding.params"
