@@ -28,4 +28,15 @@ except Exception as e:
     print("$table", "no bench line:", e)
 PY
 done
+echo "== bench --gpus $N exchange=reduce_scatter MLI_COMM_SMS=16" | tee -a $OUT.log
+MLI_COMM_SMS=16 timeout 200 $TR --master-port 29741 bench.py --gpus $N --steps 30 --warmup 5 --no-cpu-baseline --no-extras \
+    > ${OUT}_bench_rs_sms16.json 2>> $OUT.log
+python - <<PY
+import json
+try:
+    d = json.loads([l for l in open("${OUT}_bench_rs_sms16.json") if l.startswith("{")][-1])
+    print("rs comm_sms=16", "rays/s", round(d["value"]), "ms", round(d["ms_per_step"], 3), "host ms", round(d["host_enqueue_ms_per_step"], 2))
+except Exception as e:
+    print("no bench line:", e)
+PY
 tail -4 $OUT.log
