@@ -12,7 +12,7 @@ import os
 import re
 import sys
 
-DENSE = ("tc_gemm_nt", "tc_gemm_tn", "tn_reduce", "tn_colsum_reduce", "rowdot", "gemm_nt_kernel", "gemm_tn_kernel",
+DENSE = ("tc_gemm_nt", "tc_gemm_tn", "tc_heads", "tn_reduce", "tn_colsum_reduce", "rowdot", "gemm_nt_kernel", "gemm_tn_kernel",
          "sdf_trunk")  # kernels behind the dense-layer entry points counted in bench.py's roofline
 
 
