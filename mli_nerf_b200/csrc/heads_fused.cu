@@ -28,6 +28,7 @@
 // The issuer now runs warp-uniform code (operands stay in uniform registers, only the tcgen05 instructions themselves are
 // predicated on lane 0), layer 0 uses N = 256 MMAs, and ring positions are carried incrementally.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -188,6 +189,7 @@ struct HeadsArgs {
   uint32_t* mask[4];            // relu sign bits [tiles][nh*8][128]: written by forward (may be NULL), read by backward
   int64_t lds;
   int64_t M; int n_tiles;
+  int debug;   // timing experiments only (MLI_HF_DEBUG): bit 0 no wait for the bulk store, bit 1 no masks, bit 2 no bulk store
 };
 
 // Ring items the producer streams per head and tile pair (the MMA warp consumes them in the same order):
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
           }
           if (store) {
             // the bulk store that read this activation half (previous stage) must be done reading before it is rewritten
-            if (leader) bulk_wait_read0();
+            if (leader && !(p.debug & 1)) bulk_wait_read0();
             group_bar(eg);
           }
           if (has_acc) {
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
                 }
                 tmem_st32(tmem_base + lane_addr + eg * 128 + c * 32, nb);
               }
-              if (mask_out != nullptr && live) {
+              if (mask_out != nullptr && live && !(p.debug & 2)) {
                 // relu'(x) as the complement of the sign bit: one funnel shift per element collects the signs (x >= +0 is
                 // kept; the layer-by-layer kernels test x > 0 -- they differ for an exact +0.0 only, where the activation
                 // itself is 0)
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_heads_kernel(const __grid_cons
           group_bar(eg);
           if (leader) {
             if (!(BWD && l == 3)) mbar_arrive(ready0 + 8 * eg);
-            if (store && live) {
+            if (store && live && !(p.debug & 4)) {
               bulk_s2g(p.A[l] + ((tile * nh + h) * 32 + g * 16) * 1024, sAct + t * 65536 + g * 32768, 32768);
               bulk_commit();
             }
@@ -534,7 +536,9 @@ int launch_heads(const HeadsArgs& p, cudaStream_t st) {
   }
   const int n_pairs = (p.n_tiles + 1) / 2;
   const int grid = n_pairs < mli_sm_limit() ? n_pairs : mli_sm_limit();
-  tc_heads_kernel<BWD><<<grid, kThreads, smem, st>>>(p);
+  HeadsArgs q = p;
+  if (const char* e = getenv("MLI_HF_DEBUG")) q.debug = atoi(e);
+  tc_heads_kernel<BWD><<<grid, kThreads, smem, st>>>(q);
   MLI_LAUNCH_OK();
   return MLI_OK;
 }

@@ -475,8 +475,8 @@ class RenderEngine:
 
     def apply_l2_window(self, table):
         """(Re)install the access-policy window when the table pointer / stream changes; no-op when MLI_L2_PERSIST is 0."""
-        if self.l2_persist <= 0.0:
-            return
+        if self.l2_persist <= 0.0 or torch.cuda.is_current_stream_capturing():
+            return  # (stream attributes cannot change during capture: Model._graphed_train_step installs the window before)
         key = (table.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if key != self._l2_key:
             call("mli_set_l2_window", table, self.dense_table_bytes(), self.l2_persist)

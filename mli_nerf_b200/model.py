@@ -494,6 +494,8 @@ class Model(torch.nn.Module):
                 for _ in range(2):
                     self.fused_train_step(static, loss_cfg, after_backward=after_backward)
             cur.wait_stream(side)
+            # kernels captured from this stream inherit its access-policy window (L2 residency of the dense table levels)
+            eng.apply_l2_window(self.neural_sdf.tcnn_encoding.params)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 losses = self.fused_train_step(static, loss_cfg, after_backward=after_backward)

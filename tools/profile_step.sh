@@ -11,15 +11,18 @@ timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 echo "launch list rc=$?"
 K='regex:tc_gemm_nt_persist|tc_gemm_tn_kernel|tc_sdf_trunk_fused|encode_rays_tcl|encode_rays_bwd_tcl|tc_heads_kernel|sdf_trunk_bwd_kernel|tc_gemm_nt_kernel'
 $CMD > $O/${R}_plain2.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k "$K" -s 170 -c 36 -o $O/${R}_step_full $CMD > $O/${R}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none -k "$K" -s 170 -c 36 -o $O/${R}_step_full $CMD > $O/${R}_ncu_full.log 2>&1
 echo "full rc=$?"
+# gpurun copies at most 64 MiB back: keep the raw page as CSV, drop the report
+ncu -i $O/${R}_step_full.ncu-rep --page raw --csv > $O/${R}_step_full_raw.csv 2>/dev/null && rm -f $O/${R}_step_full.ncu-rep
 H="python tools/bench_heads.py --only fwd_nostore --iters 3"
 $H > /dev/null 2>&1 &&
-timeout 250 ncu --set full --clock-control none --import-source on -k regex:tc_heads -s 2 -c 1 -o $O/${R}_heads_fwd_nostore $H > $O/${R}_ncu_heads.log 2>&1
+timeout 250 ncu --set full --clock-control none -k regex:tc_heads -s 2 -c 1 -o $O/${R}_heads_fwd_nostore $H > $O/${R}_ncu_heads.log 2>&1
 echo "heads rc=$?"
+ncu -i $O/${R}_heads_fwd_nostore.ncu-rep --page raw --csv > $O/${R}_heads_fwd_nostore_raw.csv 2>/dev/null && rm -f $O/${R}_heads_fwd_nostore.ncu-rep
 B="python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline"
 for hr in 0 0.6 1.0; do
-  MLI_L2_PERSIST=$hr timeout 200 $B > $O/${R}_l2_$hr.json 2> $O/${R}_l2_$hr.err
+  MLI_L2_PERSIST=$hr timeout 200 $B > $O/${R}_l2_$hr.json 2> $O/${R}_l2_$hr.err || tail -3 $O/${R}_l2_$hr.err
   python - <<PY
 import json
 d = json.loads([l for l in open("$O/${R}_l2_$hr.json") if l.startswith("{")][-1])
@@ -30,3 +33,4 @@ done
 python -c "
 from mli_nerf_b200 import _lib
 print('L2 bytes / max persisting / max window:', _lib.l2_info())"
+du -sh $O | tail -1
