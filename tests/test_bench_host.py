@@ -1,0 +1,59 @@
+"""Host-side pieces of bench.py (CPU): workload table, ReNe frame assignment, per-call work accounting, and the torch
+stand-in for the reference trainer's loss that the drop-in-path timing uses (checked against the oracle)."""
+import torch
+
+import bench
+from oracle import port
+
+
+def test_workloads_build_and_batches_have_the_reference_data_keys():
+    for name, (exp, dict_size, rays, coarse, _) in bench.WORKLOADS.items():
+        cfg = bench.workload_cfg(name, "bf16")
+        assert cfg.model.render.num_samples.coarse == coarse and cfg.model.render.rand_rays == rays
+        assert cfg.model.object.sdf.encoding.hashgrid.dict_size == dict_size
+        b = bench.workload_batch(name, 0, 0, 1)
+        assert b["ray_idx"].shape == (1, rays) and b["pose"].shape == (1, 3, 4) and b["pose_light"].shape == (1, 3, 4)
+        for k in ("image_sampled", "pseudo_ref_sampled"):
+            assert b[k].shape == (1, rays, 3)
+        H, W = cfg.data.train.image_size
+        assert int(b["ray_idx"].max()) < H * W
+
+
+def test_rene_frames_follow_distributed_sampler_assignment():
+    W = 8
+    frames = [[int(bench.rene_batch(16, it, r, W)["idx"]) for r in range(W)] for it in range(3)]
+    flat = [f for row in frames for f in row]
+    assert len(set(flat)) == len(flat)  # rank r takes perm[it * W + r]: no frame twice within the first epoch
+    b = bench.rene_batch(16, 0, 3, W)
+    # world->camera poses: rotation part orthonormal, intrinsics rescaled to 270 x 360
+    Rm = b["pose"][0, :, :3]
+    assert torch.allclose(Rm @ Rm.t(), torch.eye(3), atol=1e-5)
+    assert abs(float(b["intr"][0, 0, 2]) - 868.2309 * 360 / 1440) < 1e-2 and abs(float(b["intr"][0, 1, 2]) - 454.0686 * 270 / 1080) < 1e-2
+
+
+def test_kernel_work_accounting():
+    M, K, N, batch = 262144, 256, 256, 3
+    a = [None] * 32
+    a[6], a[7], a[24], a[25], a[17] = K, N, M, batch, 0
+    fl, by = bench.kernel_work("mli_tc_linear", a)
+    assert fl == 2.0 * M * K * N * batch and by == M * batch * (K + N) * 2 + K * N * 2 * batch
+    a = [None] * 20
+    a[8], a[9], a[10], a[11] = M, 256, 256, 3
+    assert bench.kernel_work("mli_tc_wgrad", a)[0] == 2.0 * M * 256 * 256 * 3
+    assert bench.kernel_work("mli_some_unknown_entry", []) is None
+    # 806.0 MFLOP per ray (128 samples, 4 taps, full-grad)
+    assert abs(6.0 * 128 * 1039616 + 2.0 * 112 * 33792 - bench.MLP_FLOP_PER_RAY) < 0.1e6
+
+
+def test_trainer_loss_stand_in_matches_the_oracle():
+    from mli_nerf_b200 import config
+    torch.manual_seed(0)
+    R, N = 64, 16
+    cfg = config.experiment("syn_hotdog_b")
+    out = dict(rgb=torch.rand(1, R, 3), o_r=torch.rand(1, R, 3), o_s=torch.rand(1, R, 1), o_re=torch.randn(1, R, 3) * 0.1,
+               gradients=torch.randn(1, R, N, 3), hessians=torch.randn(1, R, N, 3),
+               outside=torch.rand(1, R, 1) > 0.8)
+    data = port.synthetic_targets(R, seed=3)
+    want, _, _ = port.total_loss(port.PathConfig(), out, data)
+    got = bench.trainer_losses_torch(cfg.trainer, out, data)
+    assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
