@@ -281,6 +281,14 @@ def roofline_kernels(prof, work, steps, hbm_peak, tf_peak):
             tf = w[0] / (ms * 1e-3) / 1e12
             gbs = w[1] / (ms * 1e-3) / 1e9
             ft, fh = tf / tf_peak, gbs / hbm_peak
+            if k.startswith("mli_encode_rays"):
+                # hash-grid gather / scatter: the algorithmic bytes are the 32-byte sectors REQUESTED (8 corners x
+                # levels per sample); most are served by L1 / L2 (ncu: 1.2 GB / 0.9 GB of DRAM traffic per step for
+                # 7.2 GB / 11.1 GB requested), so the roof is the L1TEX/L2 sector rate, not HBM: no HBM fraction claimed
+                row.update(bytes_per_step=w[1] / steps, gather_gbs=round(gbs, 1), bound="l2_gather", frac=None,
+                           note="requested sectors per second; DRAM traffic is 6-12x lower (profiles/r02_summary.md)")
+                rows.append(row)
+                continue
             row.update(flops_per_step=w[0] / steps, bytes_per_step=w[1] / steps, tflops=round(tf, 1), gbs=round(gbs, 1),
                        bound="tensor" if ft >= fh else "hbm", frac=round(max(ft, fh), 4),
                        frac_tensor=round(ft, 4), frac_hbm=round(fh, 4))

@@ -41,8 +41,13 @@ def main():
         seq.append((name, m.get("gpu__time_duration.sum", 0.0),
                     m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0)))
     starts = [k for k, s in enumerate(seq) if "rays_from_pose" in s[0]]
-    a, b = starts[0], (starts[1] if len(starts) > 1 else len(seq))
-    step = seq[a:b]
+    # one step = the launches between two ray-generation kernels; prefer a slice of the plain fwd+bwd loop (bench.py
+    # also runs a loop with the optimizer step inside)
+    spans = list(zip(starts, starts[1:] + [len(seq)]))
+    plain = [sp for sp in spans[:-1] if not any("adamw" in n for n, _, _ in seq[sp[0]:sp[1]])] or spans[:1]
+    a, b = plain[0]
+    opt = [x for x in seq[a:b] if "adamw" in x[0]]
+    step = [x for x in seq[a:b] if "adamw" not in x[0]]   # the bench value times fwd+bwd; the optimizer is reported apart
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
     for n, t, by in step:
         agg[n][0] += 1
@@ -54,6 +59,10 @@ def main():
              "| kernel | launches | us | share | DRAM MB | GB/s |", "|---|---|---|---|---|---|"]
     for n, (c, t, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{n[:70]}` | {c} | {t:.1f} | {100 * t / total:.1f}% | {by / 1e6:.1f} | {by / t / 1e3 if t else 0:.0f} |")
+    if opt:
+        lines += ["", "The captured slice came from bench.py's with-optimizer loop; its optimizer launch is not part of the "
+                  "step above: " + ", ".join(f"`{n}` {t:.1f} us, {by / 1e6:.1f} MB DRAM ({by / t / 1e3:.0f} GB/s)"
+                                             for n, t, by in opt) + "."]
     open(dst, "w").write("\n".join(lines) + "\n")
     dense_bytes = sum(by for n, t, by in step if any(k in n for k in DENSE))
     dense_us = sum(t for n, t, by in step if any(k in n for k in DENSE))
