@@ -11,6 +11,8 @@
 // Bound: HBM/L2 gather bandwidth (16 levels * 8 corners * 32 B = 4 KB per query).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -341,6 +343,137 @@ __global__ void __launch_bounds__(KS * 7) encode_rays_tcl_kernel(mli_grid_t grid
   }
 }
 
+// Corner-caching variant for the stencil launch (taps > 0): thread = (sample, level), all planes.  The tap points of
+// Neuralangelo's stencil sit a fraction of a FINE cell from the centre, so on most levels they fall into the centre's
+// cell and read the same eight table entries: those are fetched once (8 x LDG.256 in flight) and kept in registers;
+// every same-cell tap is then pure arithmetic.  Taps that left the cell are deferred to a second, warp-compacted pass
+// that re-uses the 64 value registers.  Per (sample, level) the kernel issues 8 + 8 x (taps outside the cell) sector requests instead of
+// 8 x planes, which is what the thread-per-plane kernel above was bound by (L1TEX at 69 %, ncu r02).  Results are bit
+// for bit those of encode_rays_tcl_kernel: same weights, same fma chain, delta formed in fp32.
+template <int PLANES>
+__global__ void __launch_bounds__(128, 4) encode_rays_tcl_cached_kernel(mli_grid_t grid, const float* __restrict__ table,
+                                                                        RayArgs a, __nv_bfloat16* __restrict__ X,
+                                                                        int x_chunks, int kc) {
+  constexpr int F = 8;
+  __shared__ float s_acc0[128][F];
+  __shared__ uint8_t s_items[4][32 * (PLANES - 1)];
+  const int level = blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;  // M is a multiple of 128 here (checked by the entry point)
+  const int L = grid.n_levels;
+  const bool active = level < (int)grid.active_levels;
+  const mli_level_t& lv = grid.level[level];
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  const float rc[3] = {__ldg(a.center + ray * 3), __ldg(a.center + ray * 3 + 1), __ldg(a.center + ray * 3 + 2)};
+  const float rr[3] = {__ldg(a.ray_unit + ray * 3), __ldg(a.ray_unit + ray * 3 + 1), __ldg(a.ray_unit + ray * 3 + 2)};
+  const float rd = __ldg(a.dists + ray * a.ld_d + i);
+  float p0[3], x01[3];
+  mli_sample_point(rc, rr, rd, a.taps, 0, a.tap_eps, p0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p0[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p0[k], a.vol_min), a.vol_range);
+  const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+  float vals[8][F], acc0[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc0[f] = 0.0f;
+  if (active) {
+    uint32_t rows[8];
+    float wts[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mli_corner(lv, cell0, c, &rows[c], &wts[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) load_entry<F>(table, rows[c], vals[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc0[f] = fmaf(wts[c], vals[c][f], acc0[f]);
+  }
+  store_split8(X, x_chunks, kc, m, level, acc0);
+  if (level == 0) {
+    float v[8] = {p0[0], p0[1], p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    store_split8(X, x_chunks, kc, m, L, v);
+    v[0] = v[1] = v[2] = 0.0f;
+    for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, m, c, v);
+  }
+  uint32_t deferred = 0;
+#pragma unroll 1
+  for (int pl = 1; pl < PLANES; ++pl) {
+    float p[3];
+    mli_sample_point(rc, rr, rd, a.taps, pl, a.tap_eps, p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+    const int64_t grow = (int64_t)pl * M + m;
+    if (level == 0) {
+      float v[8] = {p[0] - p0[0], p[1] - p0[1], p[2] - p0[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_split8(X, x_chunks, kc, grow, L, v);
+      v[0] = v[1] = v[2] = 0.0f;
+      for (int c = L + 1; c < kc; ++c) store_split8(X, x_chunks, kc, grow, c, v);
+    }
+    float acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.0f;
+    if (active) {
+      const mli_cell_t cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+      if (cell.g[0] != cell0.g[0] || cell.g[1] != cell0.g[1] || cell.g[2] != cell0.g[2]) {
+        deferred |= 1u << pl;
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float w = 1.0f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) w *= ((c >> d) & 1) ? cell.w[d] : 1.0f - cell.w[d];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(w, vals[c][f], acc[f]);
+      }
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] -= acc0[f];
+    }
+    store_split8(X, x_chunks, kc, grow, level, acc);
+  }
+  // Second pass, compacted per warp: the (lane, plane) pairs that left the centre's cell are listed in shared memory and
+  // handed out 32 at a time, so every round runs with full warps (the first version let each lane walk its own taps:
+  // 30 % of all executed instructions ran with 6 of 32 lanes active, ncu r02_enc2).  The owner's centre row comes
+  // through shared memory; the item's ray is re-read (L1 hits).
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (__ballot_sync(0xffffffffu, deferred != 0) == 0) return;
+#pragma unroll
+  for (int f = 0; f < F; ++f) s_acc0[threadIdx.x][f] = acc0[f];
+  int n_items = 0;
+#pragma unroll 1
+  for (int pl = 1; pl < PLANES; ++pl) {
+    const bool mine = (deferred >> pl) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (mine) s_items[warp][n_items + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(lane | ((unsigned)pl << 5));
+    n_items += __popc(bal);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = (int)lane; it < n_items; it += 32) {
+    const unsigned item = s_items[warp][it];
+    const unsigned src = item & 31u;
+    const int pl = (int)(item >> 5);
+    const int64_t m2 = m - (int64_t)lane + (int64_t)src;
+    const int64_t ray2 = m2 / a.n;
+    const int i2 = (int)(m2 - ray2 * a.n);
+    const float c2[3] = {__ldg(a.center + ray2 * 3), __ldg(a.center + ray2 * 3 + 1), __ldg(a.center + ray2 * 3 + 2)};
+    const float r2[3] = {__ldg(a.ray_unit + ray2 * 3), __ldg(a.ray_unit + ray2 * 3 + 1), __ldg(a.ray_unit + ray2 * 3 + 2)};
+    const float d2 = __ldg(a.dists + ray2 * a.ld_d + i2);
+    float p[3], acc[F];
+    mli_sample_point(c2, r2, d2, a.taps, pl, a.tap_eps, p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+    interp<F>(lv, table, x01[0], x01[1], x01[2], acc);
+    const float* own = s_acc0[(warp << 5) + src];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] -= own[f];
+    store_split8(X, x_chunks, kc, (int64_t)pl * M + m2, level, acc);
+  }
+}
+
 // backward of encode_rays_tcl w.r.t. the table: dX is bf16 TCL-128 ([.., x_chunks, 128, 8], chunk l = level l) in the
 // delta basis (see encode_rays_bwd_kernel).  All planes' 16-byte gradient slices are loaded up front (independent,
 // fully coalesced: consecutive samples -> consecutive 16 B), then the same aggregation as the fp32 kernel.
@@ -546,6 +679,11 @@ extern "C" int mli_encode_rays_bwd(const mli_grid_t* grid, const float* center, 
   return MLI_OK;
 }
 
+static int encode_variant() {
+  const char* e = getenv("MLI_ENCODE_VARIANT");  // read per call: tests and tools/bench_encode.py switch it at run time
+  return e ? atoi(e) : 2;
+}
+
 extern "C" int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, const float* center,
                                    const float* ray_unit, const float* dists, int64_t ld_d, int64_t R, int32_t n,
                                    int32_t taps, float tap_eps, float vol_min, float vol_max, void* X, int32_t x_chunks,
@@ -563,10 +701,14 @@ extern "C" int mli_encode_rays_tcl(const mli_grid_t* grid, const float* table, c
     constexpr int KS = 128;
     dim3 g(mli_cdiv(R * n, KS), grid->n_levels);
     encode_rays_tcl_kernel<KS><<<g, dim3(KS, 1), 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
-  } else {
+  } else if (encode_variant() == 1) {  // thread-per-plane kernel (MLI_ENCODE_VARIANT=1): kept for A/B and as the bit-exactness pin
     constexpr int KS = 64;
     dim3 g(mli_cdiv(R * n, KS), grid->n_levels);
     encode_rays_tcl_kernel<KS><<<g, dim3(KS, 1 + taps), 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+  } else {
+    dim3 g(mli_cdiv(R * n, 128), grid->n_levels);
+    if (taps == 4) encode_rays_tcl_cached_kernel<5><<<g, 128, 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
+    else encode_rays_tcl_cached_kernel<7><<<g, 128, 0, (cudaStream_t)stream>>>(*grid, table, a, (__nv_bfloat16*)X, x_chunks, k_chunks);
   }
   MLI_LAUNCH_OK();
   return MLI_OK;

@@ -322,6 +322,32 @@ def test_encode_rays_tcl_matches_fp32_encode(lib, taps):
         assert float((rec[p] - d).abs().max()) < 2e-5 * float(d.abs().max()) + 1e-12, p
 
 
+@pytest.mark.parametrize("taps,eps_cells", [(4, 0.15), (4, 1.0), (4, 6.0), (6, 0.5)])
+def test_encode_rays_tcl_corner_caching_variant_is_bit_exact(lib, taps, eps_cells, monkeypatch):
+    """The default stencil encode (corner values cached in registers, taps outside the centre's cell deferred) must
+    produce the very bits of the thread-per-plane kernel: tiny eps -> nearly all taps share the cell, eps of several fine
+    cells -> nearly all are deferred; an inactive level range and a partial last CTA are included."""
+    R, n = 72, 16     # 1152 samples = 9 tiles of 128
+    grid = _grid(lib)
+    grid.active_levels = 13
+    torch.manual_seed(13)
+    table = ((torch.rand(int(grid.n_entries) * 8) * 2 - 1) * 0.05).cuda()
+    center, ray, dists = _rays(R, seed=14)
+    eps = eps_cells / 2048
+    P = 1 + taps
+    outs = []
+    for variant in ("1", "2"):
+        monkeypatch.setenv("MLI_ENCODE_VARIANT", variant)
+        Xt = torch.full((P * R * n // 128, 36, 128, 8), 7.0, dtype=torch.bfloat16, device="cuda")
+        lib.call("mli_encode_rays_tcl", grid, table, center.cuda(), ray.cuda(), dists.cuda(), 16, R, n, taps, eps, -2.0,
+                 2.0, Xt, 36, 18)
+        outs.append(Xt.cpu().view(torch.int16))
+    differing = int((outs[0] != outs[1]).sum())
+    assert differing == 0, differing
+    nonzero = int((outs[1][:, :13] != 0).sum())
+    assert nonzero > 0
+
+
 def test_encode_rays_bwd_delta_basis_equals_absolute_basis(lib):
     R, n, taps = 64, 16, 4
     grid = _grid(lib)
