@@ -8,8 +8,9 @@
 //
 // Layout: per-ray arrays [R, ld] with ld = final sample count (128); a ray's samples are contiguous (512 B)
 // so one warp reads a ray with a single coalesced 128-bit-per-lane request.  One warp per ray; the parts that
-// torch evaluates sequentially with a float64 accumulator (cumprod/cumsum) are done by lane 0 from shared
-// memory so the integer bin indices are bit-identical to the oracle; everything else is lane-parallel.
+// torch evaluates sequentially with a float64 accumulator (cumprod/cumsum) keep their dependent chain on lane 0
+// (one DMUL / DADD per element, operands prepared by all lanes) so the integer bin indices are bit-identical to
+// the oracle; everything else is lane-parallel.
 // Bound: HBM bandwidth (~1.4 KB/ray/round), in practice launch latency.
 #include "common.cuh"
 
@@ -92,15 +93,88 @@ __global__ void sample_coarse_kernel(const float* __restrict__ near, const float
 // one warp per ray: weights -> cdf -> bins -> fine samples
 // ---------------------------------------------------------------------------------------------------------
 struct FineSmem {
+  double f64[kMaxN];
   float d[kMaxN], s[kMaxN], w[kMaxN], cdf[kMaxN + 1];
 };
+
+// The two scans torch evaluates sequentially with a float64 accumulator (cumprod of 1 - alpha, cumsum of the pdf) stay
+// sequential on lane 0 -- their roundings depend on the order -- but everything that is not on the dependent chain
+// (the float -> double factors, the IEEE divisions, the final float products) is done by all lanes first, so that lane 0
+// runs one DMUL / DADD per element fed by independent shared-memory loads.  Bit for bit mli_alphas_to_weights() and
+// mli_weights_to_cdf(); a ray's latency through these kernels was 127 x ~350 cycles of lane-0 work before.
+__device__ __forceinline__ void warp_alphas_to_weights(FineSmem& sm, int n_w, int lane) {
+  for (int i = lane; i < n_w; i += 32) sm.f64[i] = (double)mli_sub(1.0f, sm.w[i]);
+  __syncwarp();
+  if (lane == 0) {
+    double T = 1.0;
+#pragma unroll 8
+    for (int i = 0; i < n_w; ++i) {
+      sm.cdf[i] = (float)T;  // transmittance in front of interval i (cdf[] is free until the next scan)
+      T *= sm.f64[i];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < n_w; i += 32) sm.w[i] = mli_mul(sm.w[i], sm.cdf[i]);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void warp_weights_to_cdf(FineSmem& sm, int n_w, int lane) {
+  float denom = 0.0f;
+  if (lane == 0) {
+#pragma unroll 8
+    for (int i = 0; i < n_w; ++i) denom = mli_add(denom, fabsf(sm.w[i]));
+    denom = fmaxf(denom, 1e-12f);
+  }
+  denom = __shfl_sync(0xffffffffu, denom, 0);
+  for (int i = lane; i < n_w; i += 32) sm.f64[i] = (double)mli_div(sm.w[i], denom);
+  __syncwarp();
+  if (lane == 0) {
+    double acc = 0.0;
+    sm.cdf[0] = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < n_w; ++i) {
+      acc += sm.f64[i];
+      sm.cdf[i + 1] = (float)acc;
+    }
+  }
+  __syncwarp();
+}
+
+// rank of element i of cat(A[0..n), B[0..n_b)) under a stable ascending sort.  Both runs are sorted in every call the
+// renderer makes (coarse samples ascend, inverse-CDF samples of ascending u ascend), which turns the rank into a binary
+// search in the OTHER run; the all-pairs count is kept for anything else (unsorted input, NaNs): same result either way.
+__device__ __forceinline__ bool warp_runs_sorted(const float* v, int n, int tot, int lane) {
+  bool ok = true;
+  for (int i = lane; i + 1 < tot; i += 32)
+    if (i != n - 1) ok = ok && (v[i] <= v[i + 1]);
+  return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ int stable_rank(const float* v, int n, int tot, int i, bool sorted) {
+  const float x = v[i];
+  if (sorted) {
+    int lo, hi;
+    if (i < n) {  // elements of B strictly below x
+      lo = n; hi = tot;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+      return i + (lo - n);
+    }
+    lo = 0; hi = n;  // elements of A not above x
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] <= x) lo = mid + 1; else hi = mid; }
+    return (i - n) + lo;
+  }
+  int rank = 0;
+  for (int j = 0; j < tot; ++j) {
+    const float o = v[j];
+    rank += (o < x) || (o == x && j < i) || (x != x && o == o) || (x != x && o != o && j < i);  // NaN last
+  }
+  return rank;
+}
 
 __device__ __forceinline__ void bins_from_weights(FineSmem& sm, int n_w, int n_bins_src, int n_fine, int lane,
                                                   float* fine_out, int32_t* idx_o, int32_t* low_o, int32_t* high_o,
                                                   float* cdf_o) {
   // n_w weights -> cdf[0..n_w]; searchsorted over the n_w+1 cdf entries
-  if (lane == 0) mli_weights_to_cdf(sm.w, n_w, sm.cdf);
-  __syncwarp();
+  warp_weights_to_cdf(sm, n_w, lane);
   const int n = n_w + 1;
   for (int j = lane; j < n_fine; j += 32) {
     int idx, low, high;
@@ -126,8 +200,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
   __syncwarp();
   for (int i = lane; i < n - 1; i += 32) sm.w[i] = mli_hier_alpha(sm.d, sm.s, i, inv_s);  // 2 sigmoids each: parallel
   __syncwarp();
-  if (lane == 0) mli_alphas_to_weights(sm.w, n - 1);  // float64 running product: sequential, like torch
-  __syncwarp();
+  warp_alphas_to_weights(sm, n - 1, lane);  // float64 running product: sequential, like torch
   bins_from_weights(sm, n - 1, n, n_fine, lane, fine + r * n_fine, idx ? idx + r * n_fine : nullptr,
                     low ? low + r * n_fine : nullptr, high ? high + r * n_fine : nullptr, cdf ? cdf + r * n : nullptr);
 }
@@ -161,14 +234,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_merge_kernel(
     if (sdfs) ss[warp][i] = i < n ? sdfs[r * ld + i] : sdf_fine[r * n_fine + (i - n)];
   }
   __syncwarp();
+  const bool sorted = warp_runs_sorted(sd[warp], n, tot, lane);
   for (int i = lane; i < tot; i += 32) {
-    const float v = sd[warp][i];
-    int rank = 0;
-    for (int j = 0; j < tot; ++j) {
-      const float o = sd[warp][j];
-      rank += (o < v) || (o == v && j < i) || (v != v && o == o) || (v != v && o != o && j < i);  // NaN last
-    }
-    dists[r * ld + rank] = v;
+    const int rank = stable_rank(sd[warp], n, tot, i, sorted);
+    dists[r * ld + rank] = sd[warp][i];
     if (sdfs) sdfs[r * ld + rank] = ss[warp][i];
   }
 }
@@ -191,22 +260,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_merge_fine_kernel(
     ss[warp][i] = i < n ? sdfs[r * ld + i] : sdf_fine[r * n_fine + (i - n)];
   }
   __syncwarp();
+  const bool sorted = warp_runs_sorted(sd[warp], n, tot, lane);
   for (int i = lane; i < tot; i += 32) {
-    const float v = sd[warp][i];
-    int rank = 0;
-    for (int j = 0; j < tot; ++j) {
-      const float o = sd[warp][j];
-      rank += (o < v) || (o == v && j < i) || (v != v && o == o) || (v != v && o != o && j < i);  // NaN last
-    }
-    sm.d[rank] = v;
+    const int rank = stable_rank(sd[warp], n, tot, i, sorted);
+    sm.d[rank] = sd[warp][i];
     sm.s[rank] = ss[warp][i];
   }
   __syncwarp();
   for (int i = lane; i < tot; i += 32) { dists[r * ld + i] = sm.d[i]; sdfs[r * ld + i] = sm.s[i]; }
   for (int i = lane; i < tot - 1; i += 32) sm.w[i] = mli_hier_alpha(sm.d, sm.s, i, inv_s_next);
   __syncwarp();
-  if (lane == 0) mli_alphas_to_weights(sm.w, tot - 1);
-  __syncwarp();
+  warp_alphas_to_weights(sm, tot - 1, lane);
   bins_from_weights(sm, tot - 1, tot, n_fine, lane, fine_out + r * n_fine, nullptr, nullptr, nullptr, nullptr);
 }
 

@@ -912,3 +912,30 @@ def test_sample_merge_fine_fused_equals_two_calls(lib):
     lib.call("mli_sample_merge_fine", Db, Sb, ld, R, n, cu(fine), cu(sf), nf, 256.0, fb)
     same = lambda a, b: bool(((a == b) | (a.isnan() & b.isnan())).all())  # noqa: E731
     assert same(Da, Db) and same(Sa, Sb) and same(fa, fb)
+
+
+@pytest.mark.parametrize("sorted_fine", [True, False])
+def test_sample_merge_equals_torch_stable_sort(lib, sorted_fine):
+    """cat + stable sort + gather: sorted runs take the binary-search rank, anything else (unsorted run, NaN) the all-pairs
+    count; both must be torch.sort(stable=True) on the concatenation, ties between old and new samples included."""
+    torch.manual_seed(31)
+    R, n, nf, ld = 515, 96, 32, 128
+    d = torch.sort(torch.rand(R, n) * 3.0 + 0.5, dim=1).values
+    d[200:230, 40:44] = d[200:230, 40:41]         # ties inside the old run
+    fine = torch.rand(R, nf) * 3.0 + 0.5
+    fine[100:140, :6] = d[100:140, 10:16]           # ties between the runs
+    if sorted_fine:
+        fine = torch.sort(fine, dim=1).values
+    else:
+        fine[7, 3] = float("nan")
+    s, sf = torch.randn(R, n), torch.randn(R, nf)
+    D, S = torch.zeros(R, ld), torch.zeros(R, ld)
+    D[:, :n], S[:, :n] = d, s
+    Dg, Sg = cu(D), cu(S)
+    lib.call("mli_sample_merge", Dg, Sg, ld, R, n, cu(fine), cu(sf), nf)
+    ref_d, perm = torch.sort(torch.cat([d, fine], dim=1), dim=1, stable=True)
+    ref_s = torch.cat([s, sf], dim=1).gather(1, perm)
+    got_d, got_s = Dg.cpu(), Sg.cpu()
+    same_d = bool(((got_d == ref_d) | (got_d.isnan() & ref_d.isnan())).all())
+    same_s = bool((got_s == ref_s).all())
+    assert same_d and same_s
