@@ -579,6 +579,162 @@ __global__ void __launch_bounds__(kBwdThreads, 5) encode_rays_bwd_tcl_kernel(mli
   }
 }
 
+// Version 2 of the stencil scatter (PLANES > 1).  Two changes against encode_rays_bwd_tcl_kernel, both aimed at what ncu
+// showed for it (r02_encb: 24 % of the executed instructions ran in the "tap left the centre's cell" branch with 8 of 32
+// lanes active, and that branch issued 8 reductions per tap):
+//  * every tap -- inside the centre's cell or in a neighbouring one -- first adds what it owes to the lattice points it
+//    SHARES with the centre's cell into the centre's eight register accumulators (a tap one cell over along one axis
+//    shares four of its eight corners with the centre), branch-free: per axis the tap's weight on the centre's lower /
+//    upper lattice plane is selected from {1-w, w, 0} by the cell offset;
+//  * the remaining corners of the taps that left the cell are listed per warp in shared memory and scattered in dense
+//    rounds of 32 (lane, plane) items.
+template <int PLANES>
+__global__ void __launch_bounds__(kBwdThreads, 5) encode_rays_bwd_tcl_v2_kernel(mli_grid_t grid, RayArgs a,
+                                                                                const __nv_bfloat16* __restrict__ dX, int x_chunks,
+                                                                                float* __restrict__ table_grad, int level0) {
+  constexpr int FH = 4;
+  static_assert(PLANES > 1, "the single-plane launch uses encode_rays_bwd_tcl_kernel<1>");
+  __shared__ uint2 s_d[kBwdThreads][PLANES - 1];
+  __shared__ uint32_t s_g0[kBwdThreads][3];
+  __shared__ uint8_t s_items[kBwdThreads / 32][32 * (PLANES - 1)];
+  const int level = level0 + blockIdx.y;
+  const int64_t M = a.R * a.n;
+  const int64_t t = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;  // 2 M is a multiple of the block size (entry point)
+  const int64_t m = t >> 1;
+  const int half = (int)(t & 1);
+  if (level >= (int)grid.active_levels) return;  // block-uniform
+  const mli_level_t& lv = grid.level[level];
+  const int64_t ray = m / a.n;
+  const int i = (int)(m - ray * a.n);
+  uint2 draw[PLANES];
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    const int64_t grow = (int64_t)pl * M + m;
+    draw[pl] = __ldg(reinterpret_cast<const uint2*>(dX + (((grow >> 7) * x_chunks + level) * 128 + (grow & 127)) * 8 + half * 4));
+  }
+  const float rc[3] = {__ldg(a.center + ray * 3), __ldg(a.center + ray * 3 + 1), __ldg(a.center + ray * 3 + 2)};
+  const float rr[3] = {__ldg(a.ray_unit + ray * 3), __ldg(a.ray_unit + ray * 3 + 1), __ldg(a.ray_unit + ray * 3 + 2)};
+  const float rd = __ldg(a.dists + ray * a.ld_d + i);
+#pragma unroll
+  for (int pl = 1; pl < PLANES; ++pl) s_d[threadIdx.x][pl - 1] = draw[pl];
+  float p[3], x01[3];
+  mli_sample_point(rc, rr, rd, a.taps, 0, a.tap_eps, p);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+  const mli_cell_t cell0 = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s_g0[threadIdx.x][k] = cell0.g[k];
+  float w0[8], agg[8][FH];
+  {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&draw[0]);
+    const float2 d01 = __bfloat1622float2(h[0]), d23 = __bfloat1622float2(h[1]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float w = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? cell0.w[k] : 1.0f - cell0.w[k];
+      w0[c] = w;
+      agg[c][0] = w * d01.x; agg[c][1] = w * d01.y; agg[c][2] = w * d23.x; agg[c][3] = w * d23.y;
+    }
+  }
+  uint32_t deferred = 0;
+#pragma unroll 1
+  for (int pl = 1; pl < PLANES; ++pl) {
+    mli_sample_point(rc, rr, rd, a.taps, pl, a.tap_eps, p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+    const mli_cell_t cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+    float d[FH];
+    {
+      const uint2 cur = draw[1];  // draw[1] is always the current tap plane: the slices rotate down one slot per iteration
+#pragma unroll
+      for (int k = 1; k + 1 < PLANES; ++k) draw[k] = draw[k + 1];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { const float2 f2 = __bfloat1622float2(h[k]); d[2 * k] = f2.x; d[2 * k + 1] = f2.y; }
+    }
+    // weight of the tap on the centre cell's lower / upper lattice plane, per axis
+    float fl[3], fu[3];
+    bool moved = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int off = (int)(cell.g[k] - cell0.g[k]);
+      const float wk = cell.w[k], nk = 1.0f - wk;
+      fl[k] = off == 0 ? nk : (off == -1 ? wk : 0.0f);
+      fu[k] = off == 0 ? wk : (off == 1 ? nk : 0.0f);
+      moved = moved || off != 0;
+    }
+    if (moved) deferred |= 1u << pl;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float w = ((c & 1) ? fu[0] : fl[0]) * ((c & 2) ? fu[1] : fl[1]) * ((c & 4) ? fu[2] : fl[2]) - w0[c];
+#pragma unroll
+      for (int f = 0; f < FH; ++f) agg[c][f] = fmaf(w, d[f], agg[c][f]);
+    }
+  }
+  float* const tg = table_grad + half * FH;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t row;
+    float w;
+    mli_corner(lv, cell0, c, &row, &w);
+    atomicAdd(reinterpret_cast<float4*>(tg + (size_t)row * 8), make_float4(agg[c][0], agg[c][1], agg[c][2], agg[c][3]));
+  }
+  // second pass: the corners of the moved taps that are NOT lattice points of the centre's cell, compacted per warp
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (__ballot_sync(0xffffffffu, deferred != 0) == 0) return;
+  int n_items = 0;
+#pragma unroll 1
+  for (int pl = 1; pl < PLANES; ++pl) {
+    const bool mine = (deferred >> pl) & 1u;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (mine) s_items[warp][n_items + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(lane | ((unsigned)pl << 5));
+    n_items += __popc(bal);
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int it = (int)lane; it < n_items; it += 32) {
+    const unsigned item = s_items[warp][it];
+    const unsigned src = (warp << 5) + (item & 31u);
+    const int pl = (int)(item >> 5);
+    const int64_t t2 = t - (int64_t)lane + (int64_t)(item & 31u);
+    const int64_t m2 = t2 >> 1;
+    const int64_t ray2 = m2 / a.n;
+    const int i2 = (int)(m2 - ray2 * a.n);
+    const float c2[3] = {__ldg(a.center + ray2 * 3), __ldg(a.center + ray2 * 3 + 1), __ldg(a.center + ray2 * 3 + 2)};
+    const float r2[3] = {__ldg(a.ray_unit + ray2 * 3), __ldg(a.ray_unit + ray2 * 3 + 1), __ldg(a.ray_unit + ray2 * 3 + 2)};
+    const float d2 = __ldg(a.dists + ray2 * a.ld_d + i2);
+    mli_sample_point(c2, r2, d2, a.taps, pl, a.tap_eps, p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      x01[k] = a.inv_range != 0.0f ? mli_mul(mli_sub(p[k], a.vol_min), a.inv_range) : mli_div(mli_sub(p[k], a.vol_min), a.vol_range);
+    const mli_cell_t cell = mli_grid_cell(lv, x01[0], x01[1], x01[2]);
+    int off[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) off[k] = (int)(cell.g[k] - s_g0[src][k]);
+    const uint2 cur = s_d[src][pl - 1];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur);
+    const float2 d01 = __bfloat1622float2(h[0]), d23 = __bfloat1622float2(h[1]);
+    float* const tg2 = table_grad + (t2 & 1) * FH;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      bool shared = true;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int q = off[k] + ((c >> k) & 1);
+        shared = shared && (q == 0 || q == 1);
+      }
+      if (shared) continue;
+      uint32_t row;
+      float w;
+      mli_corner(lv, cell, c, &row, &w);
+      atomicAdd(reinterpret_cast<float4*>(tg2 + (size_t)row * 8), make_float4(w * d01.x, w * d01.y, w * d23.x, w * d23.y));
+    }
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_F(feat, CALL)                                      \
@@ -729,8 +885,11 @@ extern "C" int mli_encode_rays_bwd_tcl(const mli_grid_t* grid, const float* cent
   dim3 g(mli_cdiv(2 * R * n, kBwdThreads), level_end - level_begin);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* d = (const __nv_bfloat16*)dX;
-  if (taps == 4) encode_rays_bwd_tcl_kernel<5><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
-  else if (taps == 6) encode_rays_bwd_tcl_kernel<7><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  const bool v1 = encode_variant() == 1;  // MLI_ENCODE_VARIANT=1: the first-generation kernels, kept for A/B and as the pin
+  if (taps == 4 && v1) encode_rays_bwd_tcl_kernel<5><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else if (taps == 6 && v1) encode_rays_bwd_tcl_kernel<7><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else if (taps == 4) encode_rays_bwd_tcl_v2_kernel<5><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
+  else if (taps == 6) encode_rays_bwd_tcl_v2_kernel<7><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
   else encode_rays_bwd_tcl_kernel<1><<<g, kBwdThreads, 0, st>>>(*grid, a, d, x_chunks, table_grad, level_begin);
   MLI_LAUNCH_OK();
   return MLI_OK;

@@ -348,6 +348,38 @@ def test_encode_rays_tcl_corner_caching_variant_is_bit_exact(lib, taps, eps_cell
     assert nonzero > 0
 
 
+@pytest.mark.parametrize("taps,eps_cells", [(4, 0.15), (4, 1.0), (4, 6.0), (6, 0.5)])
+def test_encode_rays_bwd_tcl_v2_equals_v1(lib, taps, eps_cells, monkeypatch):
+    """Scatter kernel v2 (taps add into the centre cell's accumulators wherever they share a lattice point with it, the
+    rest is scattered in warp-compacted rounds) against the first-generation kernel: same table gradient up to the
+    summation order, for taps inside the centre's cell, one cell over and several cells away."""
+    R, n = 72, 16
+    grid = _grid(lib)
+    grid.active_levels = 14
+    center, ray, dists = _rays(R, seed=15)
+    eps = eps_cells / 2048
+    M, P = R * n, 1 + taps
+    torch.manual_seed(16)
+    dX = torch.randn(P, M, 128)
+    dX[1:] *= 30.0
+    dX[0] += dX[1:].sum(0)
+    dXt = to_tcl_host(dX.reshape(P * M, 128)).cuda()
+    n_par = int(grid.n_entries) * 8
+    args = (grid, center.cuda(), ray.cuda(), dists.cuda(), 16, R, n, taps, eps, -2.0, 2.0)
+    out = []
+    for variant in ("1", "2"):
+        monkeypatch.setenv("MLI_ENCODE_VARIANT", variant)
+        tg = torch.zeros(n_par, device="cuda")
+        for lv0, lv1 in ((0, 6), (6, 16)):
+            lib.call("mli_encode_rays_bwd_tcl", *args, dXt, 16, tg, lv0, lv1)
+        out.append(tg.cpu().double())
+    scale = float(out[0].abs().max())
+    err = float((out[0] - out[1]).abs().max())
+    assert scale > 0 and err < 1e-5 * scale, (err, scale)
+    untouched = int(((out[0] == 0) != (out[1] == 0)).sum())   # same support (exact zeros where nothing was scattered)
+    assert untouched < 1e-4 * out[0].numel(), untouched
+
+
 def test_encode_rays_bwd_delta_basis_equals_absolute_basis(lib):
     R, n, taps = 64, 16, 4
     grid = _grid(lib)

@@ -79,9 +79,18 @@ def main():
     if not same:
         d = (outs["1"].float() - outs["2"].float()).abs()
         print("  max abs diff", float(d.max()), "differing elements", int((d != 0).sum()))
-    tg = b[13]
-    us_all = timed(lambda: call("mli_encode_rays_bwd_tcl", *b), args.iters)
-    print(f"scatter bwd (all levels):    {us_all:8.1f} us")
+    tgs = {}
+    for variant in ("1", "2"):
+        os.environ["MLI_ENCODE_VARIANT"] = variant
+        us_all = timed(lambda: call("mli_encode_rays_bwd_tcl", *b), args.iters)
+        b[13].zero_()
+        call("mli_encode_rays_bwd_tcl", *b)
+        tgs[variant] = b[13].clone()
+        print(f"scatter bwd (all levels) variant {variant}: {us_all:8.1f} us")
+    scale = float(tgs["1"].abs().max())
+    err = float((tgs["1"] - tgs["2"]).abs().max())
+    print(f"scatter variants: max abs diff {err:.3e} at scale {scale:.3e} (rel {err / scale:.2e})")
+    del tgs
     if args.levels:
         L = b[15]
         tot = 0.0
@@ -93,7 +102,6 @@ def main():
             lvl = model.engine.grid.level[lv]
             print(f"  level {lv:2d} res {lvl.res:5d} size {lvl.size:8d} hashed {lvl.hashed}: {us:7.1f} us")
         print(f"  sum of single-level launches {tot:.1f} us")
-    del tg
 
 
 if __name__ == "__main__":
