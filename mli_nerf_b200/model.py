@@ -135,6 +135,17 @@ class LumenRGB(torch.nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def _aliases(obj):
+    """Same storages, new tensor objects (no autograd history attaches to them later), containers rebuilt."""
+    if isinstance(obj, torch.Tensor):
+        return obj.detach()
+    if isinstance(obj, dict):
+        return {k: _aliases(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_aliases(v) for v in obj)
+    return obj
+
+
 class _RenderFunction(torch.autograd.Function):
     """One autograd node for the whole render: forward and hand-written backward both run in libmli_b200."""
 
@@ -149,7 +160,11 @@ class _RenderFunction(torch.autograd.Function):
             need_bwd = any(ctx.needs_input_grad[7:])  # no parameter needs a gradient (eval / no_grad): skip the saves
             res, saved = eng.forward(p, center, ray_unit, pts_light, dists, near, far, outside, training, model.progress,
                                      keep_dz=need_bwd)
-        ctx.model, ctx.names, ctx.saved, ctx.params = model, names, saved, params
+        # Several saved tensors (gradients, weights, dists, outside ...) are also OUTPUTS of this node.  An output gets this
+        # node as its grad_fn, so keeping the same tensor object on ctx would close a reference cycle output -> node -> ctx
+        # -> output, and a step's activations (~3.7 GB at the bench shape) would live until Python's cycle collector
+        # runs: the caching allocator then grows by cudaMalloc every step.  Aliases break the cycle.
+        ctx.model, ctx.names, ctx.saved, ctx.params = model, names, _aliases(saved), params
         ctx.W = eng.W
         out = res["out"]
         hess = res["hessians"] if res["hessians"] is not None else out.new_zeros(0)

@@ -939,3 +939,46 @@ def test_sample_merge_equals_torch_stable_sort(lib, sorted_fine):
     same_d = bool(((got_d == ref_d) | (got_d.isnan() & ref_d.isnan())).all())
     same_s = bool((got_s == ref_s).all())
     assert same_d and same_s
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_autograd_path_releases_a_step_by_refcount(lib, prec):
+    """model(data) -> loss -> backward() must not need Python's cycle collector to give a step's activations back: the
+    render node once kept its own outputs on ctx (output -> grad_fn -> ctx -> output), every step's buffers then waited
+    for a gc pass and the caching allocator grew by cudaMalloc per step (bench autograd_dropin: 7 -> 22 ms/step)."""
+    import gc
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.model import Model
+    cfg = config.experiment("syn_hotdog_b", dict_size=14, rand_rays=256)
+    cfg.model.mli_precision = prec
+    torch.manual_seed(0)
+    model = Model(cfg.model, cfg.data).cuda().train()
+    model.progress = 0.5
+    pose = torch.tensor([[[1, 0, 0, 0.05], [0, -1, 0, -0.02], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[711.0, 0, 256], [0, 711.0, 256], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, 1.0], [0, 1, 0, -2.0], [0, 0, 1, 3.0]]], dtype=torch.float32)
+    ray_idx = torch.randperm(512 * 512, generator=torch.Generator().manual_seed(5))[:256][None]
+    data = dict(pose=cu(pose), intr=cu(intr), pose_light=cu(pose_light), ray_idx=cu(ray_idx), idx=torch.zeros(1).long())
+
+    def step(backward):
+        out = model(data)
+        if backward:
+            (out["rgb"].square().mean() + out["gradients"].square().mean()).backward()
+        model.zero_grad(set_to_none=True)
+
+    for _ in range(2):
+        step(True)
+    gc.collect()
+    gc.disable()
+    try:
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        for _ in range(6):
+            step(True)
+        for _ in range(6):
+            step(False)   # a forward whose graph is dropped without a backward
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    assert grown < (8 << 20), grown   # one step holds > 100 MB here

@@ -79,6 +79,7 @@ def main():
     if not same:
         d = (outs["1"].float() - outs["2"].float()).abs()
         print("  max abs diff", float(d.max()), "differing elements", int((d != 0).sum()))
+    b[11].copy_((torch.randn(b[11].shape, device="cuda") * 1e-3).to(b[11].dtype))  # geometric init: the real dX is exactly 0
     tgs = {}
     for variant in ("1", "2"):
         os.environ["MLI_ENCODE_VARIANT"] = variant
@@ -89,7 +90,7 @@ def main():
         print(f"scatter bwd (all levels) variant {variant}: {us_all:8.1f} us")
     scale = float(tgs["1"].abs().max())
     err = float((tgs["1"] - tgs["2"]).abs().max())
-    print(f"scatter variants: max abs diff {err:.3e} at scale {scale:.3e} (rel {err / scale:.2e})")
+    print(f"scatter variant 2 vs 1: max abs diff {err:.3e} at scale {scale:.3e}")
     del tgs
     if args.levels:
         L = b[15]
