@@ -490,6 +490,15 @@ int mli_reduce_slots(float* dst, const float* slots, int32_t n_slots, int64_t sl
 int mli_set_l2_window(const void* ptr, int64_t bytes, float hit_ratio, void* stream);
 int mli_l2_info(int32_t* host_out_l2_bytes, int32_t* host_out_max_persist_bytes, int32_t* host_out_max_window_bytes);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Background zero-fill of the hash-table gradient buffer (the reference gets its zeroed .grad from autograd /
+ * optimizer.zero_grad, projects/NeuralLumen/trainer.py:167): a persistent grid of `n_ctas` CTAs (<= 0: 32) instead of
+ * one that floods every SM, so that when it is issued on a side stream next to the latency-bound sampling rounds the
+ * main stream's small kernels still find free SM slots (a full-grid fill delayed them by its whole duration).
+ * ptr must be 16-byte aligned; any byte count.
+ * ---------------------------------------------------------------------------------------------------- */
+int mli_zero_fill_background(void* ptr, int64_t bytes, int32_t n_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

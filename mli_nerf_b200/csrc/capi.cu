@@ -125,3 +125,30 @@ extern "C" int mli_l2_info(int32_t* host_out_l2_bytes, int32_t* host_out_max_per
   if (host_out_max_window_bytes) { MLI_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev)); *host_out_max_window_bytes = v; }
   return MLI_OK;
 }
+
+namespace {
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint4* __restrict__ dst, int64_t n16, uint8_t* __restrict__ tail, int n_tail) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll 4
+  for (; i < n16; i += stride) __stcs(dst + i, z);  // streaming stores: nothing of this buffer is worth keeping in L2
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) tail[threadIdx.x] = 0;
+}
+}  // namespace
+
+extern "C" int mli_zero_fill_background(void* ptr, int64_t bytes, int32_t n_ctas, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(bytes >= 0 && (ptr != nullptr || bytes == 0), "zero_fill: bad arguments");
+  MLI_REQUIRE(((uintptr_t)ptr & 15u) == 0, "zero_fill: ptr must be 16-byte aligned");
+  if (bytes == 0) return MLI_OK;
+  const int64_t n16 = bytes / 16;
+  const int n_tail = (int)(bytes - n16 * 16);
+  int ctas = n_ctas > 0 ? n_ctas : 32;
+  const int64_t need = (n16 + 255) / 256;
+  if (need < ctas) ctas = need > 0 ? (int)need : 1;
+  zero_fill_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>((uint4*)ptr, n16, (uint8_t*)ptr + n16 * 16, n_tail);
+  MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+

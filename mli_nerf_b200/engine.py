@@ -139,6 +139,7 @@ class RenderEngine:
         self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
+        self.zero_fill_ctas = int(os.environ.get("MLI_ZERO_FILL_CTAS", "64"))  # 16: 1.6 ms, 32: 0.8 ms, 64: 0.44 ms for 1.46 GB
         # bf16 mode: the head stack as ONE on-chip kernel per direction (csrc/heads_fused.cu).  Measured at the bench shape
         # (tools/bench_heads.py, profiles/r02_heads_fused.md): data-gradient chain 435 us fused vs 564 us layer by layer;
         # forward WITHOUT stored activations (inference / no-grad) 493 us vs 579 us; forward that also has to write the
@@ -166,10 +167,11 @@ class RenderEngine:
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            if self.table_grad_buffer is not None:
-                tg = self.table_grad_buffer.zero_()
-            else:
-                tg = torch.zeros(self.n_table_params(), dtype=torch.float32, device=self.device)
+            tg = self.table_grad_buffer if self.table_grad_buffer is not None else \
+                torch.empty(self.n_table_params(), dtype=torch.float32, device=self.device)
+            # a persistent grid of a few CTAs, not torch's full-grid fill: that one occupied every SM slot for its 0.2 ms
+            # and the main stream's small sampling kernels queued behind it (bench: sample_coarse 4.7 us -> 160 us)
+            call("mli_zero_fill_background", tg, tg.numel() * 4, self.zero_fill_ctas)
         tg.record_stream(cur)
         self._tg_early = tg
 

@@ -155,9 +155,11 @@ class _RenderFunction(torch.autograd.Function):
         p = dict(zip(names, params))
         with torch.no_grad():
             eng.pack_weights(p)
+            need_bwd = any(ctx.needs_input_grad[7:])  # no parameter needs a gradient (eval / no_grad): skip the saves
+            if training and ctx.needs_input_grad[7 + names.index("neural_sdf.tcnn_encoding.params")]:
+                eng.start_table_grad_zero()  # the backward's 1.46 GB gradient buffer: zeroed on a side stream meanwhile
             near, far, outside = eng.bounds(center, ray_unit)
             dists = eng.sample(p["neural_sdf.tcnn_encoding.params"], center, ray_unit, near, far, rands)
-            need_bwd = any(ctx.needs_input_grad[7:])  # no parameter needs a gradient (eval / no_grad): skip the saves
             res, saved = eng.forward(p, center, ray_unit, pts_light, dists, near, far, outside, training, model.progress,
                                      keep_dz=need_bwd)
         # Several saved tensors (gradients, weights, dists, outside ...) are also OUTPUTS of this node.  An output gets this

@@ -981,4 +981,7 @@ def test_autograd_path_releases_a_step_by_refcount(lib, prec):
         grown = torch.cuda.memory_allocated() - base
     finally:
         gc.enable()
-    assert grown < (8 << 20), grown   # one step holds > 100 MB here
+    # one step holds > 100 MB here; a forward that is never followed by a backward leaves ONE pre-zeroed table-gradient
+    # buffer (8 MiB at T = 2^14) with the engine, which the next step replaces
+    table_bytes = model.engine.n_table_params() * 4
+    assert grown <= table_bytes + (1 << 20), (grown, table_bytes)

@@ -502,3 +502,13 @@ def test_fused_head_stack_matches_layer_by_layer(lib, mode, R):
     bad = {k: (e, bool(torch.isfinite(grads[False][k]).all()), bool(torch.isfinite(grads[True][k]).all()))
            for k, e in errs.items() if not e < 2e-2}
     assert not bad, bad  # (relative error, layer-by-layer finite, fused finite)
+
+
+@pytest.mark.parametrize("nbytes", [0, 4, 16, 4096 + 12, (1 << 22) + 20])
+def test_zero_fill_background(lib, nbytes):
+    """Small-footprint zero-fill: every byte of the range, nothing after it, odd tails included."""
+    buf = torch.full((nbytes + 64,), 0x5A, dtype=torch.uint8, device="cuda")
+    lib.call("mli_zero_fill_background", buf, nbytes, 8)
+    host = buf.cpu()
+    assert int(host[:nbytes].sum()) == 0
+    assert bool((host[nbytes:] == 0x5A).all())
