@@ -558,18 +558,31 @@ __global__ void __launch_bounds__(kP_Threads, 1) tc_gemm_nt_persist_kernel(TcNT 
               if (p.mask) {
                 // v >= +0 after relu, so v > 0 <=> bits(v) + 0x7fffffff carries into the sign bit; a funnel shift moves
                 // that bit into the mask: 2 instructions per element (columns >= ncol hold relu(garbage), never read)
-                uint32_t bits = 0;
+                // (four independent 8-bit chains: one 32-long dependent chain per chunk left the two epilogue warps of a
+                // scheduler stalled on ALU latency -- ncu: `wait` was the top stall of the forward GEMMs)
+                uint32_t b4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-                for (int i = 31; i >= 0; --i) bits = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, bits, 1);
+                for (int i = 7; i >= 0; --i) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) b4[g] = __funnelshift_l(__float_as_uint(v[8 * g + i]) + 0x7fffffffu, b4[g], 1);
+                }
+                const uint32_t bits = b4[0] | (b4[1] << 8) | (b4[2] << 16) | (b4[3] << 24);
                 p.mask[((int64_t)tile_m * p.mask_chunks + p.mask_chunk0 + (int64_t)batch * p.mask_batch_chunks + (n0 + c0) / 32) * kTileM + r_local] = bits;
               }
             }
             if constexpr (kDot) {  // v[] now holds the activated layer output: feed the fused output layer
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (j < nj) {
+                if (j < nj) {  // four partial sums per output: the 32-long fma chain was latency bound at two warps per scheduler
+                  float e[4] = {0.f, 0.f, 0.f, 0.f};
+                  const float4* wv = reinterpret_cast<const float4*>(s_wd + j * 256 + c0);
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) dj[j] = fmaf(v[i], s_wd[j * 256 + c0 + i], dj[j]);
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 w = wv[i];
+                    e[0] = fmaf(v[4 * i], w.x, e[0]); e[1] = fmaf(v[4 * i + 1], w.y, e[1]);
+                    e[2] = fmaf(v[4 * i + 2], w.z, e[2]); e[3] = fmaf(v[4 * i + 3], w.w, e[3]);
+                  }
+                  dj[j] += (e[0] + e[1]) + (e[2] + e[3]);
                 }
               }
             }
