@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MLI_ABI_VERSION 3
+#define MLI_ABI_VERSION 4
 
 enum {
   MLI_OK = 0,
@@ -387,6 +387,9 @@ typedef struct {
   int32_t white_bg;       /* add (1-opacity) to every composited channel */
   int32_t eval_extras;    /* also opacity, gradient, dist composites */
   float anneal_ratio;     /* min(progress/anneal_end, 1) */
+  const float* anneal_dev; /* optional DEVICE float: when non-NULL the kernels read the anneal ratio from it instead of
+                            * anneal_ratio, so a captured CUDA graph follows the schedule (neuralangelo/model.py:492-499
+                            * recomputes it from `progress` every iteration) without being re-captured */
 } mli_composite_cfg_t;
 
 /* S [M, lds] per-sample head outputs; out [R, n_out(mode)]; weights [R,N]; alphas [R,N] or NULL;
@@ -415,6 +418,9 @@ typedef struct {
   float range_sha[2], range_vis[2], factor_ref, factor_sha;
   float factor_negative, factor_positive, exponent_positive;
   int32_t has_intrinsic;  /* o_r/o_s/o_re + pseudo labels present */
+  const float* weights_dev; /* optional DEVICE float[5] = w_render, w_eikonal, w_curvature, w_intrinsic, w_regularize_re:
+                             * when non-NULL it replaces the five by-value weights (the curvature weight is re-scheduled
+                             * every iteration during warm-up, neuralangelo/trainer.py:56-63) */
 } mli_loss_cfg_t;
 
 enum { MLI_LOSS_TOTAL = 0, MLI_LOSS_RENDER, MLI_LOSS_EIKONAL, MLI_LOSS_CURVATURE, MLI_LOSS_INTRINSIC,

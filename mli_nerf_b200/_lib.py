@@ -33,7 +33,7 @@ class Grid(C.Structure):
 
 class CompositeCfg(C.Structure):
     _fields_ = [("N", C.c_int32), ("mode", C.c_int32), ("white_bg", C.c_int32), ("eval_extras", C.c_int32),
-                ("anneal_ratio", C.c_float)]
+                ("anneal_ratio", C.c_float), ("anneal_dev", C.c_void_p)]
 
 
 class LossCfg(C.Structure):
@@ -41,7 +41,7 @@ class LossCfg(C.Structure):
                 ("w_intrinsic", C.c_float), ("w_regularize_re", C.c_float), ("range_sha", C.c_float * 2),
                 ("range_vis", C.c_float * 2), ("factor_ref", C.c_float), ("factor_sha", C.c_float),
                 ("factor_negative", C.c_float), ("factor_positive", C.c_float), ("exponent_positive", C.c_float),
-                ("has_intrinsic", C.c_int32)]
+                ("has_intrinsic", C.c_int32), ("weights_dev", C.c_void_p)]
 
 
 class WnDesc(C.Structure):

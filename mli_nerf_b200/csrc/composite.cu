@@ -28,6 +28,7 @@ struct CompArgs {
   int64_t R;
   int N, n_ch, mode, white_bg, eval_extras;
   float anneal;
+  const float* anneal_dev;  // device override of `anneal` (graph replay with a moving schedule)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_fwd_kernel(CompArgs a, 
   const int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;
   const float inv_s = expf(a.s_var[0]);
+  const float anneal = a.anneal_dev ? __ldg(a.anneal_dev) : a.anneal;
   const float rv[3] = {a.ray_unit[r * 3], a.ray_unit[r * 3 + 1], a.ray_unit[r * 3 + 2]};
   const float far = a.far[r];
   const int64_t base = r * a.N;
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_fwd_kernel(CompArgs a, 
       const float d0 = a.dists[r * a.ld_d + i];
       const float d1 = (i + 1 < a.N) ? a.dists[r * a.ld_d + i + 1] : far;
       const float g[3] = {a.gradients[(base + i) * 3], a.gradients[(base + i) * 3 + 1], a.gradients[(base + i) * 3 + 2]};
-      al[k] = mli_neus_alpha(a.sdf[base + i], g, rv, d1 - d0, inv_s, a.anneal).alpha;
+      al[k] = mli_neus_alpha(a.sdf[base + i], g, rv, d1 - d0, inv_s, anneal).alpha;
       prod *= 1.0f - al[k];
     }
   }
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_bwd_kernel(CompArgs a, 
   const int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (r >= a.R) return;
   const float inv_s = expf(a.s_var[0]);
+  const float anneal = a.anneal_dev ? __ldg(a.anneal_dev) : a.anneal;
   const float rv[3] = {a.ray_unit[r * 3], a.ray_unit[r * 3 + 1], a.ray_unit[r * 3 + 2]};
   const float far = a.far[r];
   const int64_t base = r * a.N;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_bwd_kernel(CompArgs a, 
       const float d1 = (i + 1 < a.N) ? a.dists[r * a.ld_d + i + 1] : far;
       const float g[3] = {a.gradients[(base + i) * 3], a.gradients[(base + i) * 3 + 1], a.gradients[(base + i) * 3 + 2]};
       sdfv[k] = a.sdf[base + i];
-      al[k] = mli_neus_alpha(sdfv[k], g, rv, d1 - d0, inv_s, a.anneal);
+      al[k] = mli_neus_alpha(sdfv[k], g, rv, d1 - d0, inv_s, anneal);
       prod *= 1.0f - al[k].alpha;
     }
   }
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_bwd_kernel(CompArgs a, 
       const float d_alpha = Tk[k] * (dw[k] - Sx);
       Sx = fmaf(1.0f - al[k].alpha, Sx, dw[k] * al[k].alpha);
       float ds = 0.0f, dg[3] = {0.f, 0.f, 0.f};
-      d_inv_s += mli_neus_alpha_bwd(al[k], sdfv[k], rv, inv_s, a.anneal, d_alpha, &ds, dg);
+      d_inv_s += mli_neus_alpha_bwd(al[k], sdfv[k], rv, inv_s, anneal, d_alpha, &ds, dg);
       d_sdf[base + i] = ds;
       d_gradients[(base + i) * 3 + 0] += dg[0];
       d_gradients[(base + i) * 3 + 1] += dg[1];
@@ -342,7 +345,7 @@ int make_args(CompArgs* a, const mli_composite_cfg_t* cfg, const float* s_var, c
   MLI_REQUIRE(lds >= n_ch_mode[cfg->mode] && ld_d >= cfg->N, "composite: bad lds/ld_d");
   a->s_var = s_var; a->sdf = sdf; a->gradients = gradients; a->ray_unit = ray_unit; a->dists = dists; a->ld_d = ld_d;
   a->far = far; a->S = S; a->lds = lds; a->R = R; a->N = cfg->N; a->n_ch = n_ch_mode[cfg->mode]; a->mode = cfg->mode;
-  a->white_bg = cfg->white_bg; a->eval_extras = cfg->eval_extras; a->anneal = cfg->anneal_ratio;
+  a->white_bg = cfg->white_bg; a->eval_extras = cfg->eval_extras; a->anneal = cfg->anneal_ratio; a->anneal_dev = cfg->anneal_dev;
   return MLI_OK;
 }
 

@@ -18,6 +18,16 @@ enum { P_EIK = 0, P_CURV, P_SAMPLE_TERMS };
 
 __device__ __forceinline__ float sgn(float x) { return (x > 0.0f) - (x < 0.0f); }
 
+// weights_dev (device float[5]) replaces the five by-value loss weights: same kernels, but a captured CUDA graph then
+// follows a weight schedule that moves every iteration
+__device__ __forceinline__ void resolve_weights(mli_loss_cfg_t& cfg) {
+  if (cfg.weights_dev != nullptr) {
+    cfg.w_render = __ldg(cfg.weights_dev + 0); cfg.w_eikonal = __ldg(cfg.weights_dev + 1);
+    cfg.w_curvature = __ldg(cfg.weights_dev + 2); cfg.w_intrinsic = __ldg(cfg.weights_dev + 3);
+    cfg.w_regularize_re = __ldg(cfg.weights_dev + 4);
+  }
+}
+
 __global__ void minmax_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float* __restrict__ mm) {
   __shared__ float red[4][32];
   float lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
@@ -54,6 +64,7 @@ struct RayLossArgs {
 
 __global__ void __launch_bounds__(kT) ray_loss_kernel(RayLossArgs a) {
   __shared__ float red[32];
+  resolve_weights(a.cfg);
   const int64_t r = (int64_t)blockIdx.x * kT + threadIdx.x;
   float t[P_RAY_TERMS];
 #pragma unroll
@@ -117,6 +128,7 @@ __global__ void __launch_bounds__(kT) sample_loss_kernel(mli_loss_cfg_t cfg, con
                                                          float* __restrict__ d_gradients, float* __restrict__ d_hessians,
                                                          float* __restrict__ part) {
   __shared__ float red[32];
+  resolve_weights(cfg);
   const int64_t m = (int64_t)blockIdx.x * kT + threadIdx.x;
   float eik = 0.0f, curv = 0.0f;
   if (m < M) {
@@ -154,6 +166,7 @@ __global__ void final_loss_kernel(mli_loss_cfg_t cfg, const float* __restrict__ 
                                   const float* __restrict__ part_smp, int nb_smp, int64_t R, int64_t M, int n_os,
                                   int has_ore, int has_hess, float* __restrict__ losses) {
   __shared__ float red[32];
+  resolve_weights(cfg);
   float sums[P_RAY_TERMS + P_SAMPLE_TERMS];
   for (int k = 0; k < P_RAY_TERMS; ++k) {
     float v = 0.0f;

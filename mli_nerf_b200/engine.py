@@ -139,6 +139,14 @@ class RenderEngine:
         self.wgrad_after_scatter = False
         self._wg_keep = []
         self._tg_early = None
+        # Schedule scalars that move every iteration -- the s_var anneal ratio (neuralangelo/model.py:492-499) and the loss
+        # weights (curvature warm-up, neuralangelo/trainer.py:56-63) -- can live in a small device buffer
+        # [anneal, w_render, w_eikonal, w_curvature, w_intrinsic, w_regularize_re] that the composite / loss kernels read:
+        # the launches then carry no per-iteration value and ONE captured CUDA graph serves the whole schedule
+        # (Model._graphed_train_step switches this on and refreshes the buffer before each replay).
+        self.dynamic_scalars = False
+        self._dyn = torch.zeros(8, dtype=torch.float32, device=self.device) if self.device.type == "cuda" else None
+        self._dyn_last = None
         self.zero_fill_ctas = int(os.environ.get("MLI_ZERO_FILL_CTAS", "64"))  # 16: 1.6 ms, 32: 0.8 ms, 64: 0.44 ms for 1.46 GB
         # bf16 mode: the head stack as ONE on-chip kernel per direction (csrc/heads_fused.cu).  Measured at the bench shape
         # (tools/bench_heads.py, profiles/r02_heads_fused.md): data-gradient chain 435 us fused vs 564 us layer by layer;
@@ -159,6 +167,18 @@ class RenderEngine:
     # ------------------------------------------------------------------------------------------------------
     def n_table_params(self):
         return int(self.grid.n_entries) * self.cfg.feat_per_level
+
+    def set_dynamic_scalars(self, progress, lcfg):
+        """Refresh the device-resident schedule scalars (stream-ordered copy on the current stream)."""
+        # a fresh pageable host tensor per call: the driver stages it before the copy call returns, so the host may run any
+        # number of steps ahead of the GPU without a later step's values overtaking an earlier step's copy (a reused
+        # pinned buffer would race exactly that way under graph replay)
+        vals = (min(progress / self.cfg.anneal_end, 1.0), lcfg.w_render, lcfg.w_eikonal, lcfg.w_curvature,
+                lcfg.w_intrinsic, lcfg.w_regularize_re, 0.0, 0.0)
+        if vals == self._dyn_last:  # static part of training: nothing to send, replays stay back to back
+            return
+        self._dyn.copy_(torch.tensor(vals, dtype=torch.float32))
+        self._dyn_last = vals
 
     def start_table_grad_zero(self):
         """Zero-fill of the 1.46 GB hash-table gradient buffer, issued on a side stream so that it overlaps the
@@ -626,7 +646,8 @@ class RenderEngine:
                  32, M, nh, W["Wout"], W["bout"], j0s, njs, ACT_SIGMOID, self.act_mask, S, self.lds, Am[3],
                  Am[3].shape[1] if Am[3] is not None else 0, 0, 8)
         ccfg = _lib.CompositeCfg(N, self.mode, int(cfg.white_background), int(not training),
-                                 min(progress / cfg.anneal_end, 1.0))
+                                 min(progress / cfg.anneal_end, 1.0),
+                                 self._dyn.data_ptr() if self.dynamic_scalars else None)
         weights, out = self._f(R, N), self._f(R, self.n_out)
         extras = self._f(R, 5) if not training else None
         call("mli_composite_fwd", ccfg, p["s_var"], sdf, gradients, ray_unit, dists, N, far, S, self.lds, R, None, weights, out,
@@ -920,6 +941,9 @@ class RenderEngine:
         d_out, d_grad = self._f(R, self.n_out), self._f(M, 3)
         d_hess = self._f(M, 3) if hessians is not None else None
         ws = torch.empty(_lib.load().mli_losses_ws_bytes(R, M), dtype=torch.uint8, device=self.device)
+        if self.dynamic_scalars:  # the kernels read the five weights from the device buffer (see set_dynamic_scalars)
+            lcfg = _lib.LossCfg.from_buffer_copy(lcfg)
+            lcfg.weights_dev = self._dyn.data_ptr() + 4
         call("mli_losses_fwd_bwd", lcfg, self.mode, out, gradients, hessians, outside, R, N, targets["image_sampled"],
              targets.get("pseudo_ref_sampled"), targets.get("pseudo_sha_sampled"),
              targets.get("pseudo_visibility_certainty_sampled"), losses, d_out, d_grad, d_hess, ws)

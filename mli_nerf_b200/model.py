@@ -483,17 +483,23 @@ class Model(torch.nn.Module):
         return losses
 
     def _graphed_train_step(self, data, loss_cfg, after_backward=None):
-        """CUDA-graph replay of the step.  Host-side scalars (anneal ratio, tap epsilon, active levels, loss weights) are
-        baked into the captured launches, so the graph is keyed on them.  ONE graph is kept (the previous one is dropped
-        when the key changes) and a new key is only captured once it has been seen on two consecutive steps: while a
-        schedule moves every iteration (s_var anneal during the first anneal_end*max_iter iterations, the coarse-to-fine
-        warm-up of stage a) the steps run eagerly instead of re-capturing each time; the graph pays off on the static
-        part of training (stage b, and stage a after the anneal)."""
+        """CUDA-graph replay of the step.  The two schedule values that move EVERY iteration for long stretches of
+        training -- the s_var anneal ratio (first anneal_end*max_iter iterations) and the loss weights (curvature
+        warm-up) -- are read by the kernels from a small device buffer that is refreshed before each replay
+        (engine.set_dynamic_scalars), so they are not part of the graph.  What remains baked into the captured launches is
+        piecewise constant (tap epsilon and active levels change 16 times over a coarse-to-fine run; the non-weight
+        fields of the loss config, requires_grad flags, shapes): the graph is keyed on it, ONE graph is kept (the previous
+        one is dropped when the key changes), and a new key is only captured once it has been seen on two consecutive
+        steps -- the step in between runs eagerly."""
         tensors = {k: v for k, v in data.items() if isinstance(v, torch.Tensor) and v.is_cuda}
         eng = self.engine
+        static_cfg = _lib.LossCfg.from_buffer_copy(loss_cfg)
+        static_cfg.w_render = static_cfg.w_eikonal = static_cfg.w_curvature = 0.0
+        static_cfg.w_intrinsic = static_cfg.w_regularize_re = 0.0
+        static_cfg.weights_dev = None
         key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items())),
-               min(self.progress / self.anneal_end, 1.0), float(self.neural_sdf.normal_eps), int(eng.grid.active_levels),
-               tuple(p.requires_grad for p in self.parameters()), bytes(loss_cfg), self.path_cfg.precision)
+               float(self.neural_sdf.normal_eps), int(eng.grid.active_levels),
+               tuple(p.requires_grad for p in self.parameters()), bytes(static_cfg), self.path_cfg.precision)
         st = self.__dict__.get("_graph_state")
         if st is not None and st[0] != key:
             st = None
@@ -501,27 +507,33 @@ class Model(torch.nn.Module):
         if st is None:
             seen_before = self.__dict__.get("_graph_last_key") == key
             self.__dict__["_graph_last_key"] = key
-            if not seen_before:  # moving schedule: do not capture yet
+            if not seen_before:  # first step with this key: do not capture yet
                 return self.fused_train_step(data, loss_cfg, after_backward=after_backward)
             static = {k: v.clone() for k, v in tensors.items()}
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):  # eager warm-up off the capture stream (lazy loads, smem attributes)
-                for _ in range(2):
-                    self.fused_train_step(static, loss_cfg, after_backward=after_backward)
-            cur.wait_stream(side)
-            # kernels captured from this stream inherit its access-policy window (L2 residency of the dense table levels)
-            eng.apply_l2_window(self.neural_sdf.tcnn_encoding.params)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                losses = self.fused_train_step(static, loss_cfg, after_backward=after_backward)
+            eng.dynamic_scalars = True
+            try:
+                eng.set_dynamic_scalars(self.progress, loss_cfg)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):  # eager warm-up off the capture stream (lazy loads, smem attributes)
+                    for _ in range(2):
+                        self.fused_train_step(static, loss_cfg, after_backward=after_backward)
+                cur.wait_stream(side)
+                # kernels captured from this stream inherit its access-policy window (L2 residency of the dense table levels)
+                eng.apply_l2_window(self.neural_sdf.tcnn_encoding.params)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    losses = self.fused_train_step(static, loss_cfg, after_backward=after_backward)
+            finally:
+                eng.dynamic_scalars = False
             grads = {n: p.grad for n, p in self.named_parameters() if p.grad is not None}
             st = (key, graph, static, losses, grads)
             self.__dict__["_graph_state"] = st
         _, graph, static, losses, grads = st
         for k, v in tensors.items():
             static[k].copy_(v, non_blocking=True)
+        eng.set_dynamic_scalars(self.progress, loss_cfg)
         graph.replay()
         for n, p in self.named_parameters():
             if n in grads:

@@ -17,7 +17,7 @@ def test_every_declared_symbol_is_exported(mli_lib):
     lib = mli_lib.load()
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/mli_b200.h but not exported by libmli_b200.so"
-    assert lib.mli_abi_version() == 3
+    assert lib.mli_abi_version() == 4
 
 
 def test_signature_table_covers_header(mli_lib):

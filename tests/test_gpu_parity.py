@@ -985,3 +985,50 @@ def test_autograd_path_releases_a_step_by_refcount(lib, prec):
     # buffer (8 MiB at T = 2^14) with the engine, which the next step replaces
     table_bytes = model.engine.n_table_params() * 4
     assert grown <= table_bytes + (1 << 20), (grown, table_bytes)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_graph_step_follows_moving_schedules_without_recapture(lib, prec):
+    """use_graph=True while the s_var anneal ratio and the curvature weight change every iteration (the first tens of
+    thousands of iterations of a real run): the kernels read both from the engine's device buffer, so ONE captured graph
+    must reproduce the eager step of every iteration -- losses and gradients -- and must not be re-captured."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    from mli_nerf_b200.model import Model
+    R = 256
+    cfg = config.experiment("syn_hotdog_b", dict_size=14, rand_rays=R)
+    cfg.model.render.stratified = False   # torch.rand inside a graph draws from a different Philox offset than eager
+    cfg.model.mli_precision = prec
+    model = Model(cfg.model, cfg.data)
+    model.load_state_dict(port.init_params(port.PathConfig(log2_hashmap_size=14), seed=0, generic=True, table_scale=5e-3))
+    model = model.cuda().train()
+    pose = torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[711.0, 0, 256], [0, 711.0, 256], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, 1.0], [0, 1, 0, -2.0], [0, 0, 1, 3.0]]], dtype=torch.float32)
+    ray_idx = torch.randperm(512 * 512, generator=torch.Generator().manual_seed(0))[:R][None]
+    data = {k: cu(v) for k, v in dict(pose=pose, intr=intr, pose_light=pose_light, ray_idx=ray_idx,
+                                      **port.synthetic_targets(R)).items()}
+    graphs = set()
+    anneal_end = model.anneal_end
+    schedule = [(0.0, 1e-4), (0.1 * anneal_end, 2e-4), (0.35 * anneal_end, 5e-4), (0.8 * anneal_end, 5e-4), (2.0 * anneal_end, 0.0)]
+    for it, (progress, w_curv) in enumerate(schedule):
+        model.progress = progress
+        lcfg = loss_cfg_from_trainer(cfg.trainer)
+        lcfg.w_curvature = w_curv
+        lg = model.fused_train_step(data, lcfg, use_graph=True).clone()
+        gg = {n: p.grad.clone() for n, p in model.named_parameters()}
+        st = model.__dict__.get("_graph_state")
+        if st is not None:
+            graphs.add(id(st[1]))
+        le = model.fused_train_step(data, lcfg, use_graph=False)
+        assert torch.allclose(lg, le, rtol=1e-6, atol=1e-8), (it, lg, le)
+        for n, p in model.named_parameters():
+            err = float((p.grad - gg[n]).norm() / (gg[n].norm() + 1e-30))
+            assert err < 1e-5, (it, n, err)
+    assert len(graphs) == 1   # captured on the second step, replayed for every later point of the schedule
+    # the schedule really moved what the step computes
+    model.progress = 0.0
+    l_a = model.fused_train_step(data, lcfg, use_graph=True).clone()
+    model.progress = 2.0 * anneal_end
+    l_b = model.fused_train_step(data, lcfg, use_graph=True).clone()
+    assert float((l_a - l_b).abs().max()) > 1e-6
