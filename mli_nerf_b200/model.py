@@ -441,8 +441,8 @@ class Model(torch.nn.Module):
         Equivalent to ``total = trainer.model_forward(data); total.backward()`` of the reference
         (projects/nerf/trainers/base.py:99-107, NeuralLumen/trainer.py:133-149,189-196): fills ``.grad`` of every
         parameter with ``requires_grad`` and returns the device tensor of losses (see _lib.LOSS_NAMES).
-        ``use_graph``: replay the ~130 kernel launches of the step from a CUDA graph (captured on first use and
-        re-captured whenever a host-side scalar baked into the launches changes)."""
+        ``use_graph``: replay the ~75 kernel launches of the step from ONE CUDA graph (see _graphed_train_step: the
+        per-iteration schedule scalars are device resident, only a coarse-to-fine level change re-captures)."""
         if use_graph and not accumulate:
             return self._graphed_train_step(data, loss_cfg, after_backward)
         eng = self.engine
