@@ -210,7 +210,7 @@ def profile_end():
 def _n_launches(name, args):
     """How many of our kernels one call launches (for bench.py's gpu_launches claim)."""
     if name == "mli_tc_wgrad":
-        return 3 if args[17] is not None else 2
+        return 3 if args[16] is not None else 2  # TN GEMM + split-K reduce (+ bias-gradient reduce when colsum_L is given)
     if name in ("mli_linear_wgrad", "mli_tc_colsum"):
         return 2
     if name == "mli_tc_sdf_trunk_bwd":

@@ -57,3 +57,24 @@ def test_trainer_loss_stand_in_matches_the_oracle():
     want, _, _ = port.total_loss(port.PathConfig(), out, data)
     got = bench.trainer_losses_torch(cfg.trainer, out, data)
     assert abs(float(got) - float(want)) < 1e-5 * abs(float(want))
+
+
+def test_launch_count_indices_point_at_the_right_header_arguments():
+    """_lib._n_launches decides from optional pointer arguments how many kernels a call launches (bench.py's
+    gpu_launches claim); the positions are checked against include/mli_b200.h so they cannot drift from the ABI."""
+    import re
+    from mli_nerf_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+
+    def arg(name, idx):
+        m = re.search(r"\b" + name + r"\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+        return " ".join(m.group(1).split()).split(",")[idx].split()[-1].lstrip("*")
+
+    assert arg("mli_tc_wgrad", 16) == "colsum_L"
+    assert arg("mli_tc_sdf_trunk_bwd", 9) == "dw_sdf"
+    assert arg("mli_rowdot_bwd", 10) == "dA" and arg("mli_rowdot_bwd", 14) == "dw"
+    assert arg("mli_composite_bwd", 18) == "d_s_var"
+    none17 = [None] * 19
+    assert _lib._n_launches("mli_tc_wgrad", none17) == 2
+    none17[16] = 1
+    assert _lib._n_launches("mli_tc_wgrad", none17) == 3
