@@ -223,7 +223,7 @@ def kernel_work(name, a):
     if name == "mli_tc_heads_bwd":
         M, nh = a[2], a[3]
         return 2.0 * M * nh * 256 * 3 * 256 + 2.0 * M * 256 * 7, float(M * 8 * f32 + M * nh * 256 // 8 * 4 + M * nh * 256 * 2 * 4)
-    if name == "mli_tc_wgrad":
+    if name in ("mli_tc_wgrad", "mli_tc_wgrad_defer"):
         M, rows, cols, batch = a[8], a[9], a[10], a[11]
         return 2.0 * M * rows * cols * batch, float(M * batch * (rows + cols) * 2)
     if name == "mli_tc_sdf_trunk_fused":

@@ -249,6 +249,25 @@ int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_ba
                  int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
                  int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
                  int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream);
+
+/* The same GEMM with its split-K reduction DEFERRED: only the tensor-core kernel is launched and *job_on_host is filled
+ * with what is left to do; mli_tc_wgrad_reduce_batch then reduces the partials of up to any number of such jobs (weight
+ * and bias gradients of a whole backward pass: 13 small launches in the reference-shaped step) in ONE launch on the same
+ * stream.  The workspaces must stay alive until that launch has run.  Results are bit-identical to mli_tc_wgrad. */
+typedef struct {
+  const float* part;      /* [batch][S][rows*cols] fp32 partials (inside ws) */
+  const float* cs_part;   /* [batch][S][rows] column-sum partials, NULL without colsum_L */
+  float* out;
+  float* colsum;
+  int64_t ldo, out_batch_stride, colsum_batch_stride;
+  int32_t S, rows, cols, batch, transpose, reserved;
+} mli_tn_reduce_job_t;
+int mli_tc_wgrad_defer(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                       int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                       int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                       int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws,
+                       mli_tn_reduce_job_t* job_on_host, void* stream);
+int mli_tc_wgrad_reduce_batch(const mli_tn_reduce_job_t* jobs_on_host, int32_t n_jobs, void* stream);
 /* Column sums (bias gradients) of chunks [chunk0, chunk0+n_chunks) of a TCL-128 matrix -> out[8*n_chunks]. */
 int64_t mli_tc_colsum_ws_bytes(int64_t M, int32_t n_chunks);
 int mli_tc_colsum(const void* src, int32_t src_chunks, int32_t chunk0, int32_t n_chunks, int64_t M, float* out, void* ws,

@@ -44,6 +44,14 @@ class LossCfg(C.Structure):
                 ("has_intrinsic", C.c_int32), ("weights_dev", C.c_void_p)]
 
 
+class TnReduceJob(C.Structure):
+    """mli_tn_reduce_job_t (a deferred split-K reduction of mli_tc_wgrad_defer)."""
+    _fields_ = [("part", C.c_void_p), ("cs_part", C.c_void_p), ("out", C.c_void_p), ("colsum", C.c_void_p),
+                ("ldo", C.c_int64), ("out_batch_stride", C.c_int64), ("colsum_batch_stride", C.c_int64),
+                ("S", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("batch", C.c_int32),
+                ("transpose", C.c_int32), ("reserved", C.c_int32)]
+
+
 class WnDesc(C.Structure):
     """mli_wn_desc_t (batched weight_norm pack / unpack)."""
     _fields_ = [("v", C.c_void_p), ("g", C.c_void_p), ("col_map", C.c_void_p),
@@ -211,6 +219,8 @@ def _n_launches(name, args):
     """How many of our kernels one call launches (for bench.py's gpu_launches claim)."""
     if name == "mli_tc_wgrad":
         return 3 if args[16] is not None else 2  # TN GEMM + split-K reduce (+ bias-gradient reduce when colsum_L is given)
+    if name == "mli_tc_wgrad_reduce_batch":
+        return (args[1] + 15) // 16
     if name in ("mli_linear_wgrad", "mli_tc_colsum"):
         return 2
     if name == "mli_tc_sdf_trunk_bwd":

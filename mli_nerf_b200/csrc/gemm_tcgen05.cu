@@ -1447,11 +1447,11 @@ extern "C" int64_t mli_tc_wgrad_ws_bytes(int64_t M, int32_t rows_out, int32_t co
 }
 
 // out[b][r, c] (or transposed) = sum_m L[m, l0 + r] * R[m, r0 + c],  r < rows_out (multiple of 128), c < cols_out
-extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
-                            int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
-                            int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
-                            int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream) {
-  MLI_ENTRY();
+static int tc_wgrad_impl(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                         int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                         int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                         int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream,
+                         mli_tn_reduce_job_t* job) {
   MLI_REQUIRE(M >= 1 && batch >= 1 && rows_out >= 128 && rows_out % 128 == 0, "tc_wgrad: rows_out must be a multiple of 128");
   MLI_REQUIRE(cols_out >= 16 && cols_out % 16 == 0, "tc_wgrad: cols_out must be a multiple of 16");
   MLI_REQUIRE(ws != nullptr, "tc_wgrad: workspace is NULL");
@@ -1472,17 +1472,107 @@ extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, i
   if (colsum_L) {
     if (int e = set_smem((const void*)tc_gemm_tn_kernel<true>, smem)) return e;
     tc_gemm_tn_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-    MLI_LAUNCH_OK();
-    tn_colsum_reduce_kernel<<<dim3(mli_cdiv(rows_out, 256), batch), 256, 0, (cudaStream_t)stream>>>(p.cs_part, S, rows_out, colsum_L,
-                                                                                                 colsum_batch_stride);
   } else {
     if (int e = set_smem((const void*)tc_gemm_tn_kernel<false>, smem)) return e;
     tc_gemm_tn_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   }
   MLI_LAUNCH_OK();
+  if (job != nullptr) {  // deferred: the caller reduces the partials of several GEMMs in one launch
+    job->part = p.part; job->cs_part = colsum_L ? p.cs_part : nullptr; job->out = out; job->colsum = colsum_L;
+    job->ldo = ldo; job->out_batch_stride = out_batch_stride; job->colsum_batch_stride = colsum_batch_stride;
+    job->S = S; job->rows = rows_out; job->cols = cols_out; job->batch = batch; job->transpose = transpose_out;
+    job->reserved = 0;
+    return MLI_OK;
+  }
+  if (colsum_L) {
+    tn_colsum_reduce_kernel<<<dim3(mli_cdiv(rows_out, 256), batch), 256, 0, (cudaStream_t)stream>>>(p.cs_part, S, rows_out, colsum_L,
+                                                                                                 colsum_batch_stride);
+    MLI_LAUNCH_OK();
+  }
   dim3 g2(mli_cdiv((int64_t)rows_out * cols_out, 256), batch);
   tn_reduce_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(p.part, S, rows_out, cols_out, out, ldo, out_batch_stride, transpose_out);
   MLI_LAUNCH_OK();
+  return MLI_OK;
+}
+
+extern "C" int mli_tc_wgrad(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                            int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                            int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                            int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws, void* stream) {
+  MLI_ENTRY();
+  return tc_wgrad_impl(L, l_chunks, l_chunk0, l_batch_chunks, R, r_chunks, r_chunk0, r_batch_chunks, M, rows_out, cols_out,
+                       batch, out, ldo, out_batch_stride, transpose_out, colsum_L, colsum_batch_stride, ws, stream, nullptr);
+}
+
+extern "C" int mli_tc_wgrad_defer(const void* L, int32_t l_chunks, int32_t l_chunk0, int32_t l_batch_chunks, const void* R,
+                                  int32_t r_chunks, int32_t r_chunk0, int32_t r_batch_chunks, int64_t M, int32_t rows_out,
+                                  int32_t cols_out, int32_t batch, float* out, int64_t ldo, int64_t out_batch_stride,
+                                  int32_t transpose_out, float* colsum_L, int64_t colsum_batch_stride, void* ws,
+                                  mli_tn_reduce_job_t* job_on_host, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(job_on_host != nullptr, "tc_wgrad_defer: job descriptor is NULL");
+  return tc_wgrad_impl(L, l_chunks, l_chunk0, l_batch_chunks, R, r_chunks, r_chunk0, r_batch_chunks, M, rows_out, cols_out,
+                       batch, out, ldo, out_batch_stride, transpose_out, colsum_L, colsum_batch_stride, ws, stream, job_on_host);
+}
+
+namespace {
+constexpr int kMaxTnJobs = 16;
+struct TnBatch {
+  mli_tn_reduce_job_t j[kMaxTnJobs];
+  int block0[kMaxTnJobs + 1];
+  int n;
+};
+// every deferred split-K reduction of a backward pass (weight gradients + bias gradients) in one launch; per element the
+// partials are summed in split order, exactly as tn_reduce_kernel / tn_colsum_reduce_kernel do
+__global__ void __launch_bounds__(256) tn_reduce_batch_kernel(const __grid_constant__ TnBatch b) {
+  int k = 0;
+  while (k + 1 < b.n && (int)blockIdx.x >= b.block0[k + 1]) ++k;
+  const mli_tn_reduce_job_t& j = b.j[k];
+  int lb = (int)blockIdx.x - b.block0[k];
+  const int64_t total = (int64_t)j.rows * j.cols;
+  const int per_batch = (int)((total + 255) / 256);
+  const int n_main = per_batch * j.batch;
+  if (lb < n_main) {
+    const int bb = lb / per_batch;
+    const int64_t e = (int64_t)(lb - bb * per_batch) * 256 + threadIdx.x;
+    if (e >= total) return;
+    float v = 0.0f;
+    for (int s = 0; s < j.S; ++s) v += j.part[((size_t)(bb * j.S + s)) * total + e];
+    const int r = (int)(e / j.cols), c = (int)(e % j.cols);
+    if (j.transpose) j.out[bb * j.out_batch_stride + (int64_t)c * j.ldo + r] = v;
+    else j.out[bb * j.out_batch_stride + (int64_t)r * j.ldo + c] = v;
+  } else {
+    lb -= n_main;
+    const int per_b = (j.rows + 255) / 256;
+    const int bb = lb / per_b;
+    const int e = (lb - bb * per_b) * 256 + threadIdx.x;
+    if (e >= j.rows) return;
+    float v = 0.0f;
+    for (int s = 0; s < j.S; ++s) v += j.cs_part[((size_t)(bb * j.S + s)) * j.rows + e];
+    j.colsum[bb * j.colsum_batch_stride + e] = v;
+  }
+}
+}  // namespace
+
+extern "C" int mli_tc_wgrad_reduce_batch(const mli_tn_reduce_job_t* jobs_on_host, int32_t n_jobs, void* stream) {
+  MLI_ENTRY();
+  MLI_REQUIRE(n_jobs >= 0 && (jobs_on_host != nullptr || n_jobs == 0), "tc_wgrad_reduce_batch: bad arguments");
+  for (int first = 0; first < n_jobs; first += kMaxTnJobs) {
+    TnBatch b;
+    b.n = n_jobs - first < kMaxTnJobs ? n_jobs - first : kMaxTnJobs;
+    int blocks = 0;
+    for (int k = 0; k < b.n; ++k) {
+      const mli_tn_reduce_job_t& j = jobs_on_host[first + k];
+      MLI_REQUIRE(j.part && j.out && j.S >= 1 && j.rows >= 1 && j.cols >= 1 && j.batch >= 1, "tc_wgrad_reduce_batch: job %d is empty", first + k);
+      b.j[k] = j;
+      b.block0[k] = blocks;
+      blocks += (int)(((int64_t)j.rows * j.cols + 255) / 256) * j.batch;
+      if (j.colsum != nullptr) blocks += ((j.rows + 255) / 256) * j.batch;
+    }
+    b.block0[b.n] = blocks;
+    tn_reduce_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(b);
+    MLI_LAUNCH_OK();
+  }
   return MLI_OK;
 }
 

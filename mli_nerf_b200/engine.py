@@ -138,6 +138,7 @@ class RenderEngine:
         # link of the data-gradient chain, has produced a slab -- has ~0.9 ms of independent work to hide behind
         self.wgrad_after_scatter = False
         self._wg_keep = []
+        self._wg_jobs = None
         self._tg_early = None
         # Schedule scalars that move every iteration -- the s_var anneal ratio (neuralangelo/model.py:492-499) and the loss
         # weights (curvature warm-up, neuralangelo/trainer.py:56-63) -- can live in a small device buffer
@@ -446,11 +447,29 @@ class RenderEngine:
         return torch.empty((rows + 127) // 128, cols // 32, 128, dtype=torch.int32, device=self.device)
 
     def _tc_wgrad(self, L, l_chunk0, l_b, R, r_chunk0, r_b, M, rows, cols, batch, out, ldo, bstride, transpose=0,
-                  db=None):
-        """out[b] = L[b]^T R[b]; db (optional, [batch*rows]) = column sums of L from the same pass (bias gradient)."""
+                  db=None, defer=True):
+        """out[b] = L[b]^T R[b]; db (optional, [batch*rows]) = column sums of L from the same pass (bias gradient).
+        defer=False: the caller reads `out` right away (no batching of the split-K reduction)."""
         ws = torch.empty(_lib.load().mli_tc_wgrad_ws_bytes(M, rows, cols, batch), dtype=torch.uint8, device=self.device)
+        if defer and self._wg_jobs is not None:  # inside backward(): the split-K reductions of all GEMMs run as one launch later
+            job = _lib.TnReduceJob()
+            call("mli_tc_wgrad_defer", L, L.shape[1], l_chunk0, l_b, R, R.shape[1], r_chunk0, r_b, M, rows, cols, batch, out,
+                 ldo, bstride, transpose, db, rows, ws, job)
+            self._wg_jobs.append((job, ws, out, db))  # the partials (and outputs) must outlive the batched reduction
+            return
         call("mli_tc_wgrad", L, L.shape[1], l_chunk0, l_b, R, R.shape[1], r_chunk0, r_b, M, rows, cols, batch, out, ldo,
              bstride, transpose, db, rows, ws)
+
+    def _tc_wgrad_flush(self):
+        """One launch for the deferred split-K reductions (weight + bias gradients) of every weight-gradient GEMM issued
+        since backward() started; must run on the stream those GEMMs were launched on, before anything reads dW / db."""
+        jobs = self._wg_jobs
+        if not jobs:
+            return
+        arr = (_lib.TnReduceJob * len(jobs))(*[j[0] for j in jobs])
+        call("mli_tc_wgrad_reduce_batch", _lib.C.addressof(arr), len(jobs))
+        self._wg_keep.append(list(jobs))  # released at the stream join
+        jobs.clear()
 
     def _tc_colsum(self, X, chunk0, n_chunks, M, out=None):
         out = self._f(n_chunks * 8) if out is None else out
@@ -666,6 +685,7 @@ class RenderEngine:
         prec = _lib.PREC_FP32  # the CUDA-core entry points; tensor-core layers go through _tc_*
         need_sdf = ("sdf" in need) or ("table" in need)
         grads = {}
+        self._wg_jobs = [] if self.tc else None  # deferred split-K reductions of this pass (see _tc_wgrad_flush)
         d_grad = d_gradients.contiguous().clone() if d_gradients is not None else self._z(M, 3)
         dS, d_sdf_c = self._f(M, self.lds), self._f(M)
         d_svar = self._z(1) if "s_var" in need else None
@@ -677,6 +697,7 @@ class RenderEngine:
         A = ctx["A"]
         need_heads = "heads" in need
         if not (need_heads or need_sdf):
+            self._wg_jobs = None
             return grads
         train_mlp = "sdf" in need
         H0 = ctx["H0"]
@@ -751,7 +772,7 @@ class RenderEngine:
                 def _out_layer():
                     dSt = self._to_tcl(dS, self.lds, M, self.lds, self._tcl(M, 2), 128, 0, 2)
                     outT = self._f(nh, 16, HID)  # [head][j][k] = sum_m dS[m, j] A4[m, head*256 + k]
-                    self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1)
+                    self._tc_wgrad(A[3], 0, 32, dSt, 0, 0, M, HID, 16, nh, outT, HID, 16 * HID, transpose=1, defer=False)
                     dWout.copy_(torch.stack([outT[self.col_off[j] // HID, j] for j in range(self.J)]))
                     dbout.copy_(self._tc_colsum(dSt, 0, 2, M)[:self.J])
                 later.append(_out_layer)
@@ -796,12 +817,18 @@ class RenderEngine:
             dW0 = grads.pop("_dW0", None)
             if need_heads or dW0 is not None:
                 unp = {}
-                self._flush_later([lambda: unp.update(self._unpack_grads_tc(p, dW0, dW1, dWh0, dWh, dWout, need_heads,
-                                                                             dW0 is not None))])
+
+                def _reduce_and_unpack():
+                    self._tc_wgrad_flush()  # dW / db of every layer: one launch for the 13 split-K reductions
+                    unp.update(self._unpack_grads_tc(p, dW0, dW1, dWh0, dWh, dWout, need_heads, dW0 is not None))
+                self._flush_later([_reduce_and_unpack])
                 grads.update(unp)
+            else:
+                self._flush_later([self._tc_wgrad_flush])
+            self._wg_jobs = None
             if self.overlap_wgrad and self._wg_stream is not None:
                 cur.wait_stream(self._wg_stream)  # join: all gradients are complete for whoever reads them next
-                self._wg_keep.clear()
+            self._wg_keep.clear()
             if need_heads:
                 j0 = 0
                 for hi, (name, kind, odim, _) in enumerate(self.heads):
