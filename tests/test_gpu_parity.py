@@ -1032,3 +1032,43 @@ def test_graph_step_follows_moving_schedules_without_recapture(lib, prec):
     model.progress = 2.0 * anneal_end
     l_b = model.fused_train_step(data, lcfg, use_graph=True).clone()
     assert float((l_a - l_b).abs().max()) > 1e-6
+
+
+def test_short_training_run_graph_mode_with_schedules(lib):
+    """Forty optimizer steps the way a trainer drives the model: fused_train_step(use_graph=True)
+    + FusedAdamW, `progress` advancing through the s_var anneal and the curvature weight warming up every iteration.
+    The render loss on the fixed batch must go down, everything stays finite, and the graph is captured once."""
+    from mli_nerf_b200 import config
+    from mli_nerf_b200.losses import loss_cfg_from_trainer
+    from mli_nerf_b200.model import Model
+    from mli_nerf_b200.optim import FusedAdamW
+    R = 256
+    cfg = config.experiment("syn_hotdog_b", dict_size=14, rand_rays=R)
+    cfg.model.mli_precision = "bf16"
+    torch.manual_seed(0)
+    model = Model(cfg.model, cfg.data)
+    model.load_state_dict(port.init_params(port.PathConfig(log2_hashmap_size=14), seed=0, generic=True, table_scale=5e-3))
+    model = model.cuda().train()
+    pose = torch.tensor([[[1, 0, 0, 0.0], [0, -1, 0, 0.0], [0, 0, -1, 3.0]]], dtype=torch.float32)
+    intr = torch.tensor([[[711.0, 0, 256], [0, 711.0, 256], [0, 0, 1]]])
+    pose_light = torch.tensor([[[1, 0, 0, 1.0], [0, 1, 0, -2.0], [0, 0, 1, 3.0]]], dtype=torch.float32)
+    ray_idx = torch.randperm(512 * 512, generator=torch.Generator().manual_seed(0))[:R][None]
+    data = {k: cu(v) for k, v in dict(pose=pose, intr=intr, pose_light=pose_light, ray_idx=ray_idx,
+                                      **port.synthetic_targets(R)).items()}
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-2)
+    render, graphs = [], set()
+    n_steps = 40
+    for it in range(n_steps):
+        model.progress = it / n_steps * 2.0 * model.anneal_end       # crosses the end of the anneal
+        lcfg = loss_cfg_from_trainer(cfg.trainer)
+        lcfg.w_curvature = 5e-4 * min(1.0, (it + 1) / 25.0)           # warm-up: a new value every iteration
+        losses = model.fused_train_step(data, lcfg, use_graph=True)
+        opt.step()
+        render.append(float(losses[1]))
+        st = model.__dict__.get("_graph_state")
+        if st is not None:
+            graphs.add(id(st[1]))
+    assert all(math.isfinite(v) for v in render), render
+    assert all(bool(torch.isfinite(p).all()) for p in model.parameters())
+    assert sum(render[-5:]) / 5 < sum(render[:5]) / 5, (render[:5], render[-5:])   # fixed batch: it is being fitted
+    assert len(graphs) == 1
