@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timing breakdown of the autograd drop-in path (model(data) -> torch losses -> backward()) at the bench workload."""
+"""tools/profile_dropin.py -- timing breakdown of the autograd drop-in path (model(data) -> torch losses -> backward()) at the bench workload."""
 import os
 import sys
 import time
