@@ -148,7 +148,7 @@ class RenderEngine:
         self.dynamic_scalars = False
         self._dyn = torch.zeros(8, dtype=torch.float32, device=self.device) if self.device.type == "cuda" else None
         self._dyn_last = None
-        self.zero_fill_ctas = int(os.environ.get("MLI_ZERO_FILL_CTAS", "64"))  # 16: 1.6 ms, 32: 0.8 ms, 64: 0.44 ms for 1.46 GB
+        self.zero_fill_ctas = int(os.environ.get("MLI_ZERO_FILL_CTAS", "128"))  # 1.46 GB: 16 CTAs 1.6 ms, 64: 0.44, 128: 0.26 (step 4.689 / 4.671)
         # bf16 mode: the head stack as ONE on-chip kernel per direction (csrc/heads_fused.cu).  Measured at the bench shape
         # (tools/bench_heads.py, profiles/r02_heads_fused.md): data-gradient chain 435 us fused vs 564 us layer by layer;
         # forward WITHOUT stored activations (inference / no-grad) 493 us vs 579 us; forward that also has to write the
