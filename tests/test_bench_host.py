@@ -78,3 +78,43 @@ def test_launch_count_indices_point_at_the_right_header_arguments():
     assert _lib._n_launches("mli_tc_wgrad", none17) == 2
     none17[16] = 1
     assert _lib._n_launches("mli_tc_wgrad", none17) == 3
+
+
+def test_committed_profile_tables_regenerate_from_the_committed_raw_pages(tmp_path):
+    """profiles/traffic.json (read by bench.py for roofline.traffic) and the launch table must be what
+    tools/launches_summary.py makes of the committed ncu launch list, and tools/ncu_summary.py must read the committed
+    `--set full` raw page: the evidence under profiles/ stays consistent with the tools that produced it."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    prof = os.path.join(root, "profiles")
+    out_md = tmp_path / "launches.md"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "launches_summary.py"),
+                        os.path.join(prof, "r02_launches_bf16.csv"), str(out_md), "--precision", "bf16", "--grad", "full"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    regenerated = json.load(open(tmp_path / "traffic.json"))
+    committed = json.load(open(os.path.join(prof, "traffic.json")))
+    for k in ("dense_layers_dram_bytes_per_step", "dense_layers_us_per_step_ncu", "step_us_ncu"):
+        assert abs(regenerated[k] - committed[k]) <= 1e-6 * abs(committed[k]), k
+    assert open(out_md).read() == open(os.path.join(prof, "r02_launches_bf16.md")).read()
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"),
+                        os.path.join(prof, "r02_step_full_raw.csv"), "--md", "--merge"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for kernel in ("tc_gemm_nt_persist_kernel", "tc_gemm_tn_kernel", "tc_sdf_trunk_fused_kernel", "tc_heads_kernel",
+                   "encode_rays_tcl_cached_kernel", "encode_rays_bwd_tcl_v2_kernel", "sdf_trunk_bwd_kernel"):
+        assert kernel in r.stdout, kernel
+
+
+def test_saved_tensor_aliases_break_identity_not_storage():
+    """model._aliases (what the render node keeps on ctx): same storage, new tensor objects, containers rebuilt."""
+    import torch
+    from mli_nerf_b200.model import _aliases
+    a, b = torch.arange(6.0), torch.ones(3)
+    saved = {"x": a, "lst": [b, None], "tup": (a, 3), "n": 7, "s": "k"}
+    out = _aliases(saved)
+    assert out["x"] is not a and out["x"].data_ptr() == a.data_ptr()
+    assert out["lst"][0] is not b and out["lst"][0].data_ptr() == b.data_ptr() and out["lst"][1] is None
+    assert isinstance(out["tup"], tuple) and out["tup"][1] == 3 and out["n"] == 7 and out["s"] == "k"
