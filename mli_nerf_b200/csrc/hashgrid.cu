@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(KS * 7) encode_rays_tcl_kernel(mli_grid_t grid
 // cell and read the same eight table entries: those are fetched once (8 x LDG.256 in flight) and kept in registers;
 // every same-cell tap is then pure arithmetic.  Taps that left the cell are deferred to a second, warp-compacted pass
 // that re-uses the 64 value registers.  Per (sample, level) the kernel issues 8 + 8 x (taps outside the cell) sector requests instead of
-// 8 x planes, which is what the thread-per-plane kernel above was bound by (L1TEX at 69 %, ncu r02).  Results are bit
+// 8 x planes, which is what the thread-per-plane kernel above was bound by (L1TEX at 69 %: profiles/r02_summary.md section 7).  Results are bit
 // for bit those of encode_rays_tcl_kernel: same weights, same fma chain, delta formed in fp32.
 template <int PLANES>
 __global__ void __launch_bounds__(128, 4) encode_rays_tcl_cached_kernel(mli_grid_t grid, const float* __restrict__ table,
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128, 4) encode_rays_tcl_cached_kernel(mli_grid
   }
   // Second pass, compacted per warp: the (lane, plane) pairs that left the centre's cell are listed in shared memory and
   // handed out 32 at a time, so every round runs with full warps (the first version let each lane walk its own taps:
-  // 30 % of all executed instructions ran with 6 of 32 lanes active, ncu r02_enc2).  The owner's centre row comes
+  // 30 % of all executed instructions ran with 6 of 32 lanes active: profiles/r02_summary.md section 7).  The owner's centre row comes
   // through shared memory; the item's ray is re-read (L1 hits).
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (__ballot_sync(0xffffffffu, deferred != 0) == 0) return;
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(kBwdThreads, 5) encode_rays_bwd_tcl_kernel(mli
 }
 
 // Version 2 of the stencil scatter (PLANES > 1).  Two changes against encode_rays_bwd_tcl_kernel, both aimed at what ncu
-// showed for it (r02_encb: 24 % of the executed instructions ran in the "tap left the centre's cell" branch with 8 of 32
+// showed for it (profiles/r02_summary.md section 7: 24 % of the executed instructions ran in the "tap left the centre's cell" branch with 8 of 32
 // lanes active, and that branch issued 8 reductions per tap):
 //  * every tap -- inside the centre's cell or in a neighbouring one -- first adds what it owes to the lattice points it
 //    SHARES with the centre's cell into the centre's eight register accumulators (a tap one cell over along one axis
